@@ -1,0 +1,203 @@
+/*
+ * maddy_b200.h — C-ABI of the B200-native Langevin/BD step loop of MADDY (klyshko/MT).
+ *
+ * This is the drop-in boundary for ONE path of the reference: the body of
+ *   void compute(Coord* r, Coord* f, Parameters &par, Topology &top, Energies* energies)
+ * (reference src/compute_cuda.cu:1125-1260, declared src/compute_cuda.cuh:17, called once
+ * from src/main.cpp:79) and the kernels it launches.  Plain C: pointers and sizes only,
+ * no CUDA, torch or C++ types.  Every call returns 0 on success or a negative
+ * MADDY_E* code; it never calls exit().  maddy_last_error() gives the message.
+ *
+ * Conventions
+ *  - The caller owns every host array it passes; the library copies what it needs and
+ *    owns all device memory (as compute() owns d_r/d_f/topGPU in the reference,
+ *    src/compute_cuda.cu:989-1081).
+ *  - Coordinates and forces cross the boundary in the reference's AoS "Coord" layout:
+ *    7 floats per monomer {x, y, z, fi, theta, psi, w} (src/mt.h:63-71 — note theta
+ *    BEFORE psi).  On the device the library keeps two float4 SoA arrays.
+ *  - Bond/LJ lists cross the boundary in the reference encoding (signed index, ZERO
+ *    sentinel 999999 for +-0 in dynamic lateral lists; src/compute_cuda.cu:588-592,
+ *    :646-658, src/preparator.cpp:550-554).
+ *  - One handle = one GPU = a contiguous block of trajectories
+ *    [traj_first, traj_first + n_tr_local) of a global ensemble of n_tr trajectories.
+ *    RNG stream ids are the GLOBAL ones (xyz: traj*n_tot + i, angular:
+ *    n_tot*n_tr + traj*n_tot + i; src/compute_cuda.cu:952-953), so a sharded run is
+ *    bit-identical to a single-GPU run of the whole ensemble.
+ *  - Calls on one handle must be serialised by the caller (the reference is
+ *    single-threaded); several handles may coexist (no global state).
+ */
+#ifndef MADDY_B200_H_
+#define MADDY_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MADDY_ABI_VERSION 1
+
+#define MADDY_COORD_STRIDE 7      /* floats per monomer in the AoS boundary layout   */
+#define MADDY_ENERGY_TERMS 7      /* harm,long,lat,psi,fi,teta,lj (updater.cpp:35-36) */
+#define MADDY_ZERO_SENTINEL 999999 /* src/mt.h:35 (ZERO)                              */
+#define MADDY_LJ_CAPACITY 256     /* src/compute_cuda.cu:1076                         */
+#define MADDY_MAX_NTOT 3200       /* one-CTA-per-trajectory path: SMEM staging limit  */
+
+/* status codes */
+#define MADDY_OK 0
+#define MADDY_EINVAL (-1)   /* bad argument / unsupported configuration   */
+#define MADDY_ECUDA (-2)    /* CUDA runtime error (message has the detail) */
+#define MADDY_ENOMEM (-3)
+#define MADDY_EOVERFLOW (-4) /* a neighbour list exceeded its capacity (UB in the reference) */
+#define MADDY_ETEA (-5)     /* TEA "capricious" abort (bdhitea.cu:89-107 would exit(-1)) */
+#define MADDY_ENCCL (-6)
+
+/* flags for maddy_run */
+#define MADDY_RUN_SKIP_FIRST_REBUILD 1u /* caller already rebuilt lists for first_step */
+
+/* list kinds for maddy_download_list / maddy_upload_list */
+#define MADDY_LIST_LONGITUDINAL 0
+#define MADDY_LIST_LATERAL 1
+#define MADDY_LIST_LJ 2
+
+/*
+ * Scalars of the reference's `Parameters` (src/parameters.h:246-318) that the hot path
+ * reads, plus the shard description.  Derived constants (gammaR, varR, ... ;
+ * src/preparator.cpp:209-221) are computed by the host exactly as the reference does and
+ * passed in, so that both sides see the same float values.
+ */
+typedef struct maddy_params {
+    int abi_version;          /* = MADDY_ABI_VERSION */
+    int n_tot;                /* par.Ntot: monomers per trajectory */
+    int n_tr;                 /* par.Ntr: trajectories in the GLOBAL ensemble */
+    int traj_first;           /* first global trajectory held by this handle */
+    int n_tr_local;           /* trajectories held by this handle */
+    int device;               /* par.device (CUDA ordinal) */
+    int rseed;                /* par.rseed */
+
+    float dt, Temp;
+    float gammaR, gammaTheta, varR, varTheta, alpha, freeze_temp;
+
+    float C;                                  /* harmonic (intra-dimer) */
+    float B_psi, B_fi, B_theta;               /* bending */
+    float psi_0, fi_0, theta0_gtp, theta0_gdp;
+    float A_long, D_long, A_lat, D_lat, seam_coeff; /* Morse */
+
+    int barrier;
+    float a_barr_long, r_barr_long, w_barr_long;
+    float a_barr_lat, r_barr_lat, w_barr_lat;   /* w_* already FWHM-converted (preparator.cpp:139,142) */
+
+    int lj_on;
+    float ljscale, ljsigma6, ljpairscutoff;
+    int ljpairsupdatefreq;
+
+    int is_wall;
+    float rep_leftborder, rep_r, rep_eps, rep_h; /* zs[traj] == rep_h for every trajectory (preparator.cpp:176-178) */
+
+    int is_assembly;          /* dynamic bond lists rebuilt by pairs_kernel */
+
+    int tea_on;               /* par.hdi_on */
+    float tea_a;
+    int tea_epsilon_freq;
+    int tea_capricious;
+    float tea_epsmax;
+
+    int max_harmonic;         /* top.maxHarmonicPerMonomer */
+    int max_longitudinal;     /* top.maxLongitudinalPerMonomer (8 in assembly mode)  */
+    int max_lateral;          /* top.maxLateralPerMonomer (16 in assembly mode)      */
+} maddy_params;
+
+/*
+ * Host copy of the reference's `Topology` (src/mt.h:73-92) for the LOCAL trajectories.
+ * bool arrays are passed as unsigned char (sizeof(bool) == 1 in the reference build).
+ */
+typedef struct maddy_topology {
+    const int *harmonic_count;      /* [n_tot]                                  */
+    const int *harmonic;            /* [n_tot * max_harmonic], signed           */
+    const int *longitudinal_count;  /* [n_tr_local * n_tot]                     */
+    const int *longitudinal;        /* [n_tr_local * n_tot * max_longitudinal]  */
+    const int *lateral_count;       /* [n_tr_local * n_tot]                     */
+    const int *lateral;             /* [n_tr_local * n_tot * max_lateral]       */
+    const unsigned char *fixed;     /* [n_tot]                                  */
+    const unsigned char *extra;     /* [n_tr_local * n_tot]                     */
+    const int *mon_type;            /* [n_tot]                                  */
+    const int *gtp;                 /* [n_tr_local * n_tot]                     */
+    const int *on_tubule_cur;       /* [n_tr_local * n_tot]                     */
+} maddy_topology;
+
+typedef struct maddy_handle maddy_handle;
+
+/* ---- lifetime: replaces initIntegration + initRand + initTeaIntegrator
+ *      (compute_cuda.cu:977-1098, HybridTaus.cu:21-31, bdhitea.cu:13-35) and
+ *      deleteTeaIntegrator + deleteIntegration (compute_cuda.cu:1100-1123).
+ * coords_aos7: [n_tr_local * n_tot * 7] floats; angles are wrapped like
+ * compute_cuda.cu:1004-1010 before upload (the caller's array is not modified).
+ * stream: a cudaStream_t to enqueue on, or NULL for a library-owned stream. */
+int maddy_create(const maddy_params *par, const maddy_topology *top, const float *coords_aos7,
+                 void *stream, maddy_handle **out);
+int maddy_destroy(maddy_handle *h);
+/* message of the last failed call on h (h == NULL: last failed maddy_create) */
+const char *maddy_last_error(const maddy_handle *h);
+/* the cudaStream_t all work of this handle is enqueued on */
+void *maddy_stream(const maddy_handle *h);
+int maddy_sync(maddy_handle *h);
+
+/* ---- step-granular entry points (each replaces one launch of the reference loop) */
+int maddy_rebuild_lj(maddy_handle *h);     /* LJ_kernel     launch, compute_cuda.cu:1143 */
+int maddy_rebuild_bonds(maddy_handle *h);  /* pairs_kernel  launch, compute_cuda.cu:1148 */
+int maddy_force(maddy_handle *h);          /* compute_kernel launch, compute_cuda.cu:1228 */
+int maddy_integrate(maddy_handle *h);      /* integrate_kernel launch, compute_cuda.cu:1236 */
+int maddy_tea_update(maddy_handle *h, long long step); /* updateTea, bdhitea.cu:57-118  */
+int maddy_tea_integrate(maddy_handle *h);              /* integrateTea, bdhitea.cu:37-42 */
+
+/* ---- fused execution of steps [first_step, first_step + n_steps): the body of the
+ * for(step) loop of compute() between two host events (compute_cuda.cu:1137-1238 minus
+ * the hydrolysis / stride blocks).  Lists are rebuilt in-kernel at every step with
+ * step % ljpairsupdatefreq == 0 (LJ if lj_on, bonds if is_assembly); pass
+ * MADDY_RUN_SKIP_FIRST_REBUILD when the caller already called maddy_rebuild_* for
+ * first_step (the reference rebuilds BEFORE its host events, compute_cuda.cu:1140-1151).
+ * Observationally identical to n_steps x (rebuild?; force; integrate). Asynchronous. */
+int maddy_run(maddy_handle *h, long long first_step, long long n_steps, unsigned flags);
+
+/* ---- energies: energy_kernel + OutputAllEnergies (compute_cuda.cu:676-911,
+ * updater.cpp:3-43).  out_per_traj: [n_tr_local][7] doubles (harm,long,lat,psi,fi,teta,lj);
+ * out_per_monomer (may be NULL): [n_tr_local*n_tot][7] doubles in the reference's
+ * `Energies` field order (U_harm,U_long,U_lat,U_psi,U_fi,U_teta,U_lj; mt.h:94-102). */
+int maddy_energies(maddy_handle *h, double *out_per_traj, double *out_per_monomer);
+/* device-resident result of the last maddy_energies call: [n_tr_local][7] doubles */
+void *maddy_energies_device(maddy_handle *h);
+
+/* ---- state transfer (compute_cuda.cu:1157,1173,1177,1190,1202-1204) */
+int maddy_download_coords(maddy_handle *h, float *coords_aos7);
+int maddy_download_forces(maddy_handle *h, float *forces_aos7);
+int maddy_upload_coords(maddy_handle *h, const float *coords_aos7); /* no angle wrapping (matches :1204) */
+int maddy_upload_gtp(maddy_handle *h, const int *gtp);
+int maddy_upload_on_tubule(maddy_handle *h, const int *on_tubule_cur);
+int maddy_upload_extra(maddy_handle *h, const unsigned char *extra);
+/* lists in the reference layout [traj][i][capacity] / [traj][i], capacity =
+ * max_longitudinal / max_lateral / MADDY_LJ_CAPACITY */
+int maddy_download_list(maddy_handle *h, int kind, int *counts, int *entries);
+int maddy_upload_list(maddy_handle *h, int kind, const int *counts, const int *entries);
+/* RNG state: [2][n_tr_local*n_tot][4] uint32 (xyz streams then angular streams) */
+int maddy_download_rng(maddy_handle *h, unsigned *state);
+int maddy_upload_rng(maddy_handle *h, const unsigned *state);
+
+/* ---- host-side pieces of the path that need no GPU (usable without a device) */
+/* generateSeeds (HybridTaus.cu:32-48) on a FRESH ran2 state: fills seeds[np*4]. */
+void maddy_generate_seeds(unsigned *seeds, int rseed, long long np);
+/* TEA beta from the per-trajectory epsilon sum (bdhitea.cu:79-113). Returns 0, or
+ * MADDY_ETEA when the reference would exit(-1). */
+int maddy_tea_beta(double epsilon_sum, int n_noextra, int capricious, float tea_a, float epsmax,
+                   float *beta_out, double *epsilon_out);
+
+/* ---- multi-GPU ensemble statistics (new; NCCL over NVLink).  handles[n] live on n
+ * different devices of this process; values[g] points to `count` doubles on the HOST per
+ * handle; on return every values[g] holds the element-wise sum over handles.  The
+ * reduction itself runs on the GPUs with ncclAllReduce. */
+int maddy_ensemble_allreduce(maddy_handle **handles, int n, double **values, int count);
+
+/* number of kernels this handle has launched since creation (bench bookkeeping) */
+long long maddy_launch_count(const maddy_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADDY_B200_H_ */

@@ -1,0 +1,304 @@
+"""Python mirror of the reference's host interface over the C-ABI (thin: ctypes + numpy views).
+
+  HostSystem  = what initParameters()/AssemblyInit() leave in the reference's globals
+                (par, top, r): loaded by the C++ host from config.conf / forcefield / conditions.
+  Engine      = one maddy_handle: the device side of compute() for a block of trajectories.
+
+The names follow the reference (Ntot, Ntr, gtp, extra, on_tubule, harmonic/longitudinal/lateral/LJ).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import MaddyError, MaddyParams, MaddyTopology, HostParams, as_ptr
+
+
+class HostSystem:
+    """Config + topology + coordinates on the host (reference globals `par`, `top`, `r`)."""
+
+    def __init__(self, config_path, overrides: Sequence[str] = (), quiet: bool = True, write_files: bool = False):
+        self._h = C.c_void_p()
+        arr = (C.c_char_p * max(1, len(overrides)))(*[o.encode() for o in overrides])
+        flags = (capi.LOAD_QUIET if quiet else 0) | (0 if write_files else capi.LOAD_NO_FILES)
+        if capi.hostlib.mt_system_load(str(config_path).encode(), len(overrides), arr, flags, C.byref(self._h)):
+            raise MaddyError(1, capi.hostlib.mt_host_last_error().decode())
+        self.par = MaddyParams()
+        self.host = HostParams()
+        self.refresh()
+
+    def refresh(self):
+        capi.hostlib.mt_system_params(self._h, C.byref(self.par), C.byref(self.host))
+        self._top = MaddyTopology()
+        capi.hostlib.mt_system_topology(self._h, C.byref(self._top))
+
+    def close(self):
+        if self._h:
+            capi.hostlib.mt_system_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- sizes
+    @property
+    def Ntot(self) -> int:
+        return self.par.n_tot
+
+    @property
+    def Ntr(self) -> int:
+        return self.par.n_tr
+
+    # ---- live views of the host arrays
+    def _view(self, ptr, shape, dtype):
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.zeros(shape, dtype=dtype)
+        ct = {np.float32: C.c_float, np.int32: C.c_int, np.uint8: C.c_ubyte, np.float64: C.c_double}[dtype]
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).reshape(shape)
+
+    @property
+    def coords(self) -> np.ndarray:
+        """[Ntr, Ntot, 7] float32 in the reference's Coord order x,y,z,fi,theta,psi,w."""
+        return self._view(capi.hostlib.mt_system_coords(self._h), (self.Ntr, self.Ntot, 7), np.float32)
+
+    @property
+    def gtp(self):
+        return self._view(capi.hostlib.mt_system_gtp(self._h), (self.Ntr, self.Ntot), np.int32)
+
+    @property
+    def on_tubule_cur(self):
+        return self._view(capi.hostlib.mt_system_on_tubule(self._h, 0), (self.Ntr, self.Ntot), np.int32)
+
+    @property
+    def on_tubule_prev(self):
+        return self._view(capi.hostlib.mt_system_on_tubule(self._h, 1), (self.Ntr, self.Ntot), np.int32)
+
+    @property
+    def extra(self):
+        return self._view(capi.hostlib.mt_system_extra(self._h), (self.Ntr, self.Ntot), np.uint8)
+
+    @property
+    def fixed(self):
+        return self._view(self._top.fixed, (self.Ntot,), np.uint8)
+
+    @property
+    def mon_type(self):
+        return self._view(self._top.mon_type, (self.Ntot,), np.int32)
+
+    @property
+    def harmonic(self):
+        return self._view(self._top.harmonic, (self.Ntot, self.par.max_harmonic), np.int32)
+
+    @property
+    def harmonic_count(self):
+        return self._view(self._top.harmonic_count, (self.Ntot,), np.int32)
+
+    @property
+    def longitudinal(self):
+        return self._view(self._top.longitudinal, (self.Ntr, self.Ntot, self.par.max_longitudinal), np.int32)
+
+    @property
+    def longitudinal_count(self):
+        return self._view(self._top.longitudinal_count, (self.Ntr, self.Ntot), np.int32)
+
+    @property
+    def lateral(self):
+        return self._view(self._top.lateral, (self.Ntr, self.Ntot, self.par.max_lateral), np.int32)
+
+    @property
+    def lateral_count(self):
+        return self._view(self._top.lateral_count, (self.Ntr, self.Ntot), np.int32)
+
+    @property
+    def energies(self):
+        return self._view(capi.hostlib.mt_system_energies(self._h), (self.Ntr, 7), np.float64)
+
+    def topology(self, traj_first: int = 0) -> MaddyTopology:
+        """maddy_topology for the trajectories starting at traj_first (pointer arithmetic on the live arrays)."""
+        t = MaddyTopology()
+        C.memmove(C.byref(t), C.byref(self._top), C.sizeof(MaddyTopology))
+        o = traj_first * self.Ntot
+
+        def adv(ptr, ctype, off):
+            if not ptr:
+                return ptr
+            return C.cast(C.addressof(ptr.contents) + off * C.sizeof(ctype), C.POINTER(ctype))
+
+        t.longitudinal_count = adv(t.longitudinal_count, C.c_int, o)
+        t.longitudinal = adv(t.longitudinal, C.c_int, o * self.par.max_longitudinal)
+        t.lateral_count = adv(t.lateral_count, C.c_int, o)
+        t.lateral = adv(t.lateral, C.c_int, o * self.par.max_lateral)
+        t.extra = adv(t.extra, C.c_ubyte, o)
+        t.gtp = adv(t.gtp, C.c_int, o)
+        t.on_tubule_cur = adv(t.on_tubule_cur, C.c_int, o)
+        return t
+
+    # ---- the drop-in compute() and host events
+    def compute(self, fused: bool = True, n_gpus: Optional[int] = None, steps: Optional[int] = None):
+        if n_gpus is not None:
+            capi.hostlib.mt_system_set_ngpus(self._h, int(n_gpus))
+        if steps is not None:
+            capi.hostlib.mt_system_set_steps(self._h, int(steps))
+            self.refresh()
+        st = (C.c_double * 4)()
+        if capi.hostlib.mt_system_compute(self._h, int(fused), st):
+            raise MaddyError(1, capi.hostlib.mt_host_last_error().decode())
+        return {"steps": int(st[0]), "launches": int(st[1]), "h2d_bytes": st[2], "d2h_bytes": st[3]}
+
+    def mt_length(self, step: int) -> np.ndarray:
+        out = np.zeros(self.Ntr, dtype=np.int32)
+        if capi.hostlib.mt_system_mt_length(self._h, int(step), as_ptr(out, C.c_int)):
+            raise MaddyError(1, capi.hostlib.mt_host_last_error().decode())
+        return out
+
+    def hydrolyse(self):
+        if capi.hostlib.mt_system_hydrolyse(self._h):
+            raise MaddyError(1, capi.hostlib.mt_host_last_error().decode())
+
+    def change_conc(self, delta, mt_len) -> int:
+        d = np.ascontiguousarray(delta, dtype=np.int32)
+        m = np.ascontiguousarray(mt_len, dtype=np.int32)
+        ch = C.c_int()
+        if capi.hostlib.mt_system_change_conc(self._h, as_ptr(d, C.c_int), as_ptr(m, C.c_int), C.byref(ch)):
+            raise MaddyError(1, capi.hostlib.mt_host_last_error().decode())
+        return ch.value
+
+
+class Engine:
+    """One maddy_handle: device state + kernels for trajectories [traj_first, traj_first + n_tr_local)."""
+
+    def __init__(self, system: HostSystem, traj_first: int = 0, n_tr_local: Optional[int] = None, device: Optional[int] = None,
+                 stream: Optional[int] = None, coords: Optional[np.ndarray] = None, par: Optional[MaddyParams] = None):
+        self.system = system
+        p = (par or system.par).copy()
+        p.traj_first = traj_first
+        p.n_tr_local = system.Ntr - traj_first if n_tr_local is None else n_tr_local
+        if device is not None:
+            p.device = device
+        self.par = p
+        self.N, self.ntr = p.n_tot, p.n_tr_local
+        top = system.topology(traj_first)
+        if coords is None:
+            coords = system.coords[traj_first:traj_first + self.ntr]
+        c = np.ascontiguousarray(coords, dtype=np.float32).reshape(self.ntr, self.N, 7)
+        self._h = C.c_void_p()
+        rc = capi.lib.maddy_create(C.byref(p), C.byref(top), as_ptr(c, C.c_float), C.c_void_p(stream or 0), C.byref(self._h))
+        if rc:
+            raise MaddyError(rc, capi.lib.maddy_last_error(None).decode())
+
+    def _ck(self, rc):
+        if rc:
+            raise MaddyError(rc, capi.lib.maddy_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            capi.lib.maddy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return capi.lib.maddy_stream(self._h) or 0
+
+    @property
+    def launches(self) -> int:
+        return capi.lib.maddy_launch_count(self._h)
+
+    def sync(self):
+        self._ck(capi.lib.maddy_sync(self._h))
+
+    # step-granular (one per reference launch)
+    def rebuild_lj(self):
+        self._ck(capi.lib.maddy_rebuild_lj(self._h))
+
+    def rebuild_bonds(self):
+        self._ck(capi.lib.maddy_rebuild_bonds(self._h))
+
+    def force(self):
+        self._ck(capi.lib.maddy_force(self._h))
+
+    def integrate(self):
+        self._ck(capi.lib.maddy_integrate(self._h))
+
+    def tea_update(self, step: int):
+        self._ck(capi.lib.maddy_tea_update(self._h, int(step)))
+
+    def tea_integrate(self):
+        self._ck(capi.lib.maddy_tea_integrate(self._h))
+
+    def run(self, first_step: int, n_steps: int, skip_first_rebuild: bool = False):
+        self._ck(capi.lib.maddy_run(self._h, int(first_step), int(n_steps),
+                                    capi.RUN_SKIP_FIRST_REBUILD if skip_first_rebuild else 0))
+
+    def energies(self, per_monomer: bool = False):
+        out = np.empty((self.ntr, 7), dtype=np.float64)
+        mono = np.empty((self.ntr, self.N, 7), dtype=np.float64) if per_monomer else None
+        self._ck(capi.lib.maddy_energies(self._h, as_ptr(out, C.c_double), as_ptr(mono, C.c_double) if per_monomer else None))
+        return (out, mono) if per_monomer else out
+
+    @property
+    def energies_device_ptr(self) -> int:
+        return capi.lib.maddy_energies_device(self._h) or 0
+
+    def coords(self) -> np.ndarray:
+        out = np.empty((self.ntr, self.N, 7), dtype=np.float32)
+        self._ck(capi.lib.maddy_download_coords(self._h, as_ptr(out, C.c_float)))
+        return out
+
+    def forces(self) -> np.ndarray:
+        out = np.empty((self.ntr, self.N, 7), dtype=np.float32)
+        self._ck(capi.lib.maddy_download_forces(self._h, as_ptr(out, C.c_float)))
+        return out
+
+    def upload_coords(self, c):
+        c = np.ascontiguousarray(c, dtype=np.float32)
+        self._ck(capi.lib.maddy_upload_coords(self._h, as_ptr(c, C.c_float)))
+
+    def upload_gtp(self, g):
+        g = np.ascontiguousarray(g, dtype=np.int32)
+        self._ck(capi.lib.maddy_upload_gtp(self._h, as_ptr(g, C.c_int)))
+
+    def upload_on_tubule(self, g):
+        g = np.ascontiguousarray(g, dtype=np.int32)
+        self._ck(capi.lib.maddy_upload_on_tubule(self._h, as_ptr(g, C.c_int)))
+
+    def upload_extra(self, e):
+        e = np.ascontiguousarray(e, dtype=np.uint8)
+        self._ck(capi.lib.maddy_upload_extra(self._h, as_ptr(e, C.c_ubyte)))
+
+    def _cap(self, kind):
+        return {capi.LIST_LONGITUDINAL: self.par.max_longitudinal, capi.LIST_LATERAL: self.par.max_lateral,
+                capi.LIST_LJ: capi.LJ_CAPACITY}[kind]
+
+    def download_list(self, kind: int):
+        """(counts [ntr, N], entries [ntr, N, capacity]) in the reference encoding."""
+        cnt = np.zeros((self.ntr, self.N), dtype=np.int32)
+        ent = np.zeros((self.ntr, self.N, self._cap(kind)), dtype=np.int32)
+        self._ck(capi.lib.maddy_download_list(self._h, kind, as_ptr(cnt, C.c_int), as_ptr(ent, C.c_int)))
+        return cnt, ent
+
+    def upload_list(self, kind: int, counts, entries):
+        cnt = np.ascontiguousarray(counts, dtype=np.int32)
+        ent = np.ascontiguousarray(entries, dtype=np.int32)
+        self._ck(capi.lib.maddy_upload_list(self._h, kind, as_ptr(cnt, C.c_int), as_ptr(ent, C.c_int)))
+
+    def rng_state(self) -> np.ndarray:
+        out = np.empty((2, self.ntr * self.N, 4), dtype=np.uint32)
+        self._ck(capi.lib.maddy_download_rng(self._h, as_ptr(out, C.c_uint)))
+        return out
+
+    def upload_rng(self, st):
+        st = np.ascontiguousarray(st, dtype=np.uint32)
+        self._ck(capi.lib.maddy_upload_rng(self._h, as_ptr(st, C.c_uint)))

@@ -1,0 +1,729 @@
+/*
+ * maddy_capi.cu — implementation of the C-ABI declared in include/maddy_b200.h.
+ *
+ * Replaces, for the hot path only, what compute() owns in the reference
+ * (src/compute_cuda.cu:977-1260): device allocation and upload, the launch sequence, the
+ * host<->device transfers around host events, and teardown.  No CPU fallback exists: every
+ * compute entry point launches the sm_100a kernels of maddy_kernels.cu or fails.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "maddy_kernels.cuh"
+
+namespace maddy {
+cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st);
+cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
+} // namespace maddy
+
+using namespace maddy;
+
+struct maddy_handle {
+    maddy_params p;
+    DevSys a;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int mpt = 1, threads = 32, nbuf = 2;
+    size_t smem = 0;
+    CutTest cut_pairs, cut_force;
+    std::string err;
+    long long launches = 0;
+    std::vector<void *> allocs;
+    int *h_status = nullptr; // pinned
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(maddy_handle *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(h, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(h, MADDY_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));         \
+    } while (0)
+
+template <typename T> static int dalloc(maddy_handle *h, T **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n ? n * sizeof(T) : sizeof(T));
+    if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return MADDY_OK;
+}
+
+// smallest double s with float(sqrt(s)) >= c  (sqrt, the double->float conversion and the
+// comparison are all monotone, so bisection over the bit pattern is exact)
+static CutTest make_cut(float c)
+{
+    CutTest t;
+    if (!(c > 0.f)) {
+        t.t = 0.0;
+        t.lo = t.hi = 0.f;
+        return t;
+    }
+    uint64_t lo = 0, hi;
+    double big = 4.0 * (double)c * (double)c;
+    memcpy(&hi, &big, 8);
+    while (hi - lo > 1) { // invariant: pred(lo) true ("inside"), pred(hi) false
+        uint64_t mid = lo + (hi - lo) / 2;
+        double s;
+        memcpy(&s, &mid, 8);
+        if ((float)sqrt(s) < c) lo = mid;
+        else hi = mid;
+    }
+    memcpy(&t.t, &hi, 8);
+    t.lo = (float)(t.t * (1.0 - 1e-6));
+    t.hi = (float)(t.t * (1.0 + 1e-6));
+    return t;
+}
+
+static KArgs kargs(const maddy_handle *h, unsigned ops)
+{
+    KArgs k;
+    k.p = h->p;
+    k.a = h->a;
+    k.first_step = 0;
+    k.n_steps = 0;
+    k.ops = ops;
+    k.run_flags = 0;
+    k.nbuf = h->nbuf;
+    k.cut_pairs = h->cut_pairs;
+    k.cut_force = h->cut_force;
+    return k;
+}
+
+static int check_status(maddy_handle *h)
+{
+    // caller has synchronised the stream
+    int st = *h->h_status;
+    if (st) {
+        *h->h_status = 0;
+        cudaMemsetAsync(h->a.status, 0, sizeof(int), h->stream);
+        return fail(h, MADDY_EOVERFLOW, "neighbour list overflow:%s%s%s (capacities LJ %d, longitudinal %d, lateral %d)",
+                    (st & ST_LJ_OVERFLOW) ? " LJ" : "", (st & ST_LONG_OVERFLOW) ? " longitudinal" : "",
+                    (st & ST_LAT_OVERFLOW) ? " lateral" : "", MADDY_LJ_CAPACITY, h->a.capLong, h->a.capLat);
+    }
+    return MADDY_OK;
+}
+
+static int sync_and_check(maddy_handle *h)
+{
+    CU(h, cudaMemcpyAsync(h->h_status, h->a.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return check_status(h);
+}
+
+static int launch(maddy_handle *h, const KArgs &k)
+{
+    CU(h, cudaSetDevice(h->p.device));
+    cudaError_t e = launch_traj_kernel(k, h->mpt, h->threads, h->smem, h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "trajectory kernel launch (ops=%u): %s", k.ops, cudaGetErrorString(e));
+    h->launches++;
+    return MADDY_OK;
+}
+
+// ---- AoS7 {x,y,z,fi,theta,psi,w}  <->  float4 {x,y,z,0} + {fi,psi,theta,0}
+static void aos_to_soa(const float *aos, size_t n, std::vector<float4> &pos, std::vector<float4> &ang, bool wrap)
+{
+    pos.resize(n);
+    ang.resize(n);
+    for (size_t q = 0; q < n; q++) {
+        const float *c = aos + q * MADDY_COORD_STRIDE;
+        float fi = c[3], theta = c[4], psi = c[5];
+        if (wrap) { // compute_cuda.cu:1004-1010: truncation toward zero, in double
+            fi -= (2 * M_PI) * (int)(fi / (2 * M_PI));
+            psi -= (2 * M_PI) * (int)(psi / (2 * M_PI));
+            theta -= (2 * M_PI) * (int)(theta / (2 * M_PI));
+        }
+        pos[q] = make_float4(c[0], c[1], c[2], 0.f);
+        ang[q] = make_float4(fi, psi, theta, 0.f);
+    }
+}
+static void soa_to_aos(const std::vector<float4> &pos, const std::vector<float4> &ang, float *aos)
+{
+    for (size_t q = 0; q < pos.size(); q++) {
+        float *c = aos + q * MADDY_COORD_STRIDE;
+        c[0] = pos[q].x; c[1] = pos[q].y; c[2] = pos[q].z;
+        c[3] = ang[q].x; c[4] = ang[q].z; c[5] = ang[q].y;
+        c[6] = 0.f;
+    }
+}
+
+extern "C" const char *maddy_last_error(const maddy_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" void *maddy_stream(const maddy_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" long long maddy_launch_count(const maddy_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int maddy_sync(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    return sync_and_check(h);
+}
+
+extern "C" int maddy_destroy(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *q : h->allocs) cudaFree(q);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MADDY_OK;
+}
+
+extern "C" int maddy_upload_list(maddy_handle *h, int kind, const int *counts, const int *entries);
+
+extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, const float *coords, void *stream,
+                            maddy_handle **out)
+{
+    if (!par || !top || !coords || !out) return fail(nullptr, MADDY_EINVAL, "maddy_create: null argument");
+    if (par->abi_version != MADDY_ABI_VERSION)
+        return fail(nullptr, MADDY_EINVAL, "maddy_create: abi_version %d, library has %d", par->abi_version, MADDY_ABI_VERSION);
+    const int N = par->n_tot, ntr = par->n_tr_local;
+    if (N <= 0 || N > MADDY_MAX_NTOT)
+        return fail(nullptr, MADDY_EINVAL, "maddy_create: n_tot=%d outside [1,%d] (one-CTA-per-trajectory path)", N, MADDY_MAX_NTOT);
+    if (ntr <= 0 || par->traj_first < 0 || par->traj_first + ntr > par->n_tr)
+        return fail(nullptr, MADDY_EINVAL, "maddy_create: bad shard [%d,%d) of %d trajectories", par->traj_first,
+                    par->traj_first + ntr, par->n_tr);
+    if (par->max_harmonic < 1 || par->max_longitudinal < 0 || par->max_lateral < 0 || par->max_longitudinal > 255 ||
+        par->max_lateral > 255)
+        return fail(nullptr, MADDY_EINVAL, "maddy_create: bad list capacities (harmonic %d, longitudinal %d, lateral %d)",
+                    par->max_harmonic, par->max_longitudinal, par->max_lateral);
+    if (par->ljpairsupdatefreq <= 0) return fail(nullptr, MADDY_EINVAL, "maddy_create: ljpairsupdatefreq must be > 0");
+    if (par->tea_on && par->tea_epsilon_freq <= 0) return fail(nullptr, MADDY_EINVAL, "maddy_create: tea_epsilon_freq must be > 0");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MADDY_ECUDA, "maddy_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (par->device < 0 || par->device >= ndev) return fail(nullptr, MADDY_EINVAL, "maddy_create: device %d of %d", par->device, ndev);
+
+    maddy_handle *h = new maddy_handle;
+    h->p = *par;
+    int rc = MADDY_OK;
+#define CK(x)                                   \
+    do {                                        \
+        rc = (x);                               \
+        if (rc != MADDY_OK) goto bad;           \
+    } while (0)
+#define CUK(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            rc = fail(h, MADDY_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));                \
+            goto bad;                                                                          \
+        }                                                                                      \
+    } while (0)
+    {
+        CUK(cudaSetDevice(par->device));
+        if (stream) h->stream = (cudaStream_t)stream;
+        else {
+            CUK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+            h->own_stream = true;
+        }
+        CUK(cudaMallocHost(&h->h_status, sizeof(int)));
+        *h->h_status = 0;
+
+        DevSys &a = h->a;
+        memset(&a, 0, sizeof a);
+        a.N = N;
+        a.Npad = (N + 31) & ~31;
+        a.ntr = ntr;
+        a.maxH = par->max_harmonic;
+        a.capLong = par->max_longitudinal;
+        a.capLat = par->max_lateral;
+        const size_t n = (size_t)ntr * N;
+
+        // launch geometry: MPT monomers per thread, <= MD_MAX_THREADS threads, 64 B of stage per monomer
+        h->mpt = (N + MD_MAX_THREADS - 1) / MD_MAX_THREADS;
+        if (h->mpt > MD_MAX_MPT) {
+            rc = fail(h, MADDY_EINVAL, "n_tot=%d needs %d monomers per thread (max %d)", N, h->mpt, MD_MAX_MPT);
+            goto bad;
+        }
+        h->threads = (((N + h->mpt - 1) / h->mpt) + 31) & ~31;
+        h->nbuf = ((size_t)2 * 64 * N <= 100 * 1024) ? 2 : 1;
+        h->smem = (size_t)h->nbuf * 64 * N;
+        h->cut_pairs = make_cut(par->ljpairscutoff);
+        h->cut_force = make_cut(MD_LJ_FORCE_CUTOFF);
+
+        CK(dalloc(h, &a.pos, n));
+        CK(dalloc(h, &a.ang, n));
+        CK(dalloc(h, &a.fpos, n));
+        CK(dalloc(h, &a.fang, n));
+        CK(dalloc(h, &a.rng_xyz, n));
+        CK(dalloc(h, &a.rng_ang, n));
+        CK(dalloc(h, (int **)&a.harm, (size_t)N * a.maxH));
+        CK(dalloc(h, (int **)&a.harm_count, (size_t)N));
+        CK(dalloc(h, (uint8_t **)&a.sflags, (size_t)N));
+        CK(dalloc(h, &a.extra, n));
+        CK(dalloc(h, &a.gtp, n));
+        CK(dalloc(h, &a.ontub, n));
+        CK(dalloc(h, &a.bl, (size_t)ntr * (a.capLong + a.capLat) * a.Npad));
+        CK(dalloc(h, &a.bcnt, (size_t)ntr * 2 * a.Npad));
+        CK(dalloc(h, &a.lj, par->lj_on ? (size_t)ntr * MADDY_LJ_CAPACITY * a.Npad : 1));
+        CK(dalloc(h, &a.ljcnt, (size_t)ntr * a.Npad));
+        CK(dalloc(h, &a.en_mono, n * 7));
+        CK(dalloc(h, &a.en_traj, (size_t)ntr * 7));
+        CK(dalloc(h, &a.status, 1));
+        if (par->tea_on) {
+            CK(dalloc(h, &a.tea_ci, n));
+            CK(dalloc(h, &a.tea_eps, n));
+            CK(dalloc(h, &a.tea_beta, (size_t)ntr));
+        }
+        CUK(cudaMemsetAsync(a.status, 0, sizeof(int), h->stream));
+        CUK(cudaMemsetAsync(a.fpos, 0, n * sizeof(float4), h->stream));
+        CUK(cudaMemsetAsync(a.fang, 0, n * sizeof(float4), h->stream));
+        CUK(cudaMemsetAsync(a.bcnt, 0, (size_t)ntr * 2 * a.Npad, h->stream));
+        CUK(cudaMemsetAsync(a.ljcnt, 0, (size_t)ntr * a.Npad * sizeof(uint16_t), h->stream));
+        CUK(cudaMemsetAsync(a.en_mono, 0, n * 7 * sizeof(double), h->stream));
+
+        // coordinates
+        std::vector<float4> pos, ang;
+        aos_to_soa(coords, n, pos, ang, true);
+        CUK(cudaMemcpyAsync(a.pos, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+        CUK(cudaMemcpyAsync(a.ang, ang.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+
+        // static topology
+        std::vector<uint8_t> sflags(N);
+        for (int i = 0; i < N; i++) sflags[i] = (uint8_t)((top->fixed[i] ? 1 : 0) | ((top->mon_type[i] & 0x7f) << 1));
+        CUK(cudaMemcpyAsync((void *)a.sflags, sflags.data(), N, cudaMemcpyHostToDevice, h->stream));
+        CUK(cudaMemcpyAsync((void *)a.harm, top->harmonic, (size_t)N * a.maxH * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CUK(cudaMemcpyAsync((void *)a.harm_count, top->harmonic_count, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        for (int i = 0; i < N; i++) {
+            for (int kk = 0; kk < top->harmonic_count[i]; kk++) {
+                int j = abs(top->harmonic[(size_t)i * a.maxH + kk]);
+                if (j >= N || top->harmonic_count[i] > a.maxH) {
+                    rc = fail(h, MADDY_EINVAL, "harmonic list of monomer %d is out of range", i);
+                    goto bad;
+                }
+            }
+        }
+        CUK(cudaStreamSynchronize(h->stream));
+
+        // per-trajectory flags
+        CK(maddy_upload_extra(h, top->extra));
+        CK(maddy_upload_gtp(h, top->gtp));
+        CK(maddy_upload_on_tubule(h, top->on_tubule_cur));
+        if (a.capLong > 0 && top->longitudinal) CK(maddy_upload_list(h, MADDY_LIST_LONGITUDINAL, top->longitudinal_count, top->longitudinal));
+        if (a.capLat > 0 && top->lateral) CK(maddy_upload_list(h, MADDY_LIST_LATERAL, top->lateral_count, top->lateral));
+
+        // RNG: the GLOBAL table of 2*Ntot*Ntr states, sliced (HybridTaus.cu:21-31, compute_cuda.cu:1097)
+        {
+            const long long np = 2LL * N * par->n_tr;
+            std::vector<unsigned> seeds((size_t)np * 4);
+            maddy_generate_seeds(seeds.data(), par->rseed, np);
+            const size_t off_xyz = (size_t)par->traj_first * N;
+            const size_t off_ang = (size_t)N * par->n_tr + off_xyz;
+            CUK(cudaMemcpyAsync(a.rng_xyz, seeds.data() + off_xyz * 4, n * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
+            CUK(cudaMemcpyAsync(a.rng_ang, seeds.data() + off_ang * 4, n * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
+            CUK(cudaStreamSynchronize(h->stream));
+        }
+    }
+    *out = h;
+    return MADDY_OK;
+bad:
+    g_create_error = h->err;
+    maddy_destroy(h);
+    return rc;
+#undef CK
+#undef CUK
+}
+
+// ------------------------------------------------------------------ step-granular entry points
+extern "C" int maddy_rebuild_lj(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!h->p.lj_on) return MADDY_OK;
+    return launch(h, kargs(h, OP_REBUILD_LJ));
+}
+extern "C" int maddy_rebuild_bonds(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    return launch(h, kargs(h, OP_REBUILD_BONDS));
+}
+extern "C" int maddy_force(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    return launch(h, kargs(h, OP_FORCE));
+}
+extern "C" int maddy_integrate(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    cudaError_t e = launch_integrate_kernel(kargs(h, 0), h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "integrate kernel launch: %s", cudaGetErrorString(e));
+    h->launches++;
+    return MADDY_OK;
+}
+
+extern "C" int maddy_run(maddy_handle *h, long long first_step, long long n_steps, unsigned flags)
+{
+    if (!h || n_steps < 0) return MADDY_EINVAL;
+    if (n_steps == 0) return MADDY_OK;
+    if (h->p.tea_on) return fail(h, MADDY_EINVAL, "maddy_run: fused TEA loop not available; use the step-granular TEA entry points");
+    KArgs k = kargs(h, OP_RUN);
+    k.first_step = first_step;
+    k.n_steps = n_steps;
+    k.run_flags = flags;
+    return launch(h, k);
+}
+
+extern "C" int maddy_energies(maddy_handle *h, double *out_per_traj, double *out_per_monomer)
+{
+    if (!h) return MADDY_EINVAL;
+    int rc = launch(h, kargs(h, OP_ENERGY));
+    if (rc) return rc;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    if (out_per_traj)
+        CU(h, cudaMemcpyAsync(out_per_traj, h->a.en_traj, (size_t)h->a.ntr * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out_per_monomer)
+        CU(h, cudaMemcpyAsync(out_per_monomer, h->a.en_mono, n * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out_per_traj || out_per_monomer) CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+extern "C" void *maddy_energies_device(maddy_handle *h) { return h ? (void *)h->a.en_traj : nullptr; }
+
+// ------------------------------------------------------------------ state transfer
+extern "C" int maddy_download_coords(maddy_handle *h, float *aos)
+{
+    if (!h || !aos) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    std::vector<float4> pos(n), ang(n);
+    CU(h, cudaMemcpyAsync(pos.data(), h->a.pos, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(ang.data(), h->a.ang, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_and_check(h);
+    if (rc) return rc;
+    soa_to_aos(pos, ang, aos);
+    return MADDY_OK;
+}
+extern "C" int maddy_download_forces(maddy_handle *h, float *aos)
+{
+    if (!h || !aos) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    std::vector<float4> pos(n), ang(n);
+    CU(h, cudaMemcpyAsync(pos.data(), h->a.fpos, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(ang.data(), h->a.fang, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_and_check(h);
+    if (rc) return rc;
+    soa_to_aos(pos, ang, aos);
+    return MADDY_OK;
+}
+extern "C" int maddy_upload_coords(maddy_handle *h, const float *aos)
+{
+    if (!h || !aos) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    std::vector<float4> pos, ang;
+    aos_to_soa(aos, n, pos, ang, false);
+    CU(h, cudaMemcpyAsync(h->a.pos, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->a.ang, ang.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+
+static int upload_bytes(maddy_handle *h, uint8_t *dst, const std::vector<uint8_t> &v)
+{
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaMemcpyAsync(dst, v.data(), v.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+extern "C" int maddy_upload_gtp(maddy_handle *h, const int *gtp)
+{
+    if (!h || !gtp) return MADDY_EINVAL;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    std::vector<uint8_t> v(n);
+    for (size_t q = 0; q < n; q++) v[q] = (uint8_t)(gtp[q] == 1 ? 1 : (gtp[q] == 0 ? 0 : 2)); // kernels test == 1
+    return upload_bytes(h, h->a.gtp, v);
+}
+extern "C" int maddy_upload_on_tubule(maddy_handle *h, const int *on)
+{
+    if (!h || !on) return MADDY_EINVAL;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    std::vector<uint8_t> v(n);
+    for (size_t q = 0; q < n; q++) v[q] = on[q] != 0;
+    return upload_bytes(h, h->a.ontub, v);
+}
+extern "C" int maddy_upload_extra(maddy_handle *h, const unsigned char *extra)
+{
+    if (!h || !extra) return MADDY_EINVAL;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    std::vector<uint8_t> v(n);
+    for (size_t q = 0; q < n; q++) v[q] = extra[q] != 0;
+    return upload_bytes(h, h->a.extra, v);
+}
+
+// native bond code (j<<1 | neg) <-> reference encodings
+static inline int long_to_ref(unsigned code)
+{
+    int j = (int)(code >> 1);
+    return (code & 1u) ? -j : j;
+}
+static inline int lat_to_ref(unsigned code)
+{
+    int j = (int)(code >> 1);
+    if (code & 1u) return j ? -j : -MADDY_ZERO_SENTINEL;
+    return j ? j : MADDY_ZERO_SENTINEL;
+}
+
+extern "C" int maddy_download_list(maddy_handle *h, int kind, int *counts, int *entries)
+{
+    if (!h || !counts || !entries) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    const DevSys &a = h->a;
+    const int N = a.N, Npad = a.Npad, ntr = a.ntr;
+    if (kind == MADDY_LIST_LJ) {
+        if (!h->p.lj_on) return fail(h, MADDY_EINVAL, "LJ list requested but LJ_on is off");
+        std::vector<uint16_t> lj((size_t)ntr * MADDY_LJ_CAPACITY * Npad), cnt((size_t)ntr * Npad);
+        CU(h, cudaMemcpyAsync(lj.data(), a.lj, lj.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(cnt.data(), a.ljcnt, cnt.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+        int rc = sync_and_check(h);
+        if (rc) return rc;
+        for (int t = 0; t < ntr; t++)
+            for (int i = 0; i < N; i++) {
+                const int c = cnt[(size_t)t * Npad + i];
+                counts[(size_t)t * N + i] = c;
+                int *o = entries + ((size_t)t * N + i) * MADDY_LJ_CAPACITY;
+                for (int k = 0; k < MADDY_LJ_CAPACITY; k++)
+                    o[k] = k < c ? lj[((size_t)t * MADDY_LJ_CAPACITY + k) * Npad + i] : 0;
+            }
+        return MADDY_OK;
+    }
+    if (kind != MADDY_LIST_LONGITUDINAL && kind != MADDY_LIST_LATERAL) return fail(h, MADDY_EINVAL, "unknown list kind %d", kind);
+    const int rows = a.capLong + a.capLat;
+    std::vector<uint16_t> bl((size_t)ntr * rows * Npad);
+    std::vector<uint8_t> bc((size_t)ntr * 2 * Npad);
+    CU(h, cudaMemcpyAsync(bl.data(), a.bl, bl.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(bc.data(), a.bcnt, bc.size(), cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_and_check(h);
+    if (rc) return rc;
+    const bool lat = kind == MADDY_LIST_LATERAL;
+    const int cap = lat ? a.capLat : a.capLong, row0 = lat ? a.capLong : 0;
+    for (int t = 0; t < ntr; t++)
+        for (int i = 0; i < N; i++) {
+            const int c = bc[((size_t)t * 2 + (lat ? 1 : 0)) * Npad + i];
+            counts[(size_t)t * N + i] = c;
+            int *o = entries + ((size_t)t * N + i) * cap;
+            for (int k = 0; k < cap; k++) {
+                if (k >= c) {
+                    o[k] = 0;
+                    continue;
+                }
+                const unsigned code = bl[((size_t)t * rows + row0 + k) * Npad + i];
+                o[k] = lat ? lat_to_ref(code) : long_to_ref(code);
+            }
+        }
+    return MADDY_OK;
+}
+
+extern "C" int maddy_upload_list(maddy_handle *h, int kind, const int *counts, const int *entries)
+{
+    if (!h || !counts || !entries) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    const DevSys &a = h->a;
+    const int N = a.N, Npad = a.Npad, ntr = a.ntr;
+    if (kind == MADDY_LIST_LJ) {
+        if (!h->p.lj_on) return fail(h, MADDY_EINVAL, "LJ list upload but LJ_on is off");
+        std::vector<uint16_t> lj((size_t)ntr * MADDY_LJ_CAPACITY * Npad, 0), cnt((size_t)ntr * Npad, 0);
+        for (int t = 0; t < ntr; t++)
+            for (int i = 0; i < N; i++) {
+                const int c = counts[(size_t)t * N + i];
+                if (c < 0 || c > MADDY_LJ_CAPACITY) return fail(h, MADDY_EINVAL, "LJ count %d out of range", c);
+                cnt[(size_t)t * Npad + i] = (uint16_t)c;
+                for (int k = 0; k < c; k++) {
+                    const int j = entries[((size_t)t * N + i) * MADDY_LJ_CAPACITY + k];
+                    if (j < 0 || j >= N) return fail(h, MADDY_EINVAL, "LJ entry %d out of range", j);
+                    lj[((size_t)t * MADDY_LJ_CAPACITY + k) * Npad + i] = (uint16_t)j;
+                }
+            }
+        CU(h, cudaMemcpyAsync(a.lj, lj.data(), lj.size() * 2, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(a.ljcnt, cnt.data(), cnt.size() * 2, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        return MADDY_OK;
+    }
+    if (kind != MADDY_LIST_LONGITUDINAL && kind != MADDY_LIST_LATERAL) return fail(h, MADDY_EINVAL, "unknown list kind %d", kind);
+    const bool lat = kind == MADDY_LIST_LATERAL;
+    const int rows = a.capLong + a.capLat, cap = lat ? a.capLat : a.capLong, row0 = lat ? a.capLong : 0;
+    // read-modify-write of the interleaved bond table
+    std::vector<uint16_t> bl((size_t)ntr * rows * Npad);
+    std::vector<uint8_t> bc((size_t)ntr * 2 * Npad);
+    CU(h, cudaMemcpyAsync(bl.data(), a.bl, bl.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(bc.data(), a.bcnt, bc.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int t = 0; t < ntr; t++)
+        for (int i = 0; i < N; i++) {
+            const int c = counts[(size_t)t * N + i];
+            if (c < 0 || c > cap) return fail(h, MADDY_EINVAL, "bond count %d exceeds capacity %d", c, cap);
+            bc[((size_t)t * 2 + (lat ? 1 : 0)) * Npad + i] = (uint8_t)c;
+            for (int k = 0; k < c; k++) {
+                int v = entries[((size_t)t * N + i) * cap + k];
+                unsigned neg;
+                int j;
+                if (lat) { // compute_cuda.cu:307-324: `j <= 0` selects the swapped site set, ZERO stands for 0
+                    neg = v <= 0;
+                    j = abs(v);
+                    if (j == MADDY_ZERO_SENTINEL) j = 0;
+                } else { // compute_cuda.cu:191-197
+                    neg = v < 0;
+                    j = abs(v);
+                }
+                if (j >= N) return fail(h, MADDY_EINVAL, "bond entry %d out of range", v);
+                bl[((size_t)t * rows + row0 + k) * Npad + i] = (uint16_t)((j << 1) | neg);
+            }
+        }
+    CU(h, cudaMemcpyAsync(a.bl, bl.data(), bl.size() * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(a.bcnt, bc.data(), bc.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+
+extern "C" int maddy_download_rng(maddy_handle *h, unsigned *state)
+{
+    if (!h || !state) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    CU(h, cudaMemcpyAsync(state, h->a.rng_xyz, n * 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(state + n * 4, h->a.rng_ang, n * 16, cudaMemcpyDeviceToHost, h->stream));
+    return sync_and_check(h);
+}
+extern "C" int maddy_upload_rng(maddy_handle *h, const unsigned *state)
+{
+    if (!h || !state) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    CU(h, cudaMemcpyAsync(h->a.rng_xyz, state, n * 16, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->a.rng_ang, state + n * 4, n * 16, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+
+// ------------------------------------------------------------------ TEA (step-granular)
+extern "C" int maddy_tea_update(maddy_handle *h, long long step)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!h->p.tea_on) return fail(h, MADDY_EINVAL, "maddy_tea_update: tea_on is off");
+    if (step % h->p.tea_epsilon_freq != 0) return MADDY_OK;
+    CU(h, cudaSetDevice(h->p.device));
+    cudaError_t e = launch_tea_kernels(kargs(h, OP_TEA_EPS), 0, step, h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "TEA epsilon kernel: %s", cudaGetErrorString(e));
+    h->launches++;
+    // the reference aborts the process on capricious violations (bdhitea.cu:89-107): surface them here
+    CU(h, cudaMemcpyAsync(h->h_status, h->a.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (*h->h_status & 0x100) {
+        *h->h_status = 0;
+        cudaMemsetAsync(h->a.status, 0, sizeof(int), h->stream);
+        return fail(h, MADDY_ETEA, "TEA: hydrodynamic tensor outside the capricious bounds at step %lld", step);
+    }
+    return check_status(h);
+}
+extern "C" int maddy_tea_integrate(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!h->p.tea_on) return fail(h, MADDY_EINVAL, "maddy_tea_integrate: tea_on is off");
+    CU(h, cudaSetDevice(h->p.device));
+    cudaError_t e = launch_tea_kernels(kargs(h, 0), 1, 0, h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "TEA integrate kernel: %s", cudaGetErrorString(e));
+    h->launches++;
+    return MADDY_OK;
+}
+
+// ------------------------------------------------------------------ NCCL ensemble reduction
+// NCCL is loaded lazily so that the library has no link-time dependency on a particular libnccl
+// (a Python process may already carry torch's copy).
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct Nccl {
+    void *lib = nullptr;
+    int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+    }
+};
+Nccl g_nccl;
+std::vector<ncclComm_t> g_comms;
+std::vector<int> g_comm_devs;
+} // namespace
+
+extern "C" int maddy_ensemble_allreduce(maddy_handle **hs, int n, double **values, int count)
+{
+    if (!hs || n <= 0 || !values || count <= 0) return MADDY_EINVAL;
+    maddy_handle *h0 = hs[0];
+    if (n == 1) return MADDY_OK;
+    if (!g_nccl.load()) return fail(h0, MADDY_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+    std::vector<int> devs(n);
+    for (int g = 0; g < n; g++) devs[g] = hs[g]->p.device;
+    if (g_comm_devs != devs) {
+        for (ncclComm_t c : g_comms) g_nccl.CommDestroy(c);
+        g_comms.assign(n, nullptr);
+        int r = g_nccl.CommInitAll(g_comms.data(), n, devs.data());
+        if (r != 0) {
+            g_comms.clear();
+            g_comm_devs.clear();
+            return fail(h0, MADDY_ENCCL, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        }
+        g_comm_devs = devs;
+    }
+    std::vector<double *> dbuf(n, nullptr);
+    for (int g = 0; g < n; g++) {
+        CU(hs[g], cudaSetDevice(devs[g]));
+        CU(hs[g], cudaMalloc(&dbuf[g], count * sizeof(double)));
+        CU(hs[g], cudaMemcpyAsync(dbuf[g], values[g], count * sizeof(double), cudaMemcpyHostToDevice, hs[g]->stream));
+    }
+    g_nccl.GroupStart();
+    int rr = 0;
+    for (int g = 0; g < n; g++) {
+        cudaSetDevice(devs[g]);
+        int r = g_nccl.AllReduce(dbuf[g], dbuf[g], (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_comms[g], hs[g]->stream);
+        if (r) rr = r;
+    }
+    int r2 = g_nccl.GroupEnd();
+    if (rr || r2) return fail(h0, MADDY_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rr ? rr : r2) : "error");
+    for (int g = 0; g < n; g++) {
+        CU(hs[g], cudaSetDevice(devs[g]));
+        CU(hs[g], cudaMemcpyAsync(values[g], dbuf[g], count * sizeof(double), cudaMemcpyDeviceToHost, hs[g]->stream));
+        CU(hs[g], cudaStreamSynchronize(hs[g]->stream));
+        cudaFree(dbuf[g]);
+    }
+    return MADDY_OK;
+}

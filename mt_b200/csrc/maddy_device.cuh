@@ -1,0 +1,206 @@
+/*
+ * maddy_device.cuh — device-side physics of the MADDY Langevin/BD step, written for sm_100a.
+ *
+ * Everything here is a from-scratch formulation of WHAT the reference kernels compute
+ * (src/compute_cuda.cu, src/HybridTaus.cu), organised around one idea the reference does
+ * not use: every monomer's orientation frame (e1,e2,e3 = columns of Rz(psi)Ry(theta)Rx(fi))
+ * is evaluated ONCE per step by its owning thread and the three site-offset vectors every
+ * neighbour needs (r_mon*e3, R*p1, R*p2) are staged in shared memory, so a bonded
+ * neighbour costs three LDS.128 instead of six MUFU + ~60 FMAs.
+ *
+ * Arithmetic contract: float state; MUFU sin/cos/ex2/lg2 exactly where the
+ * reference's -use_fast_math build uses them; the squared site distance is summed in fp64
+ * from float components and rounded to float before the (approximate) sqrt, as the
+ * reference's `sqrtf(pow(..,2)+pow(..,2)+pow(..,2))` does; cut-off decisions on the LJ
+ * lists are taken on the exact fp64 sum against a precomputed fp64 threshold that is
+ * equivalent to the reference's `float(sqrt(double)) < cutoff` test.
+ *
+ * This translation unit is compiled with -use_fast_math so that sinf/cosf/expf/logf/sqrtf
+ * and `/` lower to the same MUFU sequences as in the reference build.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "maddy_b200.h"
+
+namespace maddy {
+
+// geometry constants of the model (reference src/mt.h:23-50)
+#define MD_R_MT 8.12f
+#define MD_R_MON 2.0f
+#define MD_ANGLE_CUTOFF 1.0f
+#define MD_PAIR_CUTOFF 2.5f
+#define MD_LJ_FORCE_CUTOFF 6.0f
+// centre-distance prefilter for bond candidates: every interaction site lies within
+// r_mon (=|p1|=|p2| up to rounding) of its monomer centre, so a site distance < 2.5
+// needs a centre distance < 2.5 + 2*2.0; 6.6^2 leaves a 0.1 nm margin.
+#define MD_BOND_PREFILTER2 43.56f
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 mk3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ float dot3(const F3 &a, const F3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// generalized force / coordinate of one monomer: x,y,z,fi,psi,theta
+struct G6 { float x, y, z, fi, psi, theta; };
+
+// lateral site local coordinates.  The reference evaluates these float expressions on the
+// device at run time under fast-math (MUFU sin/cos of 2*pi/13, see its PTX), so we do the
+// same: p1 = (xp, yp, zp), p2 = (xp, -yp, -zp)   (src/mt.h:44-50)
+struct LatSite { float xp, yp, zp; };
+__device__ __forceinline__ LatSite lateral_site()
+{
+    LatSite s;
+    const float a = (float)(2.0f * M_PI / 13.0f);
+    s.xp = 0.5f * MD_R_MT * (cosf(a) - 1.0f);
+    s.yp = 0.5f * MD_R_MT * sinf(a);
+    s.zp = -3.0f * MD_R_MON / 13.0f;
+    return s;
+}
+
+// Orientation frame of one monomer.
+struct Frame {
+    float sf, cf, sp, cp, st, ct;
+    F3 e1, e2, e3; // columns of R = Rz(psi) Ry(theta) Rx(fi)
+    F3 g;          // -d(e1)/d(theta)
+};
+
+__device__ __forceinline__ Frame make_frame(float fi, float psi, float theta)
+{
+    Frame f;
+    f.sf = sinf(fi);    f.cf = cosf(fi);
+    f.sp = sinf(psi);   f.cp = cosf(psi);
+    f.st = sinf(theta); f.ct = cosf(theta);
+    f.e1 = mk3(f.cp * f.ct, f.sp * f.ct, -f.st);
+    f.e2 = mk3(f.cp * f.sf * f.st - f.cf * f.sp, f.cf * f.cp + f.sf * f.sp * f.st, f.ct * f.sf);
+    f.e3 = mk3(f.sf * f.sp + f.cf * f.cp * f.st, -f.cp * f.sf + f.cf * f.sp * f.st, f.cf * f.ct);
+    f.g = mk3(f.cp * f.st, f.sp * f.st, f.ct);
+    return f;
+}
+
+// Site offsets staged for neighbours: a = r_mon*e3 ("end" sites are +-a), l1 = R*p1, l2 = R*p2
+__device__ __forceinline__ void site_offsets(const Frame &f, const LatSite &ls, F3 &a, F3 &l1, F3 &l2)
+{
+    a = mk3(MD_R_MON * f.e3.x, MD_R_MON * f.e3.y, MD_R_MON * f.e3.z);
+    // u = xp*e1, v = yp*e2 + zp*e3 ; l1 = u + v, l2 = u - v
+    F3 u = mk3(ls.xp * f.e1.x, ls.xp * f.e1.y, ls.xp * f.e1.z);
+    F3 v = mk3(ls.yp * f.e2.x + ls.zp * f.e3.x, ls.yp * f.e2.y + ls.zp * f.e3.y, ls.yp * f.e2.z + ls.zp * f.e3.z);
+    l1 = mk3(u.x + v.x, u.y + v.y, u.z + v.z);
+    l2 = mk3(u.x - v.x, u.y - v.y, u.z - v.z);
+}
+
+// |d| as the reference forms it: fp64 sum of squares (order z,x,y), rounded to float,
+// approximate float sqrt.  (compute_cuda.cu:89-96, :208-215, :337-350)
+__device__ __forceinline__ float site_distance(const F3 &d)
+{
+    double s = (double)d.z * (double)d.z;
+    s += (double)d.x * (double)d.x;
+    s += (double)d.y * (double)d.y;
+    return sqrtf((float)s);
+}
+// variant used by energy_kernel: fp64 sqrt, then rounded to float (compute_cuda.cu:731,:791,:858)
+__device__ __forceinline__ float site_distance_d(const F3 &d)
+{
+    double s = (double)d.z * (double)d.z;
+    s += (double)d.x * (double)d.x;
+    s += (double)d.y * (double)d.y;
+    return (float)sqrt(s);
+}
+
+// potentials (compute_cuda.cu:16-30)
+__device__ __forceinline__ float dmorse(float D, float a, float x)
+{
+    float e = expf(-a * x);
+    return 2 * a * D * (1 - e) * e;
+}
+__device__ __forceinline__ float morse_en(float D, float a, float x)
+{
+    float e = expf(-a * x);
+    return D * (1 - e) * (1 - e) - D;
+}
+__device__ __forceinline__ float dbarr(float a, float r, float w, float x)
+{
+    return -a * expf(-(x - r) * (x - r) / (2 * w * w)) * (x - r) / (w * w);
+}
+__device__ __forceinline__ float barr(float a, float r, float w, float x)
+{
+    return a * expf(-(x - r) * (x - r) / (2 * w * w));
+}
+
+// Accumulate the generalized force of one bond on monomer i.
+//   d   = site_j - site_i
+//   k   = -U'(dr)/dr * (-1) ... i.e. F_xyz += k*d,  F_q += k * d . d(site_i)/dq
+//   o   = own site offset R_i*p,  (xp,yp,zp) = p (own local site)
+// d(Rp)/dfi = yp*e3 - zp*e2 ; d(Rp)/dpsi = (-o.y, o.x, 0) ; d(Rp)/dtheta = -xp*g + (yp*sf+zp*cf)*e1
+__device__ __forceinline__ void bond_accumulate(G6 &f, float k, const F3 &d, const F3 &o, float xp, float yp, float zp,
+                                                const Frame &fr)
+{
+    f.x += k * d.x;
+    f.y += k * d.y;
+    f.z += k * d.z;
+    F3 dfi = mk3(yp * fr.e3.x - zp * fr.e2.x, yp * fr.e3.y - zp * fr.e2.y, yp * fr.e3.z - zp * fr.e2.z);
+    float c = yp * fr.sf + zp * fr.cf;
+    F3 dth = mk3(c * fr.e1.x - xp * fr.g.x, c * fr.e1.y - xp * fr.g.y, c * fr.e1.z - xp * fr.g.z);
+    f.fi += k * dot3(d, dfi);
+    f.psi += k * (d.y * o.x - d.x * o.y);
+    f.theta += k * dot3(d, dth);
+}
+
+// ---------------------------------------------------------------- HybridTaus RNG
+// Integer stream of GPU Gems 3 ch.37 as used by the reference (HybridTaus.cu:63-76):
+// three Tausworthe steps and one LCG step XOR-ed; state = uint4.
+__device__ __forceinline__ unsigned taus_step(unsigned &z, int s1, int s2, int s3, unsigned m)
+{
+    unsigned b = (((z << s1) ^ z) >> s2);
+    return z = (((z & m) << s3) ^ b);
+}
+__device__ __forceinline__ unsigned hybrid_taus(uint4 &s)
+{
+    unsigned r = taus_step(s.x, 13, 19, 12, 4294967294u);
+    r ^= taus_step(s.y, 2, 25, 4, 4294967288u);
+    r ^= taus_step(s.z, 3, 11, 17, 4294967280u);
+    s.w = 1664525u * s.w + 1013904223u;
+    return r ^ s.w;
+}
+// low 23 bits as the mantissa of a float in [1,2), minus 1; 0 -> 1e-8 (HybridTaus.cu:53-61)
+__device__ __forceinline__ float uint_to_unit_float(unsigned u)
+{
+    float r = __uint_as_float(0x3f800000u | (0x007fffffu & u)) - 1.0f;
+    return r == 0 ? 1.0e-8f : r;
+}
+// Two Box-Muller pairs from four draws; .w is produced and discarded by the callers, as in
+// the reference (HybridTaus.cu:85-98): r = sqrtf(-2 logf(u1)), angle = float(2*pi (double) * u2).
+__device__ __forceinline__ float4 rforce(uint4 &s)
+{
+    float4 n;
+    float r = sqrtf(-2.0f * logf(uint_to_unit_float(hybrid_taus(s))));
+    float t = 2.0f * M_PI * uint_to_unit_float(hybrid_taus(s));
+    n.x = r * __sinf(t);
+    n.y = r * __cosf(t);
+    r = sqrtf(-2.0f * logf(uint_to_unit_float(hybrid_taus(s))));
+    t = 2.0f * M_PI * uint_to_unit_float(hybrid_taus(s));
+    n.z = r * __sinf(t);
+    n.w = r * __cosf(t);
+    return n;
+}
+
+// exact fp64 squared distance of float differences (order x,y,z as LJ_kernel, compute_cuda.cu:929-931)
+__device__ __forceinline__ double dist2_exact(float dx, float dy, float dz)
+{
+    double s = (double)dx * (double)dx;
+    s += (double)dy * (double)dy;
+    s += (double)dz * (double)dz;
+    return s;
+}
+
+// Cut-off test equivalent to `float(sqrt(double s)) < c`: thr.t is the smallest double s for which
+// the reference's test fails; lo/hi bracket it in float so fp64 is only touched inside the band.
+struct CutTest { double t; float lo, hi; };
+__device__ __forceinline__ bool inside_cut(const CutTest &c, float dx, float dy, float dz, float sf)
+{
+    if (sf < c.lo) return true;
+    if (sf > c.hi) return false;
+    return dist2_exact(dx, dy, dz) < c.t;
+}
+
+} // namespace maddy

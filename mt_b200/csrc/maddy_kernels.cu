@@ -1,0 +1,663 @@
+/*
+ * maddy_kernels.cu — sm_100a kernels of the MADDY Langevin/BD step loop.
+ *
+ * Execution model (B200-first, not the reference's one-thread-per-(traj,monomer) 32-thread
+ * blocks with every neighbour gathered from global memory):
+ *
+ *   one CTA = one trajectory.  Each thread owns MPT monomers whose state (6 coordinates +
+ *   two HybridTaus streams) lives in REGISTERS for the whole launch.  At the top of every
+ *   step each thread publishes, for its monomers, {position, angles, the three site-offset
+ *   vectors r_mon*e3, R*p1, R*p2, flags} into a shared-memory stage (4 x float4 = 64 B per
+ *   monomer, double-buffered => ONE __syncthreads per step).  Forces, the list rebuilds and
+ *   the energies read neighbours from that stage only; HBM is touched for the neighbour
+ *   lists (uint16, k-major => coalesced) and, at launch start/end, for the state.
+ *
+ *   OP_RUN iterates the steps between two host events inside the kernel
+ *   (replaces >= 2 launches + 2 cudaDeviceSynchronize per step, compute_cuda.cu:1228-1238).
+ *   The step-granular entry points run the same device functions for a single phase, so
+ *   fused and unfused execution are bit-identical.
+ *
+ * Reference semantics restated here (file:line in /root/reference/src):
+ *   forces      compute_cuda.cu:32-525     lists   :527-674 (bonds), :913-940 (LJ)
+ *   energies    compute_cuda.cu:676-911    integrator :943-975, HybridTaus.cu:53-98
+ */
+#include "maddy_kernels.cuh"
+
+namespace maddy {
+
+#define KB_BOLTZ 0.0019872041f // kcal/(mol*K), mt.h:39
+
+struct Stage {
+    float4 *P;  // x, y, z, fi
+    float4 *E;  // r_mon*e3, psi
+    float4 *L1; // R*p1, theta
+    float4 *L2; // R*p2, flag bits (mon_type | gtp<<8 | ontub<<9 | extra<<10)
+};
+
+__device__ __forceinline__ Stage stage_at(float4 *smem, int N, int buf)
+{
+    Stage s;
+    float4 *b = smem + (size_t)buf * 4 * N;
+    s.P = b;
+    s.E = b + N;
+    s.L1 = b + 2 * N;
+    s.L2 = b + 3 * N;
+    return s;
+}
+
+struct Mono { // register-resident state of one monomer
+    float x, y, z, fi, psi, theta;
+    uint4 rx, ra;
+    int flags; // bit0 fixed, bits1-7 type, bit8 gtp, bit9 ontub, bit10 extra
+};
+#define MF_FIXED 1
+#define MF_TYPE(f) (((f) >> 1) & 0x7f)
+#define MF_GTP 0x100
+#define MF_ONTUB 0x200
+#define MF_EXTRA 0x400
+
+__device__ __forceinline__ void publish(const Stage &s, int i, const Mono &m, const LatSite &ls)
+{
+    Frame fr = make_frame(m.fi, m.psi, m.theta);
+    F3 a, l1, l2;
+    site_offsets(fr, ls, a, l1, l2);
+    s.P[i] = make_float4(m.x, m.y, m.z, m.fi);
+    s.E[i] = make_float4(a.x, a.y, a.z, m.psi);
+    s.L1[i] = make_float4(l1.x, l1.y, l1.z, m.theta);
+    int jf = MF_TYPE(m.flags) | (m.flags & (MF_GTP | MF_ONTUB | MF_EXTRA));
+    s.L2[i] = make_float4(l2.x, l2.y, l2.z, __int_as_float(jf));
+}
+
+// ------------------------------------------------------------------ forces
+// Generalized force on monomer i (non-extra) from the staged trajectory.
+__device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, int traj, int i, const Mono &m,
+                                            const LatSite &ls)
+{
+    const maddy_params &p = k.p;
+    const DevSys &a = k.a;
+    G6 f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const Frame fr = make_frame(m.fi, m.psi, m.theta);
+    const float4 Ei = s.E[i];
+    const float xi = m.x, yi = m.y, zi = m.z;
+    const bool gtp_i = (m.flags & MF_GTP) != 0;
+    const bool ontub_i = (m.flags & MF_ONTUB) != 0;
+
+    // ---- harmonic intra-dimer bond + bending (compute_cuda.cu:70-182)
+    const int nh = a.harm_count[i];
+    for (int kk = 0; kk < nh; kk++) {
+        int raw = a.harm[a.maxH * i + kk];
+        const float sg = raw < 0 ? 1.0f : -1.0f; // R_MON / r_mon
+        const int j = raw < 0 ? -raw : raw;
+        const float4 Pj = s.P[j], Ej = s.E[j];
+        F3 d;
+        d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
+        d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
+        d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+        const float dr = site_distance(d);
+        bond_accumulate(f, p.C, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), 0.f, 0.f, sg * MD_R_MON, fr);
+        if (dr < MD_ANGLE_CUTOFF) {
+            const float psiji = Ej.w - m.psi;
+            const float fiji = Pj.w - m.fi;
+            const float thetaji = s.L1[j].w - m.theta;
+            const float th0 = gtp_i ? p.theta0_gtp : p.theta0_gdp;
+            if (sg > 0) {
+                f.psi += p.B_psi * sinf(psiji - p.psi_0);
+                f.fi += p.B_fi * sinf(fiji - p.fi_0);
+                f.theta += p.B_theta * sinf(thetaji - th0);
+            } else {
+                f.psi -= p.B_psi * sinf(-psiji - p.psi_0);
+                f.fi -= p.B_fi * sinf(-fiji - p.fi_0);
+                f.theta -= p.B_theta * sinf(-thetaji - th0);
+            }
+        }
+    }
+
+    const uint16_t *bl = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
+    const uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
+
+    // ---- longitudinal Morse (+ barrier) + bending (compute_cuda.cu:189-299)
+    const int nlong = bc[0];
+    for (int kk = 0; kk < nlong; kk++) {
+        const unsigned code = bl[(size_t)kk * a.Npad];
+        const int j = code >> 1;
+        const float sg = (code & 1u) ? 1.0f : -1.0f;
+        const float4 Pj = s.P[j], Ej = s.E[j];
+        const float4 L2j = s.L2[j];
+        const int jf = __float_as_int(L2j.w);
+        F3 d;
+        d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
+        d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
+        d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+        const float dr = site_distance(d);
+        float dUdr;
+        if (dr == 0) dUdr = 0.0f;
+        else dUdr = dmorse(p.D_long, p.A_long, dr) / dr;
+        if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) {
+            if (dr != 0.0f) dUdr += dbarr(p.a_barr_long, p.r_barr_long, p.w_barr_long, dr) / dr;
+        }
+        bond_accumulate(f, dUdr, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), 0.f, 0.f, sg * MD_R_MON, fr);
+        if (dr < MD_ANGLE_CUTOFF) {
+            const float psiji = Ej.w - m.psi;
+            const float fiji = Pj.w - m.fi;
+            const float thetaji = s.L1[j].w - m.theta;
+            // the dimer closer to the plus end rules theta0 (compute_cuda.cu:282-283)
+            const bool gtp_last = (zi > Pj.z) ? gtp_i : ((jf & MF_GTP) != 0);
+            const float th0 = gtp_last ? p.theta0_gtp : p.theta0_gdp;
+            if (sg > 0) {
+                f.psi += p.B_psi * sinf(psiji - p.psi_0);
+                f.fi += p.B_fi * sinf(fiji - p.fi_0);
+                f.theta += p.B_theta * sinf(thetaji - th0);
+            } else {
+                f.psi -= p.B_psi * sinf(-psiji - p.psi_0);
+                f.fi -= p.B_fi * sinf(-fiji - p.fi_0);
+                f.theta -= p.B_theta * sinf(-thetaji - th0);
+            }
+        }
+    }
+
+    // ---- lateral Morse (+ barrier), seam scaling (compute_cuda.cu:304-466)
+    const int nlat = bc[a.Npad];
+    if (nlat > 0) {
+        const float4 L1i = s.L1[i], L2i = s.L2[i];
+        const int type_i = MF_TYPE(m.flags);
+        for (int kk = 0; kk < nlat; kk++) {
+            const unsigned code = bl[(size_t)(a.capLong + kk) * a.Npad];
+            const int j = code >> 1;
+            const bool neg = (code & 1u) != 0;
+            // negative entry: i interacts through p1, j through p2; positive: i through p2, j through p1
+            const float4 Pj = s.P[j];
+            const float4 L1j = s.L1[j], L2j = s.L2[j];
+            const int jf = __float_as_int(L2j.w);
+            const F3 oi = neg ? mk3(L1i.x, L1i.y, L1i.z) : mk3(L2i.x, L2i.y, L2i.z);
+            const F3 oj = neg ? mk3(L2j.x, L2j.y, L2j.z) : mk3(L1j.x, L1j.y, L1j.z);
+            F3 d;
+            d.x = (Pj.x - xi) - oi.x + oj.x;
+            d.y = (Pj.y - yi) - oi.y + oj.y;
+            d.z = (Pj.z - zi) - oi.z + oj.z;
+            const float dr = site_distance(d);
+            float dUdr;
+            if (dr == 0) dUdr = 0.0f;
+            else if (type_i != (jf & 0x7f)) dUdr = dmorse(p.D_lat / p.seam_coeff, p.A_lat, dr) / dr;
+            else dUdr = dmorse(p.D_lat, p.A_lat, dr) / dr;
+            if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) {
+                if (dr != 0.0f) dUdr += dbarr(p.a_barr_lat, p.r_barr_lat, p.w_barr_lat, dr) / dr;
+            }
+            const float ysg = neg ? 1.0f : -1.0f;
+            bond_accumulate(f, dUdr, d, oi, ls.xp, ysg * ls.yp, ysg * ls.zp, fr);
+        }
+    }
+
+    // ---- LJ r^-6 repulsion from the Verlet list (compute_cuda.cu:470-495)
+    if (p.lj_on) {
+        const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+        const int n = a.ljcnt[(size_t)traj * a.Npad + i];
+        const float amp = p.ljscale * p.ljsigma6;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll 4
+        for (int kk = 0; kk < n; kk++) {
+            const int j = lj[(size_t)kk * a.Npad];
+            const float4 Pj = s.P[j];
+            const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
+            const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
+                const float inv = 1.0f / sf;
+                const float inv2 = inv * inv;
+                const float df = 6.0f * (inv2 * inv2); // 6 / dr^8
+                const float c = amp * df;
+                fx += c * dx;
+                fy += c * dy;
+                fz += c * dz;
+            }
+        }
+        f.x += fx;
+        f.y += fy;
+        f.z += fz;
+    }
+
+    // ---- cylindrical repulsive walls (compute_cuda.cu:497-517); zs[traj] == rep_h
+    if (p.is_wall) {
+        if (zi < p.rep_leftborder) {
+            f.z += p.rep_eps * fabsf(zi - p.rep_leftborder);
+        } else if (zi > p.rep_h + p.rep_leftborder) {
+            f.z += -p.rep_eps * fabsf(zi - (p.rep_h + p.rep_leftborder));
+        }
+        const float rad2 = xi * xi + yi * yi;
+        if (rad2 > p.rep_r * p.rep_r) {
+            const float rad = sqrtf(rad2);
+            const float coeff = -p.rep_eps * (rad - p.rep_r);
+            f.x += (xi / rad) * coeff;
+            f.y += (yi / rad) * coeff;
+        }
+    }
+    return f;
+}
+
+// ------------------------------------------------------------------ energies (compute_cuda.cu:676-911)
+struct E7 { double harm, lng, lat, psi, fi, teta, lj; };
+
+__device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int traj, int i, const Mono &m)
+{
+    const maddy_params &p = k.p;
+    const DevSys &a = k.a;
+    float U_lat = 0.f, U_long = 0.f, U_harm = 0.f, U_fi = 0.f, U_psi = 0.f, U_teta = 0.f, U_lj = 0.f;
+    if (!(m.flags & MF_EXTRA)) {
+        const float4 Ei = s.E[i];
+        const float xi = m.x, yi = m.y, zi = m.z;
+        const bool gtp_i = (m.flags & MF_GTP) != 0;
+        const bool ontub_i = (m.flags & MF_ONTUB) != 0;
+        const int nh = a.harm_count[i];
+        for (int kk = 0; kk < nh; kk++) {
+            int raw = a.harm[a.maxH * i + kk];
+            const float sg = raw < 0 ? 1.0f : -1.0f;
+            const int j = raw < 0 ? -raw : raw;
+            const float4 Pj = s.P[j], Ej = s.E[j];
+            F3 d;
+            d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
+            d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
+            d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+            const float dr = site_distance_d(d);
+            U_harm = (float)((double)U_harm + (double)(p.C / 2) * ((double)dr * (double)dr));
+            if (dr < MD_ANGLE_CUTOFF) {
+                // quirk kept: psi and fi use (i - j), theta uses (j - i)  (compute_cuda.cu:751-757)
+                const float psiij = -(Ej.w - m.psi);
+                const float fiij = -(Pj.w - m.fi);
+                const float thetaji = s.L1[j].w - m.theta;
+                U_psi += p.B_psi * (1 - cosf(psiij - p.psi_0));
+                U_fi += p.B_fi * (1 - cosf(fiij - p.fi_0));
+                U_teta += p.B_theta * (1 - cosf(thetaji - (gtp_i ? p.theta0_gtp : p.theta0_gdp)));
+            }
+        }
+        const uint16_t *bl = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
+        const uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
+        const int nlong = bc[0];
+        for (int kk = 0; kk < nlong; kk++) {
+            const unsigned code = bl[(size_t)kk * a.Npad];
+            const int j = code >> 1;
+            const float sg = (code & 1u) ? 1.0f : -1.0f;
+            const float4 Pj = s.P[j], Ej = s.E[j];
+            const int jf = __float_as_int(s.L2[j].w);
+            F3 d;
+            d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
+            d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
+            d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+            // dr2 is rounded to float before the sqrt here (compute_cuda.cu:783-791)
+            double s2 = (double)d.z * (double)d.z;
+            s2 += (double)d.x * (double)d.x;
+            s2 += (double)d.y * (double)d.y;
+            const float dr = sqrtf((float)s2);
+            U_long += morse_en(p.D_long, p.A_long, dr);
+            if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) U_long += barr(p.a_barr_long, p.r_barr_long, p.w_barr_long, dr);
+            if (dr < MD_ANGLE_CUTOFF) {
+                const float psiij = -(Ej.w - m.psi);
+                const float fiij = -(Pj.w - m.fi);
+                const float thetaij = -(s.L1[j].w - m.theta);
+                const bool gtp_last = (zi > Pj.z) ? gtp_i : ((jf & MF_GTP) != 0);
+                const float th0 = gtp_last ? p.theta0_gtp : p.theta0_gdp;
+                U_psi += p.B_psi * (1 - cosf(psiij - p.psi_0));
+                U_fi += p.B_fi * (1 - cosf(fiij - p.fi_0));
+                U_teta += p.B_theta * (1 - cosf(thetaij - th0));
+            }
+        }
+        const int nlat = bc[a.Npad];
+        if (nlat > 0) {
+            const float4 L1i = s.L1[i], L2i = s.L2[i];
+            const int type_i = MF_TYPE(m.flags);
+            for (int kk = 0; kk < nlat; kk++) {
+                const unsigned code = bl[(size_t)(a.capLong + kk) * a.Npad];
+                const int j = code >> 1;
+                const bool neg = (code & 1u) != 0;
+                const float4 Pj = s.P[j];
+                const float4 L1j = s.L1[j], L2j = s.L2[j];
+                const int jf = __float_as_int(L2j.w);
+                const F3 oi = neg ? mk3(L1i.x, L1i.y, L1i.z) : mk3(L2i.x, L2i.y, L2i.z);
+                const F3 oj = neg ? mk3(L2j.x, L2j.y, L2j.z) : mk3(L1j.x, L1j.y, L1j.z);
+                F3 d;
+                d.x = (Pj.x - xi) - oi.x + oj.x;
+                d.y = (Pj.y - yi) - oi.y + oj.y;
+                d.z = (Pj.z - zi) - oi.z + oj.z;
+                const float dr = site_distance_d(d);
+                if (type_i != (jf & 0x7f)) U_lat += morse_en(p.D_lat / p.seam_coeff, p.A_lat, dr);
+                else U_lat += morse_en(p.D_lat, p.A_lat, dr);
+                if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) U_lat += barr(p.a_barr_lat, p.r_barr_lat, p.w_barr_lat, dr);
+            }
+        }
+        if (p.lj_on) {
+            const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+            const int n = a.ljcnt[(size_t)traj * a.Npad + i];
+            for (int kk = 0; kk < n; kk++) {
+                const int j = lj[(size_t)kk * a.Npad];
+                const float4 Pj = s.P[j];
+                const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
+                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
+                    const float dr = (float)sqrt(dist2_exact(dx, dy, dz));
+                    const double dr2 = (double)dr * (double)dr;
+                    U_lj = (float)((double)U_lj + (double)(p.ljscale * p.ljsigma6) / (dr2 * dr2 * dr2));
+                }
+            }
+        }
+    }
+    E7 e;
+    e.harm = U_harm / 2;
+    e.lng = U_long / 2;
+    e.lat = U_lat / 2;
+    e.lj = U_lj / 2;
+    e.psi = U_psi / 2;
+    e.fi = U_fi / 2;
+    e.teta = U_teta / 2;
+    return e;
+}
+
+// ------------------------------------------------------------------ list rebuild
+// One pass over all j of the staged trajectory for the MPT monomers of this thread:
+// LJ Verlet list (compute_cuda.cu:913-940) and dynamic bond lists (compute_cuda.cu:527-674).
+template <int MPT>
+__device__ __forceinline__ void rebuild_lists(const KArgs &k, const Stage &s, int traj, const Mono (&mo)[MPT],
+                                              const int (&idx)[MPT], unsigned ops)
+{
+    const maddy_params &p = k.p;
+    const DevSys &a = k.a;
+    const int N = a.N;
+    const bool do_lj = (ops & OP_REBUILD_LJ) != 0;
+    const bool do_b = (ops & OP_REBUILD_BONDS) != 0;
+
+    int nlj[MPT], nlong[MPT], nlat[MPT], hraw[MPT];
+    bool act[MPT];
+    float4 Ei[MPT], L1i[MPT], L2i[MPT];
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        nlj[t] = nlong[t] = nlat[t] = 0;
+        act[t] = idx[t] < N && !(mo[t].flags & MF_EXTRA);
+        hraw[t] = 0;
+        if (idx[t] < N) {
+            hraw[t] = a.harm[a.maxH * idx[t]]; // first entry, whatever harmonicCount says (compute_cuda.cu:548)
+            Ei[t] = s.E[idx[t]];
+            L1i[t] = s.L1[idx[t]];
+            L2i[t] = s.L2[idx[t]];
+        }
+    }
+    uint16_t *ljb = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad;
+    uint16_t *blb = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad;
+    int status = 0;
+
+    for (int j = 0; j < N; j++) {
+        const float4 Pj = s.P[j];
+#pragma unroll
+        for (int t = 0; t < MPT; t++) {
+            if (!act[t]) continue;
+            const int i = idx[t];
+            const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
+            const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (do_lj && i != j && inside_cut(k.cut_pairs, dx, dy, dz, sf)) {
+                if (nlj[t] < MADDY_LJ_CAPACITY) ljb[(size_t)nlj[t] * a.Npad + i] = (uint16_t)j;
+                else status |= ST_LJ_OVERFLOW;
+                nlj[t]++;
+            }
+            if (do_b && sf < MD_BOND_PREFILTER2 && i != j) {
+                const int hp = hraw[t] < 0 ? -hraw[t] : hraw[t];
+                if (hp == j) continue;
+                const float4 Ej = s.E[j], L1j = s.L1[j], L2j = s.L2[j];
+                const int jf = __float_as_int(L2j.w);
+                // longitudinal candidate: other monomer type, end sites opposite to the dimer bond
+                if (MF_TYPE(mo[t].flags) != (jf & 0x7f)) {
+                    const float sg = hraw[t] < 0 ? -1.0f : 1.0f; // R_MON / r_mon (compute_cuda.cu:548-551)
+                    F3 d;
+                    d.x = (Pj.x - mo[t].x) - sg * Ei[t].x - sg * Ej.x;
+                    d.y = (Pj.y - mo[t].y) - sg * Ei[t].y - sg * Ej.y;
+                    d.z = (Pj.z - mo[t].z) - sg * Ei[t].z - sg * Ej.z;
+                    if (site_distance(d) < MD_PAIR_CUTOFF) {
+                        // stored as +j when harmonic < 0, -j otherwise; -0 == 0 loses its sign (compute_cuda.cu:588-592)
+                        const unsigned neg = (hraw[t] < 0 || j == 0) ? 0u : 1u;
+                        if (nlong[t] < a.capLong) blb[(size_t)nlong[t] * a.Npad + i] = (uint16_t)((j << 1) | neg);
+                        else status |= ST_LONG_OVERFLOW;
+                        nlong[t]++;
+                    }
+                }
+                // lateral candidates: (i:p1, j:p2) stored negative, then (i:p2, j:p1) stored positive
+                {
+                    F3 d;
+                    d.x = (Pj.x - mo[t].x) - L1i[t].x + L2j.x;
+                    d.y = (Pj.y - mo[t].y) - L1i[t].y + L2j.y;
+                    d.z = (Pj.z - mo[t].z) - L1i[t].z + L2j.z;
+                    if (site_distance(d) < MD_PAIR_CUTOFF) {
+                        if (nlat[t] < a.capLat) blb[(size_t)(a.capLong + nlat[t]) * a.Npad + i] = (uint16_t)((j << 1) | 1u);
+                        else status |= ST_LAT_OVERFLOW;
+                        nlat[t]++;
+                    }
+                    d.x = (Pj.x - mo[t].x) - L2i[t].x + L1j.x;
+                    d.y = (Pj.y - mo[t].y) - L2i[t].y + L1j.y;
+                    d.z = (Pj.z - mo[t].z) - L2i[t].z + L1j.z;
+                    if (site_distance(d) < MD_PAIR_CUTOFF) {
+                        if (nlat[t] < a.capLat) blb[(size_t)(a.capLong + nlat[t]) * a.Npad + i] = (uint16_t)(j << 1);
+                        else status |= ST_LAT_OVERFLOW;
+                        nlat[t]++;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        if (idx[t] >= N) continue;
+        const int i = idx[t];
+        if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj[t], MADDY_LJ_CAPACITY);
+        if (do_b) {
+            uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
+            bc[0] = (uint8_t)min(nlong[t], a.capLong);
+            bc[a.Npad] = (uint8_t)min(nlat[t], a.capLat);
+        }
+    }
+    if (status) atomicOr(a.status, status);
+}
+
+// ------------------------------------------------------------------ integrator (compute_cuda.cu:943-975)
+__device__ __forceinline__ void integrate_monomer(const maddy_params &p, Mono &m, const G6 &f)
+{
+    if (!(m.flags & MF_FIXED) && !(m.flags & MF_EXTRA)) {
+        const float4 rf_xyz = rforce(m.rx);
+        const float4 rf_ang = rforce(m.ra);
+        m.x += (p.dt / p.gammaR) * f.x + p.varR * rf_xyz.x;
+        m.y += (p.dt / p.gammaR) * f.y + p.varR * rf_xyz.y;
+        m.z += (p.dt / p.gammaR) * f.z + p.varR * rf_xyz.z;
+        m.fi += (p.dt / (p.gammaTheta * p.alpha)) * f.fi + (p.varTheta * sqrtf(p.freeze_temp / p.alpha)) * rf_ang.x;
+        m.psi += (p.dt / (p.gammaTheta * p.alpha)) * f.psi + (p.varTheta * sqrtf(p.freeze_temp / p.alpha)) * rf_ang.y;
+        m.theta += (p.dt / p.gammaTheta) * f.theta + p.varTheta * rf_ang.z;
+    }
+}
+
+// ------------------------------------------------------------------ block reduction of 7 doubles
+__device__ __forceinline__ void block_reduce_e7(E7 e, double *out7, double *scratch /* [32*7] shared */)
+{
+    double v[7] = {e.harm, e.lng, e.lat, e.psi, e.fi, e.teta, e.lj};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) scratch[warp * 7 + q] = v[q];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+            double w = lane < nwarp ? scratch[lane * 7 + q] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+            if (lane == 0) out7[q] = w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the trajectory kernel
+// Threads per CTA never exceed MD_MAX_THREADS (the host picks MPT = ceil(N / MD_MAX_THREADS)),
+// which leaves ptxas up to 112 registers per thread for the fused loop.
+template <int MPT>
+__global__ void __launch_bounds__(MD_MAX_THREADS, 1) traj_kernel(const __grid_constant__ KArgs k)
+{
+    extern __shared__ float4 smem[];
+    __shared__ double red_scratch[32 * 7];
+    const maddy_params &p = k.p;
+    const DevSys &a = k.a;
+    const int N = a.N;
+    const int traj = blockIdx.x;
+    const size_t base = (size_t)traj * N;
+    const LatSite ls = lateral_site();
+
+    Mono mo[MPT];
+    int idx[MPT];
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int i = threadIdx.x + t * blockDim.x;
+        idx[t] = i;
+        if (i < N) {
+            const float4 P = a.pos[base + i], A = a.ang[base + i];
+            mo[t].x = P.x; mo[t].y = P.y; mo[t].z = P.z;
+            mo[t].fi = A.x; mo[t].psi = A.y; mo[t].theta = A.z;
+            mo[t].flags = (int)a.sflags[i] | (a.gtp[base + i] == 1 ? MF_GTP : 0) | (a.ontub[base + i] ? MF_ONTUB : 0) |
+                          (a.extra[base + i] ? MF_EXTRA : 0);
+            if (k.ops & OP_RUN) {
+                mo[t].rx = a.rng_xyz[base + i];
+                mo[t].ra = a.rng_ang[base + i];
+            }
+        } else {
+            mo[t].flags = MF_EXTRA | MF_FIXED;
+        }
+    }
+
+    if (k.ops & OP_RUN) {
+        int buf = 0;
+        for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
+            const Stage s = stage_at(smem, N, buf);
+#pragma unroll
+            for (int t = 0; t < MPT; t++)
+                if (idx[t] < N) publish(s, idx[t], mo[t], ls);
+            __syncthreads();
+            if (step % p.ljpairsupdatefreq == 0 && !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD))) {
+                const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
+                if (rops) rebuild_lists<MPT>(k, s, traj, mo, idx, rops);
+            }
+#pragma unroll
+            for (int t = 0; t < MPT; t++) {
+                if (idx[t] < N && !(mo[t].flags & MF_EXTRA)) {
+                    const G6 f = monomer_force(k, s, traj, idx[t], mo[t], ls);
+                    integrate_monomer(p, mo[t], f);
+                }
+            }
+            if (k.nbuf == 2) buf ^= 1;
+            else __syncthreads();
+        }
+#pragma unroll
+        for (int t = 0; t < MPT; t++) {
+            const int i = idx[t];
+            if (i < N) {
+                a.pos[base + i] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
+                a.ang[base + i] = make_float4(mo[t].fi, mo[t].psi, mo[t].theta, 0.f);
+                a.rng_xyz[base + i] = mo[t].rx;
+                a.rng_ang[base + i] = mo[t].ra;
+            }
+        }
+        return;
+    }
+
+    // ---- single-phase modes (step-granular API)
+    const Stage s = stage_at(smem, N, 0);
+#pragma unroll
+    for (int t = 0; t < MPT; t++)
+        if (idx[t] < N) publish(s, idx[t], mo[t], ls);
+    __syncthreads();
+
+    if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) rebuild_lists<MPT>(k, s, traj, mo, idx, k.ops);
+
+    if (k.ops & OP_FORCE) {
+#pragma unroll
+        for (int t = 0; t < MPT; t++) {
+            const int i = idx[t];
+            if (i < N && !(mo[t].flags & MF_EXTRA)) {
+                // extras keep the zero written by the integrator (compute_cuda.cu:55, :966-972)
+                const G6 f = monomer_force(k, s, traj, i, mo[t], ls);
+                a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
+                a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
+            }
+        }
+    }
+
+    if (k.ops & OP_ENERGY) {
+        E7 acc = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < MPT; t++) {
+            const int i = idx[t];
+            if (i < N) {
+                const E7 e = monomer_energy(k, s, traj, i, mo[t]);
+                double *o = a.en_mono + (base + i) * 7;
+                o[0] = e.harm; o[1] = e.lng; o[2] = e.lat; o[3] = e.psi; o[4] = e.fi; o[5] = e.teta; o[6] = e.lj;
+                acc.harm += e.harm; acc.lng += e.lng; acc.lat += e.lat; acc.psi += e.psi;
+                acc.fi += e.fi; acc.teta += e.teta; acc.lj += e.lj;
+            }
+        }
+        // per-trajectory order for the host: harm,long,lat,psi,fi,teta,lj (updater.cpp:35-36)
+        block_reduce_e7(acc, a.en_traj + (size_t)traj * 7, red_scratch);
+    }
+}
+
+// Stand-alone integrator over forces stored in HBM (step-granular maddy_integrate).
+__global__ void __launch_bounds__(256) integrate_kernel(const __grid_constant__ KArgs k)
+{
+    const DevSys &a = k.a;
+    const size_t n = (size_t)a.ntr * a.N;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(q % a.N);
+        Mono m;
+        m.flags = (int)a.sflags[i] | (a.extra[q] ? MF_EXTRA : 0);
+        if (!(m.flags & MF_FIXED) && !(m.flags & MF_EXTRA)) {
+            const float4 P = a.pos[q], A = a.ang[q], FP = a.fpos[q], FA = a.fang[q];
+            m.x = P.x; m.y = P.y; m.z = P.z; m.fi = A.x; m.psi = A.y; m.theta = A.z;
+            m.rx = a.rng_xyz[q];
+            m.ra = a.rng_ang[q];
+            G6 f = {FP.x, FP.y, FP.z, FA.x, FA.y, FA.z};
+            integrate_monomer(k.p, m, f);
+            a.pos[q] = make_float4(m.x, m.y, m.z, 0.f);
+            a.ang[q] = make_float4(m.fi, m.psi, m.theta, 0.f);
+            a.rng_xyz[q] = m.rx;
+            a.rng_ang[q] = m.ra;
+        }
+        a.fpos[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a.fang[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------ launch helpers (called from the C-ABI)
+template <int MPT>
+static cudaError_t launch_traj(const KArgs &k, int threads, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(traj_kernel<MPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    traj_kernel<MPT><<<k.a.ntr, threads, smem, st>>>(k);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st)
+{
+    switch (mpt) {
+    case 1: return launch_traj<1>(k, threads, smem, st);
+    case 2: return launch_traj<2>(k, threads, smem, st);
+    case 3: return launch_traj<3>(k, threads, smem, st);
+    case 4: return launch_traj<4>(k, threads, smem, st);
+    case 5: return launch_traj<5>(k, threads, smem, st);
+    case 6: return launch_traj<6>(k, threads, smem, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st)
+{
+    const size_t n = (size_t)k.a.ntr * k.a.N;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    integrate_kernel<<<blocks, 256, 0, st>>>(k);
+    return cudaGetLastError();
+}
+
+} // namespace maddy

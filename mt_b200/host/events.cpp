@@ -1,0 +1,380 @@
+/*
+ * events.cpp — host-side per-stride events and the step loop of the drop-in host.
+ *
+ * Host events keep the reference's semantics and its use of the single libc rand() stream
+ * (src/updater.cpp:74-257): tubule length / on-tubule flags, constant-concentration insertion,
+ * hydrolysis, energy and force printing, DCD frames.  The step loop is compute()
+ * (src/compute_cuda.cu:1125-1260) re-expressed over the C-ABI: all steps between two host
+ * events run inside ONE fused maddy_run() launch per GPU; trajectories are sharded in
+ * contiguous blocks over `n_gpus` devices driven by this single host thread, so the order in
+ * which host events consume rand() is unchanged.
+ */
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include "mt_host.hpp"
+
+namespace mt {
+
+static const float R_MT = 8.12f, R_MON = 2.0f, ANG_THRES = 1.0f, R_THRES = R_MON * 8;
+static const int PF_NUMBER = 13;
+
+// ---------------------------------------------------------------- timers (timer.cpp)
+void init_timer(System &s) { s.initial_clock = s.last_clock = (long)clock(); }
+
+static void print_formatted_time(float timer)
+{
+    int days = (int)(timer / (3600.0f * 24.0f));
+    int hours = (int)(timer / 3600.0f - days * 24.0f);
+    int minutes = (int)(timer / 60.0f - hours * 60.0f - days * 24.0f * 60.0f);
+    int seconds = (int)(timer - hours * 3600.0f - days * 24.0f * 3600.0f - minutes * 60.0f);
+    printf("%dd %dh %dm %ds", days, hours, minutes, seconds);
+}
+static void print_time(System &s, long long step)
+{
+    float timer = ((float)(clock() - s.initial_clock)) / ((float)CLOCKS_PER_SEC);
+    printf("Computation time: ");
+    print_formatted_time(timer);
+    timer = ((float)(clock() - s.last_clock)) / ((float)CLOCKS_PER_SEC);
+    if (step != 0) printf(" (~%f steps/sec)\n", ((float)step) / timer);
+    else printf("\n");
+}
+static void print_estimated_timeleft(System &s, float fraction)
+{
+    if (fraction != 0.0f) {
+        float timer = ((float)(clock() - s.initial_clock)) / ((float)CLOCKS_PER_SEC) * (1.0f / fraction - 1.0f);
+        printf("Estimated time left: ");
+        print_formatted_time(timer);
+        printf(" (%3.1f%% completed)\n", fraction * 100.0f);
+    }
+}
+
+// ---------------------------------------------------------------- outputs (updater.cpp:3-72)
+void output_all_energies(System &s, long long)
+{
+    for (int t = 0; t < s.par.n_tr; t++) {
+        const double *e = &s.energies[(size_t)t * 7];
+        if (!std::isfinite(e[0]) || !std::isfinite(e[1]) || !std::isfinite(e[2]) || !std::isfinite(e[6]))
+            printf("Some energy in %d trajectory is NaN. NOT Exit program\n", t);
+        printf("Energies[%d]:\t%f\t%f\t%f\t%f\t%f\t%f\t%f\n", t, e[0], e[1], e[2], e[3], e[4], e[5], e[6]);
+    }
+}
+void output_sum_force(System &s)
+{
+    const int N = s.par.n_tot;
+    for (int t = 0; t < s.par.n_tr; t++) {
+        float sx = 0, sy = 0, sz = 0;
+        for (int i = t * N; i < (t + 1) * N; i++) {
+            sx += s.f[(size_t)i * 7 + 0];
+            sy += s.f[(size_t)i * 7 + 1];
+            sz += s.f[(size_t)i * 7 + 2];
+        }
+        printf("SF for %d traj %.16f\n", t, sqrt(sx * sx + sy * sy + sz * sz));
+    }
+}
+void output_forces(System &s)
+{
+    const size_t n = (size_t)s.par.n_tot * s.par.n_tr;
+    for (size_t i = 0; i < n; i++) {
+        const float *f = &s.f[i * 7], *r = &s.r[i * 7];
+        printf("Force[%d].theta = %f, fi = %f, psi = %f\n", (int)i, f[4], f[3], f[5]);
+        printf("Angle[%d].theta = %f, fi = %f, psi = %f\n", (int)i, r[4], r[3], r[5]);
+    }
+}
+
+void update(System &s, long long step, std::vector<int> &)
+{
+    if (!s.quiet) {
+        printf("Saving coordinates at step %lld\n", step);
+        print_time(s, step);
+        print_estimated_timeleft(s, (float)step / (float)s.hp.steps);
+    }
+    if (s.write_files) {
+        save_coord_dcd(s);
+        if (s.hp.hydrolysis && (step % (s.hp.stride * 10) == 0)) {
+            if (step == 0) {
+                FILE *first = fopen("dcd/hydrolysis.pdb", "w");
+                if (first) fclose(first);
+            }
+            append_coord_pdb(s);
+        }
+    }
+    if (s.hp.out_force && !s.quiet) {
+        output_sum_force(s);
+        output_forces(s);
+    }
+    if (s.hp.out_energy && !s.quiet) output_all_energies(s, step);
+}
+
+// ---------------------------------------------------------------- tubule length (updater.cpp:154-227)
+void mt_length(System &s, long long step, std::vector<int> &mt_len)
+{
+    const int N = s.par.n_tot;
+    if (step == 0 && s.write_files) {
+        FILE *first = fopen("mt_len.dat", "w");
+        if (first) fclose(first);
+    }
+    for (int t = 0; t < s.par.n_tr; t++) {
+        int sum = 0;
+        for (int i = t * N; i < (t + 1) * N; i++) {
+            const float *c = &s.r[(size_t)i * 7];
+            float rad = sqrt(c[0] * c[0] + c[1] * c[1]);
+            if ((rad < R_MT + R_THRES) && (rad > 1.0) && (cosf(c[4]) > cosf(ANG_THRES))) {
+                sum++;
+                s.on_tubule_cur[i] = 1;
+            } else {
+                s.on_tubule_cur[i] = 0;
+            }
+        }
+        mt_len[t] = sum;
+        if (!s.quiet) printf("tubule[%d]: %d\n", t, sum);
+    }
+    if (s.write_files) {
+        FILE *f = fopen("mt_len.dat", "a");
+        if (f) {
+            fprintf(f, "%lld\t", step);
+            for (int t = 0; t < s.par.n_tr; t++) fprintf(f, "%f\t", 2 * R_MON * (float)mt_len[t] / PF_NUMBER);
+            fprintf(f, "\n");
+            fclose(f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- constant concentration (updater.cpp:97-152)
+int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len)
+{
+    const maddy_params &par = s.par;
+    const int N = par.n_tot;
+    int flag = 0;
+    for (int tr = 0; tr < par.n_tr; tr++) {
+        int num_of_extra = 0;
+        for (int i = 0; i < N; i++)
+            if (s.extra[i + (size_t)tr * N]) num_of_extra++;
+        const float zs = par.rep_h;
+        float Vol = float(3.14 * par.rep_r * par.rep_r * zs);
+        int NFreeDimers = (N - mt_len[tr] - num_of_extra) / 2;
+        while (1.0e7 * NFreeDimers / 6.0 < s.hp.conc * Vol) {
+            for (int i = 0; i < N; i += 2) {
+                const size_t q = i + (size_t)tr * N;
+                if (s.extra[q] && s.mon_type[i] == 0) {
+                    s.extra[q] = 0;
+                    s.extra[q + 1] = 0;
+                    float x, y;
+                    for (;;) {
+                        x = par.rep_r - 2 * (rand() % int(par.rep_r));
+                        y = par.rep_r - 2 * (rand() % int(par.rep_r));
+                        if (x * x + y * y <= par.rep_r * par.rep_r) { // inside the cylinder
+                            if (!s.quiet) printf("New x,y coordinates for extra particle: %f  %f index: %d\n", x, y, (int)q);
+                            num_of_extra -= 2;
+                            break;
+                        }
+                    }
+                    float z = zs + par.rep_leftborder + 3 * 2 * R_MON;
+                    s.r[q * 7 + 0] = x;
+                    s.r[q * 7 + 1] = y;
+                    s.r[q * 7 + 2] = z;
+                    s.r[(q + 1) * 7 + 0] = x;
+                    s.r[(q + 1) * 7 + 1] = y;
+                    s.r[(q + 1) * 7 + 2] = z + 2 * R_MON;
+                    flag++;
+                    break;
+                }
+            }
+            NFreeDimers += 1;
+            if (num_of_extra == 0) {
+                if (!s.quiet) printf("No more extra particles for trajectory[%d]!\n", tr);
+                break;
+            }
+        }
+        if (!s.quiet)
+            printf("Concentration for tajectory[%d]: %f [muMole / L],\t %f [Dimers / nm^3],\t %d [Dimers / Volume],\t  Volume: %f [nm^3]\n",
+                   tr, 1.0e7 * NFreeDimers / (6.0 * Vol), NFreeDimers / Vol, NFreeDimers, Vol);
+    }
+    return flag;
+}
+
+// ---------------------------------------------------------------- hydrolysis (updater.cpp:229-257)
+void hydrolyse(System &s)
+{
+    const int N = s.par.n_tot, Ntr = s.par.n_tr;
+    for (int i = 0; i < N; i += 2)
+        for (int tr = 0; tr < Ntr; tr++) {
+            const size_t q = i + (size_t)tr * N;
+            if (s.gtp[q] == 1 && !s.extra[q] && s.on_tubule_cur[q] * s.on_tubule_prev[q] == 1) {
+                double prob = rand() / (double)RAND_MAX;
+                if (prob < 0.02) {
+                    s.gtp[q] = 0;
+                    s.gtp[q + 1] = 0;
+                    if (!s.quiet) printf("*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", i / 2, tr);
+                }
+            }
+        }
+    for (int i = 0; i < N; i += 2)
+        for (int tr = 0; tr < Ntr; tr++) {
+            const size_t q = i + (size_t)tr * N;
+            if (s.gtp[q] == 0 && !s.extra[q] && s.on_tubule_cur[q] == 0 && s.on_tubule_prev[q] == 0) {
+                s.gtp[q] = 1;
+                s.gtp[q + 1] = 1;
+                if (!s.quiet) printf("*** Transition to GTP occured to dimer # %d trajectory #%d ***\n", i / 2, tr);
+            }
+        }
+}
+
+// ---------------------------------------------------------------- the step loop
+namespace {
+struct Shard {
+    maddy_handle *h = nullptr;
+    int first = 0, count = 0;
+};
+struct Shards {
+    std::vector<Shard> v;
+    ~Shards()
+    {
+        for (Shard &s : v)
+            if (s.h) maddy_destroy(s.h);
+    }
+};
+void ck(int rc, maddy_handle *h, const char *what)
+{
+    if (rc != MADDY_OK) die("%s failed (%d): %s", what, rc, maddy_last_error(h));
+}
+} // namespace
+
+void compute(System &s, bool fused, ComputeStats *stats)
+{
+    const maddy_params &par = s.par;
+    const HostParams &hp = s.hp;
+    const int N = par.n_tot, Ntr = par.n_tr;
+    const size_t n = (size_t)N * Ntr;
+    ComputeStats st;
+
+    // initIntegration: forces zeroed; the angle wrap happens inside maddy_create on the device copy
+    // AND on the host copy (compute_cuda.cu:995-1010 modifies r in place)
+    std::fill(s.f.begin(), s.f.end(), 0.f);
+    for (size_t q = 0; q < n; q++) {
+        float *c = &s.r[q * 7];
+        c[3] -= (2 * M_PI) * (int)(c[3] / (2 * M_PI));
+        c[5] -= (2 * M_PI) * (int)(c[5] / (2 * M_PI));
+        c[4] -= (2 * M_PI) * (int)(c[4] / (2 * M_PI));
+    }
+
+    // contiguous trajectory blocks per GPU
+    int G = hp.n_gpus < 1 ? 1 : hp.n_gpus;
+    if (G > Ntr) G = Ntr;
+    Shards sh;
+    sh.v.resize(G);
+    for (int g = 0; g < G; g++) {
+        Shard &d = sh.v[g];
+        d.first = (int)((long long)Ntr * g / G);
+        d.count = (int)((long long)Ntr * (g + 1) / G) - d.first;
+        maddy_params p = par;
+        p.traj_first = d.first;
+        p.n_tr_local = d.count;
+        p.device = par.device + g;
+        maddy_topology top = s.topology_view(d.first);
+        int rc = maddy_create(&p, &top, &s.r[(size_t)d.first * N * 7], nullptr, &d.h);
+        if (rc != MADDY_OK) die("maddy_create failed (%d): %s", rc, maddy_last_error(nullptr));
+        st.h2d_bytes += (double)d.count * N * (7 * 4 + 32 + 3);
+    }
+    if (!s.quiet) printf("Using %d device(s), first device %d\n", G, par.device);
+    s.energies.assign((size_t)Ntr * 7, 0.0);
+
+    std::vector<int> mt_len(Ntr, 0), mt_len_prev(Ntr, 0);
+    auto for_each = [&](auto fn) {
+        for (Shard &d : sh.v) fn(d);
+    };
+
+    long long step = 0;
+    while (step < hp.steps) {
+        // ---- list rebuild (compute_cuda.cu:1140-1151) — before the host events of this step
+        const bool rebuild_now = step % par.ljpairsupdatefreq == 0;
+        if (rebuild_now) {
+            for_each([&](Shard &d) {
+                if (par.lj_on) ck(maddy_rebuild_lj(d.h), d.h, "maddy_rebuild_lj");
+                if (par.is_assembly) ck(maddy_rebuild_bonds(d.h), d.h, "maddy_rebuild_bonds");
+            });
+        }
+        // ---- hydrolysis (compute_cuda.cu:1153-1160)
+        if (hp.hydrolysis && step % hp.hydrostep == 0 && step != 0) {
+            hydrolyse(s);
+            for_each([&](Shard &d) { ck(maddy_upload_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_upload_gtp"); });
+            st.h2d_bytes += (double)n;
+        }
+        // ---- stride block (compute_cuda.cu:1163-1226)
+        if (step % hp.stride == 0) {
+            if (hp.out_energy) {
+                for_each([&](Shard &d) { ck(maddy_energies(d.h, &s.energies[(size_t)d.first * 7], nullptr), d.h, "maddy_energies"); });
+                st.d2h_bytes += (double)Ntr * 7 * 8;
+            }
+            if (hp.out_force) {
+                for_each([&](Shard &d) { ck(maddy_download_forces(d.h, &s.f[(size_t)d.first * N * 7]), d.h, "maddy_download_forces"); });
+                st.d2h_bytes += (double)n * 32;
+            }
+            for_each([&](Shard &d) { ck(maddy_download_coords(d.h, &s.r[(size_t)d.first * N * 7]), d.h, "maddy_download_coords"); });
+            st.d2h_bytes += (double)n * 32;
+            if (hp.tub_length) {
+                s.on_tubule_prev = s.on_tubule_cur;
+                if (step != 0) {
+                    mt_len_prev = mt_len;
+                    mt_length(s, step, mt_len);
+                    if (par.barrier) {
+                        for_each([&](Shard &d) {
+                            ck(maddy_upload_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N]), d.h, "maddy_upload_on_tubule");
+                        });
+                        st.h2d_bytes += (double)n;
+                    }
+                    if (hp.is_const_conc) {
+                        for (int t = 0; t < Ntr; t++) mt_len_prev[t] = mt_len[t] - mt_len_prev[t];
+                        if (change_conc(s, mt_len_prev, mt_len)) {
+                            for_each([&](Shard &d) {
+                                ck(maddy_upload_extra(d.h, &s.extra[(size_t)d.first * N]), d.h, "maddy_upload_extra");
+                                ck(maddy_upload_coords(d.h, &s.r[(size_t)d.first * N * 7]), d.h, "maddy_upload_coords");
+                            });
+                            st.h2d_bytes += (double)n * 33;
+                        }
+                    }
+                    update(s, step, mt_len);
+                } else {
+                    update(s, step, mt_len);
+                    mt_length(s, step, mt_len);
+                }
+            } else {
+                update(s, step, mt_len);
+            }
+        }
+        // ---- steps up to the next host event
+        long long next = hp.steps;
+        next = std::min(next, (step / hp.stride + 1) * hp.stride);
+        if (hp.hydrolysis && hp.hydrostep > 0) next = std::min(next, (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
+        const long long count = next - step;
+        if (par.tea_on || !fused) {
+            for (long long q = step; q < next; q++) {
+                for_each([&](Shard &d) {
+                    if (q != step && q % par.ljpairsupdatefreq == 0) {
+                        if (par.lj_on) ck(maddy_rebuild_lj(d.h), d.h, "maddy_rebuild_lj");
+                        if (par.is_assembly) ck(maddy_rebuild_bonds(d.h), d.h, "maddy_rebuild_bonds");
+                    }
+                    ck(maddy_force(d.h), d.h, "maddy_force");
+                    if (par.tea_on) {
+                        ck(maddy_tea_update(d.h, q), d.h, "maddy_tea_update");
+                        ck(maddy_tea_integrate(d.h), d.h, "maddy_tea_integrate");
+                    } else {
+                        ck(maddy_integrate(d.h), d.h, "maddy_integrate");
+                    }
+                });
+            }
+        } else {
+            for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, rebuild_now ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u), d.h, "maddy_run"); });
+        }
+        step = next;
+        st.steps += count;
+    }
+    for_each([&](Shard &d) {
+        ck(maddy_sync(d.h), d.h, "maddy_sync");
+        st.launches += maddy_launch_count(d.h);
+    });
+    if (stats) *stats = st;
+}
+
+} // namespace mt

@@ -1,0 +1,148 @@
+/*
+ * mt_host.hpp — drop-in compatible C++ host of MADDY around the B200 C-ABI (internal API).
+ *
+ * The reference host (src/main.cpp, preparator.cpp, updater.cpp, configreader.cpp, pdbio.cpp,
+ * dcdio.cpp, xyzio.cpp) is a set of free functions over file-scope globals.  This host keeps
+ * the same observable behaviour — config.conf / forcefield / conditions keys, PDB/XYZ inputs,
+ * DCD + stdout outputs, the order of host events inside the step loop — but is re-entrant:
+ * all state lives in `mt::System`, and fatal conditions throw `mt::Fatal` (the `mt` executable
+ * turns that into the reference's "Fatal error!" + exit(-1), the Python binding into a status).
+ */
+#pragma once
+#include <cstdio>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "maddy_b200.h"
+
+namespace mt {
+
+struct Fatal : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+[[noreturn]] void die(const char *fmt, ...);
+
+// ---------------------------------------------------------------- config (configreader.cpp)
+class ParamTable {
+  public:
+    // replaces the table (configreader.cpp:31) and re-applies name=value overrides (:62-75)
+    void parse(const std::string &filename, const std::vector<std::string> &overrides);
+    void set(const std::string &name, const std::string &value, bool force);
+    bool raw(const std::string &name, std::string &value) const;
+
+    std::string masked(const std::string &name);                               // mandatory
+    std::string masked(const std::string &name, const std::string &def);       // with default
+    std::string masked_replace(const std::string &name, const std::string &replacement, const std::string &what);
+    int integer(const std::string &name);
+    int integer(const std::string &name, int def);
+    long long long_integer(const std::string &name, long def);
+    float real(const std::string &name);
+    float real(const std::string &name, float def);
+    int yesno(const std::string &name, int def, bool allow_default = true);
+    bool quiet = false;
+
+  private:
+    bool lookup(const std::string &name, const std::string *def, std::string &out);
+    std::string apply_mask(const std::string &token) const;
+    std::vector<std::pair<std::string, std::string>> items_;
+};
+
+// ---------------------------------------------------------------- PDB (pdbio.cpp)
+struct PDBAtom {
+    int id = 0;
+    char name[5] = {0}, chain = ' ', resName[4] = {0}, altLoc = ' ';
+    int resid = 0;
+    double x = 0, y = 0, z = 0, occupancy = 0, beta = 0;
+};
+struct PDB {
+    std::vector<PDBAtom> atoms;
+};
+void read_pdb(const std::string &filename, PDB &pdb, bool quiet = false);
+void write_pdb(const std::string &filename, const PDB &pdb, bool quiet = false);
+void append_pdb(const std::string &filename, const PDB &pdb, bool quiet = false);
+
+// ---------------------------------------------------------------- DCD (dcdio.cpp)
+struct DCDHeader {
+    int n_atoms = 0, nfile = 0, npriv = 0, nsavc = 0;
+    float delta = 0;
+    std::string remark1, remark2;
+};
+DCDHeader make_dcd_header(int n_atoms, int frame_count, int first_frame, float timestep, int dcd_freq);
+void dcd_write_header(FILE *f, const DCDHeader &h);
+void dcd_write_frame(FILE *f, int n, const float *x, const float *y, const float *z);
+bool dcd_read_header(FILE *f, DCDHeader &h);
+bool dcd_read_frame(FILE *f, int n, float *x, float *y, float *z);
+
+// ---------------------------------------------------------------- XYZ (xyzio.cpp)
+struct XYZAtom {
+    char name;
+    double x, y, z;
+};
+void read_xyz(const std::string &filename, std::vector<XYZAtom> &atoms, bool quiet = false);
+void write_xyz(const std::string &filename, const std::vector<XYZAtom> &atoms, bool quiet = false);
+
+// ---------------------------------------------------------------- system (preparator.cpp, globals)
+struct HostParams { // scalars of `Parameters` that only the host uses
+    long long steps = 0, firststep = 0, stride = 0;
+    int fix = 1;
+    bool tub_length = true, out_energy = true, out_force = false, is_restart = false;
+    bool is_const_conc = false, hydrolysis = false;
+    float conc = 0, khydro = 0, viscosity = 0;
+    long hydrostep = 0;
+    std::string coord_xyz, coord_ang, ff_file, cond_file, restartkey;
+    std::vector<std::string> dcd_xyz, dcd_ang, restart_xyz, restart_ang;
+    int n_gpus = 1; // extension key `n_gpus` (default 1): shard trajectories over this many devices
+};
+
+struct System {
+    maddy_params par{};
+    HostParams hp;
+    ParamTable table;
+    std::vector<std::string> overrides;
+    PDB pdb, pdb_ang, coordspdb;
+    DCDHeader dcd;
+    // coordinates / forces, AoS7 {x,y,z,fi,theta,psi,w} per (traj, monomer)   (globals r, f)
+    std::vector<float> r, f;
+    // topology (global `top`)
+    std::vector<int> harmonic_count, harmonic, longitudinal_count, longitudinal, lateral_count, lateral;
+    std::vector<unsigned char> fixed, extra;
+    std::vector<int> mon_type, gtp, on_tubule_cur, on_tubule_prev;
+    std::vector<double> energies; // [Ntr][7] per-trajectory sums of the last energy evaluation
+    bool quiet = false;           // suppress the reference's stdout chatter (tests / bench)
+    bool write_files = true;      // DCD / mt_len.dat / hydrolysis.pdb side effects
+    std::string workdir;          // relative output paths are taken relative to the cwd, like the reference
+    // timers (timer.cpp)
+    long initial_clock = 0, last_clock = 0;
+
+    maddy_topology topology_view(int traj_first = 0) const;
+};
+
+// initParameters (+ read_PDB, DCD headers, restart) — preparator.cpp:4-246
+void init_parameters(System &s, const std::string &config, const std::vector<std::string> &overrides);
+void assembly_init(System &s);                 // preparator.cpp:717-731
+void save_coord_pdb(System &s, const std::string &xyz, const std::string &ang); // :566-580
+void save_coord_dcd(System &s);                // :582-602
+void append_coord_pdb(System &s);              // :604-636
+void read_restart(System &s);                  // :664-684
+void write_restart(System &s, long long step); // :686-714
+
+// updater.cpp
+void mt_length(System &s, long long step, std::vector<int> &mt_len);
+int change_conc(System &s, std::vector<int> &delta, std::vector<int> &mt_len);
+void hydrolyse(System &s);
+void output_all_energies(System &s, long long step);
+void output_sum_force(System &s);
+void output_forces(System &s);
+void update(System &s, long long step, std::vector<int> &mt_len);
+void init_timer(System &s);
+
+// the step loop: compute() of compute_cuda.cu:1125-1260 over the C-ABI.
+// fused = false uses one C-ABI call per reference launch (force; integrate) — same results.
+struct ComputeStats {
+    long long steps = 0, launches = 0;
+    double h2d_bytes = 0, d2h_bytes = 0;
+};
+void compute(System &s, bool fused = true, ComputeStats *stats = nullptr);
+
+} // namespace mt
