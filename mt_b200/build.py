@@ -84,7 +84,7 @@ def build_oracle(force=False):
     if force or _stale(LIB_ORACLE, deps):
         LIB_ORACLE.parent.mkdir(parents=True, exist_ok=True)
         # -ffp-contract=off: the restatement states every rounding explicitly
-        _run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", f"-I{ROOT / 'include'}", "-o", LIB_ORACLE,
+        _run(["gcc", "-O2", "-std=gnu11", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", f"-I{ROOT / 'include'}", "-o", LIB_ORACLE,
               *srcs, "-lm"])
     return LIB_ORACLE
 
