@@ -1,0 +1,67 @@
+"""Host events of the step loop (updater.cpp): tubule length / on-tubule flags, hydrolysis, constant concentration."""
+import ctypes
+
+import numpy as np
+
+libc = ctypes.CDLL("libc.so.6")
+
+
+def test_mt_length_classification(rundir, load_system):
+    s = load_system(rundir(runnum=2))
+    c = s.coords
+    n = s.mt_length(1000)
+    assert n.tolist() == [520, 520] and (s.on_tubule_cur == 1).all()  # intact lattice: radius 8.12, theta 0
+    c[0, 10, 0] += 30.0          # radius beyond R_MT + 8 r_mon = 24.12
+    c[0, 11, 4] = 1.2            # theta beyond ANG_THRES (cos(theta) <= cos(1.0)); Coord order x,y,z,fi,theta,psi
+    c[1, 5, 0], c[1, 5, 1] = 0.5, 0.1  # radius below 1.0
+    n = s.mt_length(2000)
+    assert n.tolist() == [518, 519]
+    assert s.on_tubule_cur[0, 10] == 0 and s.on_tubule_cur[0, 11] == 0 and s.on_tubule_cur[1, 5] == 0
+
+
+def test_hydrolysis_uses_libc_rand_in_reference_order(rundir, load_system):
+    """2 % per on-tubule GTP dimer, loop i-outer / trajectory-inner, one rand() per candidate (updater.cpp:229-257)."""
+    s = load_system(rundir(runnum=3))
+    s.on_tubule_cur[:] = 1
+    s.on_tubule_prev[:] = 1
+    s.on_tubule_cur[2, 100:104] = 0   # not on tubule now -> not a candidate (and consumes no rand())
+    libc.srand(1234567)
+    s.hydrolyse()
+    got = s.gtp.copy()
+    # replay the stream
+    libc.srand(1234567)
+    exp = np.ones((3, 520), dtype=np.int32)
+    for i in range(0, 520, 2):
+        for tr in range(3):
+            if tr == 2 and 100 <= i < 104:
+                continue
+            if libc.rand() / 2147483647.0 < 0.02:
+                exp[tr, i] = exp[tr, i + 1] = 0
+    assert np.array_equal(got, exp) and 0 < (got == 0).sum() < 200
+    # GDP dimers that are off the tubule now and at the previous stride turn back to GTP, deterministically
+    idx = np.argwhere(got == 0)[0]
+    s.on_tubule_cur[idx[0], idx[1] - idx[1] % 2] = 0
+    s.on_tubule_prev[idx[0], idx[1] - idx[1] % 2] = 0
+    before = (s.gtp == 0).sum()
+    libc.srand(1)
+    s.hydrolyse()
+    assert s.gtp[idx[0], idx[1]] == 1
+
+
+def test_change_conc_inserts_reserve_dimers(rundir, load_system):
+    d = rundir("mt120_constconc", structure=("reserve", 20, 6), runnum=2)
+    s = load_system(d, ["is_const_conc=yes", "conc=30", "rep_r=20", "rep_h=60", "repulsive_walls=yes"])
+    assert s.extra.sum() == 2 * 78
+    mt_len = np.array([260, 260], dtype=np.int32)
+    libc.srand(7)
+    changed = s.change_conc(np.zeros(2, dtype=np.int32), mt_len)
+    # V = 3.14 r^2 h ; dimers wanted: conc * V * 6e-7
+    want = int(np.ceil(30 * 3.14 * 20 * 20 * 60 * 6e-7))
+    assert changed == 2 * want
+    freed = np.argwhere(s.extra[0] == 0)
+    freed = [i for i in freed.ravel() if i >= 260]
+    assert len(freed) == 2 * want
+    c = s.coords
+    for i in freed[::2]:
+        assert s.mon_type[i] == 0 and c[0, i, 0] ** 2 + c[0, i, 1] ** 2 <= 400.0
+        assert c[0, i, 2] == 60 + 0.0 + 12 and c[0, i + 1, 2] == c[0, i, 2] + 4 and c[0, i + 1, 0] == c[0, i, 0]

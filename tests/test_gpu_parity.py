@@ -1,0 +1,313 @@
+"""GPU parity tests: the sm_100a kernels, called through the C-ABI, against
+  (1) the golden dumps of the REFERENCE'S OWN KERNELS (tests/golden/ref_*.npz),
+  (2) the CPU oracle on the same seeded inputs,
+  (3) the live reference binaries (oracle/_ref/{ref_probe,mt}) when they travelled with the tree,
+  (4) size-independent properties at BASELINE sizes (520 x 256, 1560 x 64).
+
+Bars: seed table, RNG state, LJ lists and bond lists BIT-EXACT; forces |dF| <= 1e-3 + 1e-5 |F|; per-monomer
+energies 2e-5; one integrator step <= 2 float ulps of the coordinate; step windows |dxyz| <= 1e-3 nm,
+|dangle| <= 1e-4 rad (fp32 tolerance stated in BASELINE/north_star terms)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_npz
+from helpers import lists_equal, system_from_golden
+from mt_b200 import Engine, capi
+from mt_b200.capi import as_ptr
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["mt40", "mt120_gdp_barrier", "reserve_walls", "mt40_static"]
+F_ATOL, F_RTOL = 1e-3, 1e-5
+E_ATOL = 2e-5
+
+
+def ulps(a, b, floor=2e-7):
+    """max (|a-b| - floor) in units of the float32 spacing at max(|a|,|b|); `floor` absorbs the dt/gamma * dF term
+    of one step (2e-4 * 1e-3), which dominates for coordinates near zero where the spacing is tiny"""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    sp = np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32))
+    return float((np.maximum(np.abs(a.astype(np.float64) - b) - floor, 0) / sp).max())
+
+
+def engine_from_golden(g, rundir, load_system):
+    s = system_from_golden(g, rundir, load_system)
+    e = Engine(s)
+    e.upload_gtp(g["gtp"])
+    e.upload_on_tubule(g["ontub"])
+    return s, e
+
+
+def oracle_for(s, g=None):
+    from oracle.pyoracle import OracleState
+    o = OracleState(s)
+    if g is not None:
+        o._keep = (np.ascontiguousarray(g["gtp"]), np.ascontiguousarray(g["ontub"]))
+        o.top.gtp = as_ptr(o._keep[0], C.c_int)
+        o.top.on_tubule_cur = as_ptr(o._keep[1], C.c_int)
+    return o
+
+
+def rebuild(e, s):
+    if s.par.lj_on:
+        e.rebuild_lj()
+    if s.par.is_assembly:
+        e.rebuild_bonds()
+
+
+# ------------------------------------------------------------------ (1) golden dumps of the reference kernels
+@pytest.mark.parametrize("name", CASES)
+def test_initial_state_and_lists_bit_exact(name, rundir, load_system):
+    g = golden_npz(name)
+    s, e = engine_from_golden(g, rundir, load_system)
+    assert np.array_equal(e.rng_state(), g["seeds0"])
+    assert np.array_equal(e.coords()[..., :6], g["coords0"][..., :6])  # includes the angle wrap of initIntegration
+    rebuild(e, s)
+    assert lists_equal(*e.download_list(capi.LIST_LJ), g["ljcnt0"], g["lj0"])
+    assert lists_equal(*e.download_list(capi.LIST_LONGITUDINAL), g["longcnt0"], g["long0"])
+    assert lists_equal(*e.download_list(capi.LIST_LATERAL), g["latcnt0"], g["lat0"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forces_energies_one_step(name, rundir, load_system):
+    g = golden_npz(name)
+    s, e = engine_from_golden(g, rundir, load_system)
+    rebuild(e, s)
+    e.force()
+    F = e.forces()
+    assert np.allclose(F[..., :6], g["forces0"][..., :6], rtol=F_RTOL, atol=F_ATOL), np.abs(F[..., :6] - g["forces0"][..., :6]).max()
+    et, em = e.energies(per_monomer=True)
+    assert np.allclose(em, g["energy0"], rtol=1e-6, atol=E_ATOL), np.abs(em - g["energy0"]).max()
+    assert np.allclose(et, g["energy0"].sum(axis=1), rtol=1e-9, atol=1e-6)
+    e.integrate()
+    c1 = e.coords()
+    assert ulps(c1[..., :6], g["coords1"][..., :6]) <= 2.0
+    assert np.abs(e.forces()).max() == 0.0  # the integrator zeroes the forces (compute_cuda.cu:966-972)
+    # second force evaluation on the reference's own step-1 coordinates
+    e.upload_coords(g["coords1"])
+    e.force()
+    F1 = e.forces()
+    assert np.allclose(F1[..., :6], g["forces1"][..., :6], rtol=F_RTOL, atol=F_ATOL), np.abs(F1[..., :6] - g["forces1"][..., :6]).max()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fused_window_against_reference_trajectory(name, rundir, load_system):
+    g = golden_npz(name)
+    s, e = engine_from_golden(g, rundir, load_system)
+    window = int(g["window"])
+    e.run(0, window)
+    c = e.coords()
+    assert np.array_equal(e.rng_state(), g["seeds_end"])  # integer stream: bit-exact
+    assert np.abs(c[..., :3] - g["coords_end"][..., :3]).max() < 1e-3
+    assert np.abs(c[..., 3:6] - g["coords_end"][..., 3:6]).max() < 1e-4
+
+
+def test_tea_against_reference(rundir, load_system):
+    g = golden_npz("tea")
+    s, e = engine_from_golden(g, rundir, load_system)
+    rebuild(e, s)
+    e.force()
+    assert np.allclose(e.forces()[..., :6], g["forces0"][..., :6], rtol=F_RTOL, atol=F_ATOL)
+    e.tea_update(0)
+    e.tea_integrate()
+    c1 = e.coords()
+    assert np.abs(c1[..., :3] - g["coords1"][..., :3]).max() < 2e-5
+    assert np.abs(c1[..., 3:6] - g["coords1"][..., 3:6]).max() < 2e-6
+    freq = s.par.ljpairsupdatefreq
+    for step in range(1, int(g["window"])):
+        if step % freq == 0:
+            rebuild(e, s)
+        e.force()
+        e.tea_update(step)
+        e.tea_integrate()
+    assert np.array_equal(e.rng_state(), g["seeds_end"])
+    c = e.coords()
+    assert np.abs(c[..., :3] - g["coords_end"][..., :3]).max() < 1e-3
+    assert np.abs(c[..., 3:6] - g["coords_end"][..., 3:6]).max() < 1e-4
+
+
+# ------------------------------------------------------------------ (2) the CPU oracle on seeded inputs
+@pytest.mark.parametrize("case,ntr,over", [
+    ("mt40_single", 3, ["hydrolysis=no"]),
+    ("mt40_single", 2, ["hydrolysis=no", "a_barr_long=3.4", "a_barr_lat=1.9", "seam_coeff=2", "LJ_on=no"]),
+    ("mt40_single", 2, ["hydrolysis=no", "is_assembly=no", "repulsive_walls=yes", "rep_r=7.5", "rep_h=100", "rep_leftborder=5"]),
+])
+def test_against_oracle_on_perturbed_inputs(case, ntr, over, rundir, load_system):
+    s = load_system(rundir(case, runnum=ntr), over)
+    rng = np.random.default_rng(11)
+    c0 = s.coords.copy()
+    c0[..., :3] += rng.normal(0, 0.05, c0[..., :3].shape).astype(np.float32)
+    c0[..., 3:6] += rng.normal(0, 0.02, c0[..., 3:6].shape).astype(np.float32)
+    e = Engine(s, coords=c0)
+    o = oracle_for(s)
+    o.coords[:] = e.coords()
+    gtp = np.ones((ntr, s.Ntot), dtype=np.int32)
+    gtp[:, 100:140] = 0
+    on = (rng.random((ntr, s.Ntot)) < 0.5).astype(np.int32)
+    e.upload_gtp(gtp)
+    e.upload_on_tubule(on)
+    o._keep = (gtp, on)
+    o.top.gtp, o.top.on_tubule_cur = as_ptr(gtp, C.c_int), as_ptr(on, C.c_int)
+    rebuild(e, s)
+    if s.par.lj_on:
+        o.rebuild_lj()
+        assert lists_equal(*e.download_list(capi.LIST_LJ), o.lj_count, o.lj)
+    if s.par.is_assembly:
+        o.rebuild_bonds()
+    assert lists_equal(*e.download_list(capi.LIST_LONGITUDINAL), o.long_count, o.long)
+    assert lists_equal(*e.download_list(capi.LIST_LATERAL), o.lat_count, o.lat)
+    e.force()
+    F, OF = e.forces(), o.force()
+    assert np.allclose(F[..., :6], OF[..., :6], rtol=1e-4, atol=2e-2), np.abs(F - OF).max()  # libm vs MUFU: 10x looser
+    et, em = e.energies(per_monomer=True)
+    assert np.allclose(em, o.energies(), rtol=1e-5, atol=2e-4)
+    e.run(0, 30, skip_first_rebuild=True)
+    o.run(0, 30, skip_first_rebuild=True)
+    assert np.array_equal(e.rng_state(), o.rng)
+    c = e.coords()
+    assert np.abs(c[..., :3] - o.coords[..., :3]).max() < 2e-3 and np.abs(c[..., 3:6] - o.coords[..., 3:6]).max() < 2e-3
+
+
+# ------------------------------------------------------------------ (3) live reference binaries
+def test_live_reference_mt_binary_dcd(rundir, load_system):
+    """The UNMODIFIED reference executable with stride 1: its DCD frames are the golden trajectory."""
+    from oracle import refprobe
+    import mt_b200
+    if not refprobe.REF_MT.exists():
+        pytest.skip("oracle/_ref/mt did not travel with the tree")
+    steps = 30
+    d = rundir("mt40_single", runnum=2, steps=steps, stride=1)
+    refprobe.run_reference_mt(d, ["hydrolysis=no", "tubule_length=no", "output_energy=no"])
+    s = load_system(d, ["hydrolysis=no"])
+    e = Engine(s)
+    N = s.Ntot
+    frames = [np.concatenate([mt_b200.read_dcd(d / "dcd" / f"run_{t}.dcd")[None], mt_b200.read_dcd(d / "dcd" / f"run_{t}.dcd_ang")[None]])
+              for t in range(2)]
+    assert frames[0].shape == (2, steps, N, 3)
+    worst = 0.0
+    for step in range(steps):
+        c = e.coords()
+        for t in range(2):
+            xyz, ang = frames[t][0, step], frames[t][1, step]  # ang file stores (fi, psi, theta)
+            worst = max(worst, np.abs(c[t, :, :3] - xyz).max())
+            assert np.abs(c[t, :, :3] - xyz).max() < 1e-3
+            assert np.abs(c[t, :, [3, 5, 4]].T - ang).max() < 1e-4
+        e.run(step, 1)
+    assert worst < 1e-3
+
+
+def test_live_probe_long_window(rundir, load_system):
+    """1000-step window against the reference kernels (SURVEY.md 8c tolerance: 1e-3 nm / 1e-4 rad)."""
+    from oracle import refprobe
+    if not refprobe.REF_PROBE.exists():
+        pytest.skip("oracle/_ref/ref_probe did not travel with the tree")
+    window = 1000
+    d = rundir("mt40_single", runnum=2, steps=window, stride=100000)
+    dump = refprobe.run_probe(d, d / "probe.bin", window, 0, ["hydrolysis=no"])
+    s = load_system(d, ["hydrolysis=no"])
+    e = Engine(s)
+    e.run(0, window)
+    c, r = e.coords(), dump.coords(window)
+    assert np.array_equal(e.rng_state(), dump.seeds(window))
+    dx, da = np.abs(c[..., :3] - r[..., :3]).max(), np.abs(c[..., 3:6] - r[..., 3:6]).max()
+    print(f"1000-step window vs reference kernels: |dxyz|max={dx:.3e} nm, |dang|max={da:.3e} rad")
+    assert dx < 1e-3 and da < 1e-4
+    # the lists the fused loop rebuilt in-kernel at step 980 equal the reference's
+    cnt, _ = e.download_list(capi.LIST_LJ)
+    assert np.array_equal(cnt, dump.ints("ljcnt", 980))
+    lc, le = e.download_list(capi.LIST_LONGITUDINAL)
+    tc, te = e.download_list(capi.LIST_LATERAL)
+    rlc, rle, rtc, rte = dump.bonds(980)
+    assert lists_equal(lc, le, rlc, rle) and lists_equal(tc, te, rtc, rte)
+
+
+# ------------------------------------------------------------------ (4) properties at BASELINE sizes
+@pytest.mark.parametrize("case,ntr,steps", [("mt40_ensemble", 256, 60), ("mt120_disassembly", 64, 40), ("mt120_constconc", 16, 40)])
+def test_fused_equals_step_granular_bitwise(case, ntr, steps, rundir, load_system):
+    s = load_system(rundir(case, runnum=ntr), ["hydrolysis=no", "is_const_conc=no"])
+    a, b = Engine(s), Engine(s)
+    a.run(0, steps)
+    freq = s.par.ljpairsupdatefreq
+    for step in range(steps):
+        if step % freq == 0:
+            rebuild(b, s)
+        b.force()
+        b.integrate()
+    ca, cb = a.coords(), b.coords()
+    assert np.isfinite(ca).all()
+    assert np.array_equal(ca, cb) and np.array_equal(a.rng_state(), b.rng_state())
+    for kind in (capi.LIST_LJ, capi.LIST_LONGITUDINAL, capi.LIST_LATERAL):
+        assert lists_equal(*a.download_list(kind), *b.download_list(kind))
+    # split windows == one window
+    c = Engine(s)
+    c.run(0, 17)
+    c.run(17, 23)
+    c.run(40, steps - 40)
+    assert np.array_equal(c.coords(), ca)
+
+
+def test_shard_invariance_and_trajectory_independence(rundir, load_system):
+    """A shard [first, first+k) of a larger ensemble reproduces exactly those trajectories (global RNG stream ids)."""
+    s = load_system(rundir("mt40_ensemble", runnum=12), ["hydrolysis=no"])
+    full = Engine(s)
+    full.run(0, 45)
+    cf = full.coords()
+    for first, k in ((0, 5), (5, 4), (9, 3)):
+        sh = Engine(s, traj_first=first, n_tr_local=k)
+        sh.run(0, 45)
+        assert np.array_equal(sh.coords(), cf[first:first + k])
+    # identical initial structures but different noise: trajectories differ from one another
+    assert not np.array_equal(cf[0], cf[1])
+
+
+def test_newton_third_law_list_symmetry_and_energy_reduction(rundir, load_system):
+    s = load_system(rundir("mt40_ensemble", runnum=32), ["hydrolysis=no"])
+    e = Engine(s)
+    e.run(0, 40)
+    rebuild(e, s)
+    e.force()
+    F = e.forces()
+    assert np.abs(F[..., :3].sum(axis=1)).max() < 0.05  # pair potentials, no walls
+    cnt, ent = e.download_list(capi.LIST_LJ)
+    for t in (0, 31):
+        A = np.zeros((s.Ntot, s.Ntot), dtype=bool)
+        for i in range(s.Ntot):
+            A[i, ent[t, i, :cnt[t, i]]] = True
+        assert np.array_equal(A, A.T) and not A.diagonal().any()
+    et, em = e.energies(per_monomer=True)
+    assert np.allclose(et, em.sum(axis=1), rtol=1e-12, atol=1e-9)  # warp-shuffle reduction == host sum of doubles
+
+
+def test_list_upload_download_roundtrip_and_encoding(rundir, load_system):
+    s = load_system(rundir("mt40_single", runnum=2), ["hydrolysis=no"])
+    e = Engine(s)
+    rebuild(e, s)
+    tc, te = e.download_list(capi.LIST_LATERAL)
+    # monomer 40 is laterally bonded to monomer 0: stored as the ZERO sentinel, never as +-0 (compute_cuda.cu:646-658)
+    assert capi.ZERO_SENTINEL in np.abs(te[0, 40, :tc[0, 40]]).tolist()
+    lc, le = e.download_list(capi.LIST_LONGITUDINAL)
+    e.force()
+    F0 = e.forces()
+    e.upload_list(capi.LIST_LATERAL, tc, te)
+    e.upload_list(capi.LIST_LONGITUDINAL, lc, le)
+    jc, je = e.download_list(capi.LIST_LJ)
+    e.upload_list(capi.LIST_LJ, jc, je)
+    assert lists_equal(*e.download_list(capi.LIST_LATERAL), tc, te)
+    e.force()
+    assert np.array_equal(e.forces(), F0)
+
+
+def test_overflow_and_bad_arguments_fail_loudly(rundir, load_system):
+    from mt_b200 import MaddyError
+    s = load_system(rundir("mt40_single", runnum=1), ["hydrolysis=no", "LJPairsCutoff=40"])
+    e = Engine(s)
+    e.rebuild_lj()
+    with pytest.raises(MaddyError) as err:
+        e.sync()
+    assert err.value.code == -4 and "overflow" in str(err.value)
+    with pytest.raises(MaddyError) as err:
+        Engine(s, traj_first=1)  # empty shard
+    assert err.value.code == -1
