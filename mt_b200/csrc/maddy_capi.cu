@@ -18,7 +18,7 @@
 #include "maddy_kernels.cuh"
 
 namespace maddy {
-cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int shape, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 } // namespace maddy
@@ -30,7 +30,7 @@ struct maddy_handle {
     DevSys a;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int mpt = 1, threads = 32, nbuf = 2;
+    int mpt = 1, threads = 32, nbuf = 2, near_cap = 0, shape = 0;
     size_t smem = 0;
     CutTest cut_pairs, cut_force;
     std::string err;
@@ -105,6 +105,11 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
     k.ops = ops;
     k.run_flags = 0;
     k.nbuf = h->nbuf;
+    k.near_cap = h->near_cap;
+    {
+        const float rb = fmaxf(h->p.lj_on ? h->p.ljpairscutoff : 0.f, 7.0f) + MD_CAND_SKIN;
+        k.rcand2 = rb * rb;
+    }
     k.cut_pairs = h->cut_pairs;
     k.cut_force = h->cut_force;
     return k;
@@ -134,7 +139,7 @@ static int sync_and_check(maddy_handle *h)
 static int launch(maddy_handle *h, const KArgs &k)
 {
     CU(h, cudaSetDevice(h->p.device));
-    cudaError_t e = launch_traj_kernel(k, h->mpt, h->threads, h->smem, h->stream);
+    cudaError_t e = launch_traj_kernel(k, h->mpt, h->shape, h->threads, h->smem, h->stream);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "trajectory kernel launch (ops=%u): %s", k.ops, cudaGetErrorString(e));
     h->launches++;
     return MADDY_OK;
@@ -260,8 +265,23 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             goto bad;
         }
         h->threads = (((N + h->mpt - 1) / h->mpt) + 31) & ~31;
-        h->nbuf = ((size_t)2 * 64 * N <= 100 * 1024) ? 2 : 1;
-        h->smem = (size_t)h->nbuf * 64 * N;
+        h->shape = 0;
+        // shared memory: stage (64 B per monomer, double-buffered when small), tile boxes, near list
+        {
+            const size_t budget = 200 * 1024;
+            const size_t tiles = (size_t)2 * 16 * ((N + MD_TILE - 1) / MD_TILE);
+            h->nbuf = ((size_t)2 * 64 * N <= 100 * 1024) ? 2 : 1;
+            const size_t stage = (size_t)h->nbuf * 64 * N;
+            size_t cap = (budget - stage - tiles - N - 64) / ((size_t)2 * N);
+            if (cap > 32) cap = 32;
+            h->near_cap = cap >= 12 ? (int)cap : 0; // too little room: all-pairs path, lists from HBM only
+            if (getenv("MADDY_NO_NEAR")) h->near_cap = 0;
+            h->smem = stage + tiles + (size_t)h->near_cap * N * 2 + N + 64;
+            h->smem = (h->smem + 15) & ~(size_t)15;
+            // small trajectories: 9-warp CTAs, two per SM (needs 2 x smem <= 227 KB)
+            const char *force_shape = getenv("MADDY_SHAPE");
+            if (N <= MD_MAX_THREADS && 2 * (h->smem + 2048) <= 227 * 1024 && !(force_shape && force_shape[0] == '0')) h->shape = 1;
+        }
         h->cut_pairs = make_cut(par->ljpairscutoff);
         h->cut_force = make_cut(MD_LJ_FORCE_CUTOFF);
 
@@ -281,6 +301,11 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         CK(dalloc(h, &a.bcnt, (size_t)ntr * 2 * a.Npad));
         CK(dalloc(h, &a.lj, par->lj_on ? (size_t)ntr * MADDY_LJ_CAPACITY * a.Npad : 1));
         CK(dalloc(h, &a.ljcnt, (size_t)ntr * a.Npad));
+        CK(dalloc(h, &a.cand, h->near_cap > 0 ? (size_t)ntr * MD_CAND_CAPACITY * a.Npad : 1));
+        CK(dalloc(h, &a.candcnt, (size_t)ntr * a.Npad));
+        CK(dalloc(h, &a.cpos, n));
+        CK(dalloc(h, &a.cand_valid, (size_t)ntr));
+        CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
         CK(dalloc(h, &a.en_mono, n * 7));
         CK(dalloc(h, &a.en_traj, (size_t)ntr * 7));
         CK(dalloc(h, &a.status, 1));
@@ -436,6 +461,7 @@ extern "C" int maddy_upload_coords(maddy_handle *h, const float *aos)
     const size_t n = (size_t)h->a.ntr * h->a.N;
     std::vector<float4> pos, ang;
     aos_to_soa(aos, n, pos, ang, false);
+    CU(h, cudaMemsetAsync(h->a.cand_valid, 0, (size_t)h->a.ntr * sizeof(int), h->stream)); // candidate lists refer to the old positions
     CU(h, cudaMemcpyAsync(h->a.pos, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->a.ang, ang.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -471,6 +497,7 @@ extern "C" int maddy_upload_extra(maddy_handle *h, const unsigned char *extra)
     const size_t n = (size_t)h->a.ntr * h->a.N;
     std::vector<uint8_t> v(n);
     for (size_t q = 0; q < n; q++) v[q] = extra[q] != 0;
+    if (h->a.cand_valid) cudaMemsetAsync(h->a.cand_valid, 0, (size_t)h->a.ntr * sizeof(int), h->stream); // rows of former extras are empty
     return upload_bytes(h, h->a.extra, v);
 }
 
@@ -480,9 +507,12 @@ static inline int long_to_ref(unsigned code)
     int j = (int)(code >> 1);
     return (code & 1u) ? -j : j;
 }
-static inline int lat_to_ref(unsigned code)
+// dynamic lists (pairs_kernel) write the ZERO sentinel for +-0; the static host builder
+// (preparator.cpp:550-554) stores a plain 0, which compute_kernel then decodes on its `j <= 0` branch
+static inline int lat_to_ref(unsigned code, bool dynamic)
 {
     int j = (int)(code >> 1);
+    if (j == 0 && !dynamic) return 0;
     if (code & 1u) return j ? -j : -MADDY_ZERO_SENTINEL;
     return j ? j : MADDY_ZERO_SENTINEL;
 }
@@ -531,7 +561,7 @@ extern "C" int maddy_download_list(maddy_handle *h, int kind, int *counts, int *
                     continue;
                 }
                 const unsigned code = bl[((size_t)t * rows + row0 + k) * Npad + i];
-                o[k] = lat ? lat_to_ref(code) : long_to_ref(code);
+                o[k] = lat ? lat_to_ref(code, h->p.is_assembly != 0) : long_to_ref(code);
             }
         }
     return MADDY_OK;

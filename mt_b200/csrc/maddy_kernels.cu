@@ -45,6 +45,14 @@ __device__ __forceinline__ Stage stage_at(float4 *smem, int N, int buf)
     return s;
 }
 
+struct Near { // shared-memory near list of the fused loop (see MD_NEAR_R2 in maddy_kernels.cuh)
+    uint16_t *list; // [cap][N], k-major
+    uint8_t *cnt;   // [N]
+    float4 *tlo, *thi; // bounding boxes of tiles of MD_TILE consecutive monomers
+    int cap, ntiles;
+    bool ok;        // CTA-uniform: the near list is valid for this step
+};
+
 struct Mono { // register-resident state of one monomer
     float x, y, z, fi, psi, theta;
     uint4 rx, ra;
@@ -70,7 +78,7 @@ __device__ __forceinline__ void publish(const Stage &s, int i, const Mono &m, co
 
 // ------------------------------------------------------------------ forces
 // Generalized force on monomer i (non-extra) from the staged trajectory.
-__device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, int traj, int i, const Mono &m,
+__device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, const Near &near, int traj, int i, const Mono &m,
                                             const LatSite &ls)
 {
     const maddy_params &p = k.p;
@@ -189,24 +197,44 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, int 
 
     // ---- LJ r^-6 repulsion from the Verlet list (compute_cuda.cu:470-495)
     if (p.lj_on) {
-        const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
-        const int n = a.ljcnt[(size_t)traj * a.Npad + i];
         const float amp = p.ljscale * p.ljsigma6;
         float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (near.ok) {
+            // shared-memory near list: the listed pairs that can be inside the 6-nm cut-off (see MD_NEAR_R2)
+            const int n = near.cnt[i];
+            const uint16_t *nl = near.list + i;
+            for (int kk = 0; kk < n; kk++) {
+                const unsigned e = nl[kk * a.N];
+                if (!(e & MD_NEAR_LJ_FLAG)) continue;
+                const float4 Pj = s.P[e & 0x7fffu];
+                const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
+                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
+                    const float inv = 1.0f / sf;
+                    const float inv2 = inv * inv;
+                    const float c = amp * (6.0f * (inv2 * inv2)); // 6 / dr^8
+                    fx += c * dx;
+                    fy += c * dy;
+                    fz += c * dz;
+                }
+            }
+        } else {
+            const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+            const int n = a.ljcnt[(size_t)traj * a.Npad + i];
 #pragma unroll 4
-        for (int kk = 0; kk < n; kk++) {
-            const int j = lj[(size_t)kk * a.Npad];
-            const float4 Pj = s.P[j];
-            const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
-            const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
-                const float inv = 1.0f / sf;
-                const float inv2 = inv * inv;
-                const float df = 6.0f * (inv2 * inv2); // 6 / dr^8
-                const float c = amp * df;
-                fx += c * dx;
-                fy += c * dy;
-                fz += c * dz;
+            for (int kk = 0; kk < n; kk++) {
+                const int j = lj[(size_t)kk * a.Npad];
+                const float4 Pj = s.P[j];
+                const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
+                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
+                    const float inv = 1.0f / sf;
+                    const float inv2 = inv * inv;
+                    const float c = amp * (6.0f * (inv2 * inv2)); // 6 / dr^8
+                    fx += c * dx;
+                    fy += c * dy;
+                    fz += c * dz;
+                }
             }
         }
         f.x += fx;
@@ -349,105 +377,340 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
 }
 
 // ------------------------------------------------------------------ list rebuild
-// One pass over all j of the staged trajectory for the MPT monomers of this thread:
-// LJ Verlet list (compute_cuda.cu:913-940) and dynamic bond lists (compute_cuda.cu:527-674).
-template <int MPT>
-__device__ __forceinline__ void rebuild_lists(const KArgs &k, const Stage &s, int traj, const Mono (&mo)[MPT],
-                                              const int (&idx)[MPT], unsigned ops)
+// Dynamic bond candidates of monomer i against monomer j (pairs_kernel, compute_cuda.cu:564-669):
+// longitudinal (other monomer type, end sites opposite to the dimer bond) then the two lateral pairings.
+struct BondOut {
+    uint16_t *col; // &bl[traj][0][i]
+    int nlong, nlat, status;
+};
+__device__ __forceinline__ void bond_candidates(const DevSys &a, const Stage &s, int i, int j, const Mono &m, int hraw, const float4 &Pj,
+                                                const float4 &Ei, const float4 &L1i, const float4 &L2i, BondOut &o)
 {
-    const maddy_params &p = k.p;
+    const float4 Ej = s.E[j], L1j = s.L1[j], L2j = s.L2[j];
+    const int jf = __float_as_int(L2j.w);
+    if (MF_TYPE(m.flags) != (jf & 0x7f)) {
+        const float sg = hraw < 0 ? -1.0f : 1.0f; // R_MON / r_mon (compute_cuda.cu:548-551)
+        F3 d;
+        d.x = (Pj.x - m.x) - sg * Ei.x - sg * Ej.x;
+        d.y = (Pj.y - m.y) - sg * Ei.y - sg * Ej.y;
+        d.z = (Pj.z - m.z) - sg * Ei.z - sg * Ej.z;
+        if (site_distance(d) < MD_PAIR_CUTOFF) {
+            // stored as +j when harmonic < 0, -j otherwise; -0 == 0 loses its sign (compute_cuda.cu:588-592)
+            const unsigned neg = (hraw < 0 || j == 0) ? 0u : 1u;
+            if (o.nlong < a.capLong) o.col[(size_t)o.nlong * a.Npad] = (uint16_t)((j << 1) | neg);
+            else o.status |= ST_LONG_OVERFLOW;
+            o.nlong++;
+        }
+    }
+    // lateral: (i:p1, j:p2) stored negative, then (i:p2, j:p1) stored positive (compute_cuda.cu:612-661)
+    F3 d;
+    d.x = (Pj.x - m.x) - L1i.x + L2j.x;
+    d.y = (Pj.y - m.y) - L1i.y + L2j.y;
+    d.z = (Pj.z - m.z) - L1i.z + L2j.z;
+    if (site_distance(d) < MD_PAIR_CUTOFF) {
+        if (o.nlat < a.capLat) o.col[(size_t)(a.capLong + o.nlat) * a.Npad] = (uint16_t)((j << 1) | 1u);
+        else o.status |= ST_LAT_OVERFLOW;
+        o.nlat++;
+    }
+    d.x = (Pj.x - m.x) - L2i.x + L1j.x;
+    d.y = (Pj.y - m.y) - L2i.y + L1j.y;
+    d.z = (Pj.z - m.z) - L2i.z + L1j.z;
+    if (site_distance(d) < MD_PAIR_CUTOFF) {
+        if (o.nlat < a.capLat) o.col[(size_t)(a.capLong + o.nlat) * a.Npad] = (uint16_t)(j << 1);
+        else o.status |= ST_LAT_OVERFLOW;
+        o.nlat++;
+    }
+}
+
+// General path: one pass over ALL j for the MPT monomers of this thread (LJ Verlet list,
+// compute_cuda.cu:913-940, and bond lists).  Used by the step-granular entry points when the near
+// list is disabled and as the fallback when a near list overflows.
+template <int MPT>
+__device__ __forceinline__ void rebuild_lists_all_pairs(const KArgs &k, const Stage &s, int traj, const Mono (&mo)[MPT],
+                                                        const int (&idx)[MPT], unsigned ops)
+{
     const DevSys &a = k.a;
     const int N = a.N;
     const bool do_lj = (ops & OP_REBUILD_LJ) != 0;
     const bool do_b = (ops & OP_REBUILD_BONDS) != 0;
-
-    int nlj[MPT], nlong[MPT], nlat[MPT], hraw[MPT];
-    bool act[MPT];
-    float4 Ei[MPT], L1i[MPT], L2i[MPT];
-#pragma unroll
-    for (int t = 0; t < MPT; t++) {
-        nlj[t] = nlong[t] = nlat[t] = 0;
-        act[t] = idx[t] < N && !(mo[t].flags & MF_EXTRA);
-        hraw[t] = 0;
-        if (idx[t] < N) {
-            hraw[t] = a.harm[a.maxH * idx[t]]; // first entry, whatever harmonicCount says (compute_cuda.cu:548)
-            Ei[t] = s.E[idx[t]];
-            L1i[t] = s.L1[idx[t]];
-            L2i[t] = s.L2[idx[t]];
-        }
-    }
     uint16_t *ljb = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad;
-    uint16_t *blb = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad;
     int status = 0;
-
-    for (int j = 0; j < N; j++) {
-        const float4 Pj = s.P[j];
-#pragma unroll
-        for (int t = 0; t < MPT; t++) {
-            if (!act[t]) continue;
-            const int i = idx[t];
-            const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
-            const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (do_lj && i != j && inside_cut(k.cut_pairs, dx, dy, dz, sf)) {
-                if (nlj[t] < MADDY_LJ_CAPACITY) ljb[(size_t)nlj[t] * a.Npad + i] = (uint16_t)j;
-                else status |= ST_LJ_OVERFLOW;
-                nlj[t]++;
-            }
-            if (do_b && sf < MD_BOND_PREFILTER2 && i != j) {
-                const int hp = hraw[t] < 0 ? -hraw[t] : hraw[t];
-                if (hp == j) continue;
-                const float4 Ej = s.E[j], L1j = s.L1[j], L2j = s.L2[j];
-                const int jf = __float_as_int(L2j.w);
-                // longitudinal candidate: other monomer type, end sites opposite to the dimer bond
-                if (MF_TYPE(mo[t].flags) != (jf & 0x7f)) {
-                    const float sg = hraw[t] < 0 ? -1.0f : 1.0f; // R_MON / r_mon (compute_cuda.cu:548-551)
-                    F3 d;
-                    d.x = (Pj.x - mo[t].x) - sg * Ei[t].x - sg * Ej.x;
-                    d.y = (Pj.y - mo[t].y) - sg * Ei[t].y - sg * Ej.y;
-                    d.z = (Pj.z - mo[t].z) - sg * Ei[t].z - sg * Ej.z;
-                    if (site_distance(d) < MD_PAIR_CUTOFF) {
-                        // stored as +j when harmonic < 0, -j otherwise; -0 == 0 loses its sign (compute_cuda.cu:588-592)
-                        const unsigned neg = (hraw[t] < 0 || j == 0) ? 0u : 1u;
-                        if (nlong[t] < a.capLong) blb[(size_t)nlong[t] * a.Npad + i] = (uint16_t)((j << 1) | neg);
-                        else status |= ST_LONG_OVERFLOW;
-                        nlong[t]++;
-                    }
-                }
-                // lateral candidates: (i:p1, j:p2) stored negative, then (i:p2, j:p1) stored positive
-                {
-                    F3 d;
-                    d.x = (Pj.x - mo[t].x) - L1i[t].x + L2j.x;
-                    d.y = (Pj.y - mo[t].y) - L1i[t].y + L2j.y;
-                    d.z = (Pj.z - mo[t].z) - L1i[t].z + L2j.z;
-                    if (site_distance(d) < MD_PAIR_CUTOFF) {
-                        if (nlat[t] < a.capLat) blb[(size_t)(a.capLong + nlat[t]) * a.Npad + i] = (uint16_t)((j << 1) | 1u);
-                        else status |= ST_LAT_OVERFLOW;
-                        nlat[t]++;
-                    }
-                    d.x = (Pj.x - mo[t].x) - L2i[t].x + L1j.x;
-                    d.y = (Pj.y - mo[t].y) - L2i[t].y + L1j.y;
-                    d.z = (Pj.z - mo[t].z) - L2i[t].z + L1j.z;
-                    if (site_distance(d) < MD_PAIR_CUTOFF) {
-                        if (nlat[t] < a.capLat) blb[(size_t)(a.capLong + nlat[t]) * a.Npad + i] = (uint16_t)(j << 1);
-                        else status |= ST_LAT_OVERFLOW;
-                        nlat[t]++;
-                    }
-                }
-            }
-        }
-    }
 #pragma unroll
     for (int t = 0; t < MPT; t++) {
-        if (idx[t] >= N) continue;
         const int i = idx[t];
-        if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj[t], MADDY_LJ_CAPACITY);
+        if (i >= N) continue;
+        int nlj = 0;
+        BondOut bo;
+        bo.col = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
+        bo.nlong = bo.nlat = bo.status = 0;
+        if (!(mo[t].flags & MF_EXTRA)) {
+            const int hraw = a.harm[a.maxH * i]; // first entry, whatever harmonicCount says (compute_cuda.cu:548)
+            const int hp = hraw < 0 ? -hraw : hraw;
+            const float4 Ei = s.E[i], L1i = s.L1[i], L2i = s.L2[i];
+            for (int j = 0; j < N; j++) {
+                const float4 Pj = s.P[j];
+                const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
+                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (i == j) continue;
+                if (do_lj && inside_cut(k.cut_pairs, dx, dy, dz, sf)) {
+                    if (nlj < MADDY_LJ_CAPACITY) ljb[(size_t)nlj * a.Npad + i] = (uint16_t)j;
+                    else status |= ST_LJ_OVERFLOW;
+                    nlj++;
+                }
+                if (do_b && sf < MD_BOND_PREFILTER2 && hp != j) bond_candidates(a, s, i, j, mo[t], hraw, Pj, Ei, L1i, L2i, bo);
+            }
+        }
+        if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj, MADDY_LJ_CAPACITY);
         if (do_b) {
             uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
-            bc[0] = (uint8_t)min(nlong[t], a.capLong);
-            bc[a.Npad] = (uint8_t)min(nlat[t], a.capLat);
+            bc[0] = (uint8_t)min(bo.nlong, a.capLong);
+            bc[a.Npad] = (uint8_t)min(bo.nlat, a.capLat);
         }
+        status |= bo.status;
     }
     if (status) atomicOr(a.status, status);
+}
+
+// Bounding boxes of tiles of MD_TILE consecutive monomers (caller syncs afterwards).
+__device__ __forceinline__ void compute_tiles(const Stage &s, const Near &near, int N)
+{
+    for (int t = threadIdx.x; t < near.ntiles; t += blockDim.x) {
+        const int j0 = t * MD_TILE, j1 = min(N, j0 + MD_TILE);
+        float4 p = s.P[j0];
+        float lx = p.x, ly = p.y, lz = p.z, hx = p.x, hy = p.y, hz = p.z;
+        for (int j = j0 + 1; j < j1; j++) {
+            p = s.P[j];
+            lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
+            hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
+        }
+        near.tlo[t] = make_float4(lx, ly, lz, 0.f);
+        near.thi[t] = make_float4(hx, hy, hz, 0.f);
+    }
+}
+
+// Fast path, phase 1a (rare): tile-culled scan that builds the CANDIDATE list.  Every lane walks ITS OWN
+// sequence of tiles whose bounding box is within the candidate radius (lanes of a warp sit far apart along
+// the protofilament, so a warp-uniform tile loop would visit nearly every tile); tiles are visited in
+// ascending order, so candidates come out in ascending j like the reference's all-pairs loop.
+// Returns true if a candidate list overflowed.
+template <int MPT>
+__device__ __forceinline__ bool scan_candidates(const KArgs &k, const Stage &s, const Near &near, int traj, const Mono (&mo)[MPT],
+                                                const int (&idx)[MPT])
+{
+    const DevSys &a = k.a;
+    const int N = a.N;
+    const float rc2 = k.rcand2;
+    bool ovf = false;
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int i = idx[t];
+        if (i >= N) continue;
+        int nc = 0;
+        if (!(mo[t].flags & MF_EXTRA)) {
+            uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
+            const float x = mo[t].x, y = mo[t].y, z = mo[t].z;
+            int tile = 0;
+            for (;;) {
+                while (tile < near.ntiles) {
+                    const float4 lo = near.tlo[tile], hi = near.thi[tile];
+                    const float ex = fmaxf(fmaxf(lo.x - x, x - hi.x), 0.f);
+                    const float ey = fmaxf(fmaxf(lo.y - y, y - hi.y), 0.f);
+                    const float ez = fmaxf(fmaxf(lo.z - z, z - hi.z), 0.f);
+                    if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < rc2) break;
+                    tile++;
+                }
+                if (tile >= near.ntiles) break;
+                const int j0 = tile * MD_TILE, j1 = min(N, j0 + MD_TILE);
+                for (int j = j0; j < j1; j++) {
+                    const float4 Pj = s.P[j];
+                    const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
+                    if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < rc2 && j != i) {
+                        if (nc < MD_CAND_CAPACITY) {
+                            *cp = (uint16_t)j;
+                            cp += a.Npad;
+                        }
+                        nc++;
+                    }
+                }
+                tile++;
+            }
+        }
+        a.candcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nc, MD_CAND_CAPACITY);
+        ovf |= nc > MD_CAND_CAPACITY;
+    }
+    return ovf;
+}
+
+// Fast path, phase 1b (every list-update step): the reference's Verlet list = candidates that pass the exact
+// cut-off test (HBM, k-major); near list (SMEM) = candidates within MD_NEAR_R.  Returns near-list overflow.
+template <int MPT>
+__device__ __forceinline__ bool filter_candidates(const KArgs &k, const Stage &s, const Near &near, int traj, const Mono (&mo)[MPT],
+                                                  const int (&idx)[MPT], bool do_lj)
+{
+    const DevSys &a = k.a;
+    const int N = a.N;
+    int status = 0;
+    bool ovf = false;
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int i = idx[t];
+        if (i >= N) continue;
+        int nlj = 0, nn = 0;
+        if (!(mo[t].flags & MF_EXTRA)) {
+            const uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
+            uint16_t *lp = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+            uint16_t *np = near.list + i;
+            const int n = a.candcnt[(size_t)traj * a.Npad + i];
+            const float x = mo[t].x, y = mo[t].y, z = mo[t].z;
+            for (int kk = 0; kk < n; kk++, cp += a.Npad) {
+                const unsigned j = *cp;
+                const float4 Pj = s.P[j];
+                const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
+                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const bool inlj = do_lj && inside_cut(k.cut_pairs, dx, dy, dz, sf);
+                if (inlj) {
+                    if (nlj < MADDY_LJ_CAPACITY) {
+                        *lp = (uint16_t)j;
+                        lp += a.Npad;
+                    } else status |= ST_LJ_OVERFLOW;
+                    nlj++;
+                }
+                if (sf < MD_NEAR_R2) {
+                    if (nn < near.cap) {
+                        *np = (uint16_t)(j | (inlj ? MD_NEAR_LJ_FLAG : 0u));
+                        np += N;
+                    }
+                    nn++;
+                }
+            }
+        }
+        if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj, MADDY_LJ_CAPACITY);
+        near.cnt[i] = (uint8_t)min(nn, near.cap);
+        ovf |= nn > near.cap;
+    }
+    if (status) atomicOr(a.status, status);
+    return ovf;
+}
+
+// Fast path, phase 2: bond lists from the near list (every candidate lies within 6.6 nm < MD_NEAR_R).
+template <int MPT>
+__device__ __forceinline__ void bonds_from_near(const KArgs &k, const Stage &s, const Near &near, int traj, const Mono (&mo)[MPT],
+                                                const int (&idx)[MPT])
+{
+    const DevSys &a = k.a;
+    const int N = a.N;
+    int status = 0;
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int i = idx[t];
+        if (i >= N) continue;
+        BondOut bo;
+        bo.col = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
+        bo.nlong = bo.nlat = bo.status = 0;
+        if (!(mo[t].flags & MF_EXTRA)) {
+            const int hraw = a.harm[a.maxH * i];
+            const int hp = hraw < 0 ? -hraw : hraw;
+            const float4 Ei = s.E[i], L1i = s.L1[i], L2i = s.L2[i];
+            const int n = near.cnt[i];
+            for (int kk = 0; kk < n; kk++) {
+                const int j = near.list[kk * N + i] & 0x7fffu;
+                const float4 Pj = s.P[j];
+                const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
+                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (sf < MD_BOND_PREFILTER2 && hp != j) bond_candidates(a, s, i, j, mo[t], hraw, Pj, Ei, L1i, L2i, bo);
+            }
+        }
+        uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
+        bc[0] = (uint8_t)min(bo.nlong, a.capLong);
+        bc[a.Npad] = (uint8_t)min(bo.nlat, a.capLat);
+        status |= bo.status;
+    }
+    if (status) atomicOr(a.status, status);
+}
+
+// Near list := entries of the full LJ list (HBM) whose CURRENT distance is below MD_NEAR_R.
+// Used at the start of a fused window and when the displacement guard trips.  Returns overflow.
+template <int MPT>
+__device__ __forceinline__ bool refresh_near(const KArgs &k, const Stage &s, const Near &near, int traj, const Mono (&mo)[MPT],
+                                             const int (&idx)[MPT])
+{
+    const DevSys &a = k.a;
+    const int N = a.N;
+    bool ovf = false;
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int i = idx[t];
+        if (i >= N) continue;
+        int nn = 0;
+        if (k.p.lj_on && !(mo[t].flags & MF_EXTRA)) {
+            const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+            const int n = a.ljcnt[(size_t)traj * a.Npad + i];
+            for (int kk = 0; kk < n; kk++) {
+                const int j = lj[(size_t)kk * a.Npad];
+                const float4 Pj = s.P[j];
+                const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
+                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < MD_NEAR_R2) {
+                    if (nn < near.cap) near.list[nn * N + i] = (uint16_t)(j | MD_NEAR_LJ_FLAG);
+                    nn++;
+                }
+            }
+        }
+        near.cnt[i] = (uint8_t)min(nn, near.cap);
+        ovf |= nn > near.cap;
+    }
+    return ovf;
+}
+
+// Candidate-list state of one trajectory, carried in registers through a launch (and in HBM between launches).
+template <int MPT> struct CandState {
+    float x[MPT], y[MPT], z[MPT]; // positions when the candidate list was built
+    int valid;                    // CTA-uniform
+    bool dirty;
+};
+
+// Rebuild at a list-update step.  CTA-uniform control flow; returns whether the near list is valid.
+template <int MPT>
+__device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Near &near, CandState<MPT> &cs, int traj,
+                                              const Mono (&mo)[MPT], const int (&idx)[MPT], unsigned ops)
+{
+    if (near.cap == 0) {
+        rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
+        return false;
+    }
+    // has anything moved more than half the candidate skin since the candidate list was built?
+    bool moved = !cs.valid;
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        if (idx[t] < k.a.N) {
+            const float dx = mo[t].x - cs.x[t], dy = mo[t].y - cs.y[t], dz = mo[t].z - cs.z[t];
+            moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_CAND_GUARD2;
+        }
+    }
+    if (__syncthreads_or(moved)) {
+        compute_tiles(s, near, k.a.N);
+        __syncthreads();
+        const bool covf = scan_candidates<MPT>(k, s, near, traj, mo, idx);
+        cs.dirty = true;
+        if (__syncthreads_or(covf)) { // more candidates than MD_CAND_CAPACITY: general path, candidates stay invalid
+            cs.valid = 0;
+            rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
+            return false;
+        }
+        cs.valid = 1;
+#pragma unroll
+        for (int t = 0; t < MPT; t++) {
+            cs.x[t] = mo[t].x;
+            cs.y[t] = mo[t].y;
+            cs.z[t] = mo[t].z;
+        }
+    }
+    const bool ovf = filter_candidates<MPT>(k, s, near, traj, mo, idx, (ops & OP_REBUILD_LJ) != 0);
+    if (__syncthreads_or(ovf)) { // a near list overflowed: redo everything on the general path
+        rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
+        return false;
+    }
+    if (ops & OP_REBUILD_BONDS) bonds_from_near<MPT>(k, s, near, traj, mo, idx);
+    return (ops & OP_REBUILD_LJ) != 0 || !k.p.lj_on;
 }
 
 // ------------------------------------------------------------------ integrator (compute_cuda.cu:943-975)
@@ -491,11 +754,27 @@ __device__ __forceinline__ void block_reduce_e7(E7 e, double *out7, double *scra
     }
 }
 
+template <int MPT>
+__device__ __forceinline__ void store_cand_state(const DevSys &a, const CandState<MPT> &cs, int traj, size_t base, const int (&idx)[MPT])
+{
+    if (!cs.dirty) return;
+#pragma unroll
+    for (int t = 0; t < MPT; t++)
+        if (idx[t] < a.N) a.cpos[base + idx[t]] = make_float4(cs.x[t], cs.y[t], cs.z[t], 0.f);
+    if (threadIdx.x == 0) a.cand_valid[traj] = cs.valid;
+}
+
 // ------------------------------------------------------------------ the trajectory kernel
 // Threads per CTA never exceed MD_MAX_THREADS (the host picks MPT = ceil(N / MD_MAX_THREADS)),
 // which leaves ptxas up to 112 registers per thread for the fused loop.
-template <int MPT>
-__global__ void __launch_bounds__(MD_MAX_THREADS, 1) traj_kernel(const __grid_constant__ KArgs k)
+// Dynamic shared memory: [nbuf][4][N] float4 stage | 2*ntiles float4 tile boxes | near list u16[cap][N] | u8[N] counts
+// Two launch shapes: <MPT, 576, 1> (one CTA per SM, 96 registers) and <1, 576, 2> (two CTAs per SM at 56
+// registers, N <= 576): the second CTA fills the issue slots the first one leaves idle at its per-step
+// barrier and during MUFU / LDS latencies.
+// Register budget (the SM allocates registers per 4-warp group): 18 warps -> 20 slots -> 96 registers for one
+// CTA per SM; two 17-warp CTAs per SM need <= 56 registers per thread.
+template <int MPT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_kernel(const __grid_constant__ KArgs k)
 {
     extern __shared__ float4 smem[];
     __shared__ double red_scratch[32 * 7];
@@ -505,6 +784,15 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) traj_kernel(const __grid_co
     const int traj = blockIdx.x;
     const size_t base = (size_t)traj * N;
     const LatSite ls = lateral_site();
+
+    Near near;
+    near.cap = k.near_cap;
+    near.ntiles = (N + MD_TILE - 1) / MD_TILE;
+    near.tlo = smem + (size_t)k.nbuf * 4 * N;
+    near.thi = near.tlo + near.ntiles;
+    near.list = reinterpret_cast<uint16_t *>(near.thi + near.ntiles);
+    near.cnt = reinterpret_cast<uint8_t *>(near.list + (size_t)near.cap * N);
+    near.ok = false;
 
     Mono mo[MPT];
     int idx[MPT];
@@ -527,22 +815,62 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) traj_kernel(const __grid_co
         }
     }
 
+    // candidate-list state (persists in HBM between launches)
+    CandState<MPT> cs;
+    cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
+    cs.dirty = false;
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        cs.x[t] = cs.y[t] = cs.z[t] = 0.f;
+        if (cs.valid && idx[t] < N) {
+            const float4 c = a.cpos[base + idx[t]];
+            cs.x[t] = c.x; cs.y[t] = c.y; cs.z[t] = c.z;
+        }
+    }
+
     if (k.ops & OP_RUN) {
         int buf = 0;
+        int near_state = 0; // 0: not built, 1: valid, 2: overflowed (full list until the next rebuild)
+        float gx[MPT], gy[MPT], gz[MPT]; // positions when the near list was formed (displacement guard)
+#pragma unroll
+        for (int t = 0; t < MPT; t++) gx[t] = gy[t] = gz[t] = 0.f;
+        const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
         for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
             const Stage s = stage_at(smem, N, buf);
+            bool moved = false;
 #pragma unroll
-            for (int t = 0; t < MPT; t++)
-                if (idx[t] < N) publish(s, idx[t], mo[t], ls);
-            __syncthreads();
-            if (step % p.ljpairsupdatefreq == 0 && !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD))) {
-                const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
-                if (rops) rebuild_lists<MPT>(k, s, traj, mo, idx, rops);
+            for (int t = 0; t < MPT; t++) {
+                if (idx[t] < N) {
+                    publish(s, idx[t], mo[t], ls);
+                    const float dx = mo[t].x - gx[t], dy = mo[t].y - gy[t], dz = mo[t].z - gz[t];
+                    moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_NEAR_GUARD2;
+                }
             }
+            const bool any_moved = __syncthreads_or(moved && near_state == 1) != 0;
+            const bool do_rebuild = rops != 0 && step % p.ljpairsupdatefreq == 0 &&
+                                    !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
+            bool formed = false;
+            if (do_rebuild) {
+                near_state = rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, rops) ? 1 : 2;
+                formed = true;
+            } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
+                const bool ovf = refresh_near<MPT>(k, s, near, traj, mo, idx);
+                near_state = __syncthreads_or(ovf) ? 2 : 1;
+                formed = true;
+            }
+            if (formed) {
+#pragma unroll
+                for (int t = 0; t < MPT; t++) {
+                    gx[t] = mo[t].x;
+                    gy[t] = mo[t].y;
+                    gz[t] = mo[t].z;
+                }
+            }
+            near.ok = near.cap > 0 && near_state == 1;
 #pragma unroll
             for (int t = 0; t < MPT; t++) {
                 if (idx[t] < N && !(mo[t].flags & MF_EXTRA)) {
-                    const G6 f = monomer_force(k, s, traj, idx[t], mo[t], ls);
+                    const G6 f = monomer_force(k, s, near, traj, idx[t], mo[t], ls);
                     integrate_monomer(p, mo[t], f);
                 }
             }
@@ -559,17 +887,22 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) traj_kernel(const __grid_co
                 a.rng_ang[base + i] = mo[t].ra;
             }
         }
+        store_cand_state<MPT>(a, cs, traj, base, idx);
         return;
     }
 
-    // ---- single-phase modes (step-granular API)
+    // ---- single-phase modes (step-granular API): same device functions, full lists from HBM
     const Stage s = stage_at(smem, N, 0);
 #pragma unroll
     for (int t = 0; t < MPT; t++)
         if (idx[t] < N) publish(s, idx[t], mo[t], ls);
     __syncthreads();
 
-    if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) rebuild_lists<MPT>(k, s, traj, mo, idx, k.ops);
+    if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) {
+        rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, k.ops);
+        store_cand_state<MPT>(a, cs, traj, base, idx);
+    }
+    near.ok = false;
 
     if (k.ops & OP_FORCE) {
 #pragma unroll
@@ -577,7 +910,7 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) traj_kernel(const __grid_co
             const int i = idx[t];
             if (i < N && !(mo[t].flags & MF_EXTRA)) {
                 // extras keep the zero written by the integrator (compute_cuda.cu:55, :966-972)
-                const G6 f = monomer_force(k, s, traj, i, mo[t], ls);
+                const G6 f = monomer_force(k, s, near, traj, i, mo[t], ls);
                 a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
                 a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
             }
@@ -629,24 +962,29 @@ __global__ void __launch_bounds__(256) integrate_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ launch helpers (called from the C-ABI)
-template <int MPT>
+template <int MPT, int MAXT, int MINB>
 static cudaError_t launch_traj(const KArgs &k, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(traj_kernel<MPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(traj_kernel<MPT, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    traj_kernel<MPT><<<k.a.ntr, threads, smem, st>>>(k);
+    traj_kernel<MPT, MAXT, MINB><<<k.a.ntr, threads, smem, st>>>(k);
     return cudaGetLastError();
 }
 
-cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st)
+// shape 0: <= MD_MAX_THREADS threads, 1 CTA/SM; shape 1: <= MD_SMALL_THREADS threads, 2 CTAs/SM
+cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int shape, int threads, size_t smem, cudaStream_t st)
 {
+    if (shape == 1) {
+        if (mpt != 1) return cudaErrorInvalidValue;
+        return launch_traj<1, MD_MAX_THREADS, 2>(k, threads, smem, st);
+    }
     switch (mpt) {
-    case 1: return launch_traj<1>(k, threads, smem, st);
-    case 2: return launch_traj<2>(k, threads, smem, st);
-    case 3: return launch_traj<3>(k, threads, smem, st);
-    case 4: return launch_traj<4>(k, threads, smem, st);
-    case 5: return launch_traj<5>(k, threads, smem, st);
-    case 6: return launch_traj<6>(k, threads, smem, st);
+    case 1: return launch_traj<1, MD_MAX_THREADS, 1>(k, threads, smem, st);
+    case 2: return launch_traj<2, MD_MAX_THREADS, 1>(k, threads, smem, st);
+    case 3: return launch_traj<3, MD_MAX_THREADS, 1>(k, threads, smem, st);
+    case 4: return launch_traj<4, MD_MAX_THREADS, 1>(k, threads, smem, st);
+    case 5: return launch_traj<5, MD_MAX_THREADS, 1>(k, threads, smem, st);
+    case 6: return launch_traj<6, MD_MAX_THREADS, 1>(k, threads, smem, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -11,6 +11,7 @@ namespace maddy {
 
 #define MD_MAX_THREADS 576 // threads per trajectory CTA (18 warps)
 #define MD_MAX_MPT 6
+#define MD_SMALL_THREADS 288 // launch shape 1: two CTAs per SM (N <= 2 * 288)
 
 // operation mask of the trajectory kernel
 enum : unsigned {
@@ -51,11 +52,33 @@ struct DevSys {
     double *en_mono; // [n][7]
     double *en_traj; // [ntr][7]
     int *status;
+    uint16_t *cand;    // [ntr][MD_CAND_CAPACITY][Npad] candidate list, k-major
+    uint16_t *candcnt; // [ntr][Npad]
+    float4 *cpos;      // [n] positions when the candidate list was built (.w unused)
+    int *cand_valid;   // [ntr] 1 = cand/candcnt/cpos describe the current extra flags
     // TEA (bdhitea): per-bead sum of squared tensor rows (d_ci), per-bead epsilon sums, per-traj beta
     float4 *tea_ci;
     float *tea_eps;
     float *tea_beta;
 };
+
+// Near list (shared memory, fused loop only): all j != i with centre distance < MD_NEAR_R at the last
+// rebuild / refresh, ascending j, bit 15 = "is in the reference LJ list".  It caches the part of the
+// 15-nm Verlet list that can reach the 6-nm force cut-off before any monomer has moved MD_NEAR_GUARD:
+// a pair at >= 7.0 needs a relative displacement > 1.0 to get inside 6.0, i.e. one endpoint > 0.5.
+// The guard is checked every step (folded into the step barrier); a trip refreshes the cache from the
+// full list in HBM, so forces are bit-identical to walking the full list.
+#define MD_NEAR_R2 49.0f
+#define MD_NEAR_GUARD2 0.2401f // 0.49^2 (< 0.5^2: margin for float rounding)
+#define MD_NEAR_LJ_FLAG 0x8000u
+#define MD_TILE 8              // consecutive monomers per culling tile (bounding boxes rebuilt with the lists)
+// Candidate list (HBM): all j != i within (cut-off + MD_CAND_SKIN) when it was built.  The O(N^2)
+// tile-culled scan only runs when some monomer has moved more than MD_CAND_SKIN / 2 since then
+// (checked at every list-update step); otherwise the reference's Verlet list is obtained by
+// re-testing the ~60 candidates with the exact cut-off test — identical output, ~30x less work.
+#define MD_CAND_SKIN 1.5f
+#define MD_CAND_GUARD2 0.5476f // 0.74^2 (< (MD_CAND_SKIN/2)^2)
+#define MD_CAND_CAPACITY 320
 
 struct KArgs {
     maddy_params p;
@@ -64,6 +87,8 @@ struct KArgs {
     unsigned ops;
     unsigned run_flags;
     int nbuf;          // 1 or 2 shared-memory stage buffers
+    int near_cap;      // rows of the shared-memory near list (0: fast path disabled)
+    float rcand2;      // squared candidate radius: (max(LJ pairs cut-off, near radius) + MD_CAND_SKIN)^2
     CutTest cut_pairs; // LJ list cut-off (ljpairscutoff)
     CutTest cut_force; // LJ force cut-off (6.0)
 };
