@@ -295,8 +295,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100000, help="MD steps to time (default: the 1e5-step run length of the BASELINE configs)")
+    ap.add_argument("--warmup", type=int, default=1000)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="mt40_ensemble")
     ap.add_argument("--ntr", type=int, default=256, help="trajectories per GPU")

@@ -59,13 +59,30 @@ static int fail(maddy_handle *h, int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(h, MADDY_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));         \
     } while (0)
 
-template <typename T> static int dalloc(maddy_handle *h, T **p, size_t n)
+// All device arrays of a handle are carved out of ONE cudaMalloc (create/destroy sit inside the timed region of
+// the drop-in compute()): requests are recorded first, then committed.
+struct PoolReq {
+    void **slot;
+    size_t bytes;
+};
+static thread_local std::vector<PoolReq> *g_pool_reqs;
+template <typename T> static void pool_req(T **p, size_t n)
 {
-    void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, n ? n * sizeof(T) : sizeof(T));
-    if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
-    h->allocs.push_back(q);
-    *p = (T *)q;
+    g_pool_reqs->push_back({(void **)p, ((n ? n : 1) * sizeof(T) + 255) & ~(size_t)255});
+}
+static int pool_commit(maddy_handle *h, std::vector<PoolReq> &reqs)
+{
+    size_t total = 0;
+    for (const PoolReq &r : reqs) total += r.bytes;
+    void *base = nullptr;
+    cudaError_t e = cudaMalloc(&base, total);
+    if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "cudaMalloc(%zu bytes): %s", total, cudaGetErrorString(e));
+    h->allocs.push_back(base);
+    char *q = (char *)base;
+    for (const PoolReq &r : reqs) {
+        *r.slot = q;
+        q += r.bytes;
+    }
     return MADDY_OK;
 }
 
@@ -285,35 +302,38 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         h->cut_pairs = make_cut(par->ljpairscutoff);
         h->cut_force = make_cut(MD_LJ_FORCE_CUTOFF);
 
-        CK(dalloc(h, &a.pos, n));
-        CK(dalloc(h, &a.ang, n));
-        CK(dalloc(h, &a.fpos, n));
-        CK(dalloc(h, &a.fang, n));
-        CK(dalloc(h, &a.rng_xyz, n));
-        CK(dalloc(h, &a.rng_ang, n));
-        CK(dalloc(h, (int **)&a.harm, (size_t)N * a.maxH));
-        CK(dalloc(h, (int **)&a.harm_count, (size_t)N));
-        CK(dalloc(h, (uint8_t **)&a.sflags, (size_t)N));
-        CK(dalloc(h, &a.extra, n));
-        CK(dalloc(h, &a.gtp, n));
-        CK(dalloc(h, &a.ontub, n));
-        CK(dalloc(h, &a.bl, (size_t)ntr * (a.capLong + a.capLat) * a.Npad));
-        CK(dalloc(h, &a.bcnt, (size_t)ntr * 2 * a.Npad));
-        CK(dalloc(h, &a.lj, par->lj_on ? (size_t)ntr * MADDY_LJ_CAPACITY * a.Npad : 1));
-        CK(dalloc(h, &a.ljcnt, (size_t)ntr * a.Npad));
-        CK(dalloc(h, &a.cand, h->near_cap > 0 ? (size_t)ntr * MD_CAND_CAPACITY * a.Npad : 1));
-        CK(dalloc(h, &a.candcnt, (size_t)ntr * a.Npad));
-        CK(dalloc(h, &a.cpos, n));
-        CK(dalloc(h, &a.cand_valid, (size_t)ntr));
-        CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
-        CK(dalloc(h, &a.en_mono, n * 7));
-        CK(dalloc(h, &a.en_traj, (size_t)ntr * 7));
-        CK(dalloc(h, &a.status, 1));
+        std::vector<PoolReq> reqs;
+        g_pool_reqs = &reqs;
+        pool_req(&a.pos, n);
+        pool_req(&a.ang, n);
+        pool_req(&a.fpos, n);
+        pool_req(&a.fang, n);
+        pool_req(&a.rng_xyz, n);
+        pool_req(&a.rng_ang, n);
+        pool_req(const_cast<int **>(&a.harm), (size_t)N * a.maxH);
+        pool_req(const_cast<int **>(&a.harm_count), (size_t)N);
+        pool_req(const_cast<uint8_t **>(&a.sflags), (size_t)N);
+        pool_req(&a.extra, n);
+        pool_req(&a.gtp, n);
+        pool_req(&a.ontub, n);
+        pool_req(&a.bl, (size_t)ntr * (a.capLong + a.capLat) * a.Npad);
+        pool_req(&a.bcnt, (size_t)ntr * 2 * a.Npad);
+        pool_req(&a.lj, par->lj_on ? (size_t)ntr * MADDY_LJ_CAPACITY * a.Npad : 1);
+        pool_req(&a.ljcnt, (size_t)ntr * a.Npad);
+        pool_req(&a.cand, h->near_cap > 0 ? (size_t)ntr * MD_CAND_CAPACITY * a.Npad : 1);
+        pool_req(&a.candcnt, (size_t)ntr * a.Npad);
+        pool_req(&a.cpos, n);
+        pool_req(&a.cand_valid, (size_t)ntr);
+        pool_req(&a.en_mono, n * 7);
+        pool_req(&a.en_traj, (size_t)ntr * 7);
+        pool_req(&a.status, 1);
         if (par->tea_on) {
-            CK(dalloc(h, &a.tea_ci, n));
-            CK(dalloc(h, &a.tea_eps, n));
-            CK(dalloc(h, &a.tea_beta, (size_t)ntr));
+            pool_req(&a.tea_ci, n);
+            pool_req(&a.tea_eps, n);
+            pool_req(&a.tea_beta, (size_t)ntr);
         }
+        CK(pool_commit(h, reqs));
+        CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.status, 0, sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.fpos, 0, n * sizeof(float4), h->stream));
         CUK(cudaMemsetAsync(a.fang, 0, n * sizeof(float4), h->stream));

@@ -315,3 +315,41 @@ def test_overflow_and_bad_arguments_fail_loudly(rundir, load_system):
     with pytest.raises(MaddyError) as err:
         Engine(s, traj_first=1)  # empty shard
     assert err.value.code == -1
+
+
+# ------------------------------------------------------------------ (5) the drop-in executable end to end
+def test_drop_in_mt_executable_vs_reference_executable(rundir):
+    """`mt config.conf` of this repo vs the reference's own `mt` on the same run directory contents:
+    host events on (hydrolysis every 100 steps, tubule length + energies every stride), DCD frames and the
+    printed energies compared."""
+    import re
+    import shutil
+    import subprocess
+    import mt_b200
+    from oracle import refprobe
+    if not refprobe.REF_MT.exists():
+        pytest.skip("oracle/_ref/mt did not travel with the tree")
+    mine_bin = ROOT / "mt_b200" / "mt"
+    d_ref = rundir("mt40_single", runnum=2, steps=300, stride=100)
+    d_own = d_ref.parent / (d_ref.name + "_own")
+    shutil.copytree(d_ref, d_own)
+    _, out_ref = refprobe.run_reference_mt(d_ref)
+    r = subprocess.run([str(mine_bin), "config.conf"], cwd=str(d_own), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for t in range(2):
+        for suffix, tol in ((".dcd", 1e-3), (".dcd_ang", 1e-4)):
+            a = mt_b200.read_dcd(d_own / "dcd" / f"run_{t}{suffix}")
+            b = mt_b200.read_dcd(d_ref / "dcd" / f"run_{t}{suffix}")
+            assert a.shape == b.shape == (3, 520, 3)
+            assert np.abs(a - b).max() < tol, (t, suffix, np.abs(a - b).max())
+        # DCD headers are byte-identical up to the date remark (bytes 180..260)
+        ha = (d_own / "dcd" / f"run_{t}.dcd").read_bytes()[:276]
+        hb = (d_ref / "dcd" / f"run_{t}.dcd").read_bytes()[:276]
+        assert ha[:180] == hb[:180] and ha[260:] == hb[260:]
+    pat = re.compile(r"Energies\[(\d+)\]:\s+(.*)")
+    e_own = [[float(x) for x in m.group(2).split()] for m in map(pat.match, r.stdout.splitlines()) if m]
+    e_ref = [[float(x) for x in m.group(2).split()] for m in map(pat.match, out_ref.splitlines()) if m]
+    assert len(e_own) == len(e_ref) == 6
+    assert np.allclose(e_own, e_ref, rtol=1e-4, atol=2e-2)
+    assert re.findall(r"tubule\[\d\]: \d+", r.stdout) == re.findall(r"tubule\[\d\]: \d+", out_ref)
+    assert (d_own / "result_xyz.pdb").exists() and (d_own / "mt_len.dat").read_text() == (d_ref / "mt_len.dat").read_text()
