@@ -44,6 +44,9 @@ METRIC = "monomer-steps/s (ensemble, device-timed)"
 UNIT = "monomer-steps/s"
 B_ALG = 352.0  # algorithmic bytes per monomer-step, intact lattice (BASELINE.md 3 / SURVEY.md 8d)
 B_ALG_TERMS = "64 state r/w + 64 RNG r/w + 4*(46+1) LJ list + 4*(4+3) bond lists + 8 flags"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (a 100-step fused window at 520 x 256) from the
+# `ncu --set full` capture summarised in profiles/r1_traj_kernel_ncu_full.txt (37.5 MB read + 5.3 MB written)
+NCU_TRAFFIC_PER_LAUNCH = {("mt40_ensemble", 256, 100): 42.8e6}
 REF_NTR_LIMIT = 100
 
 
@@ -224,8 +227,10 @@ def run_own(args):
                                  "within a window the state is register/SMEM resident by design"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
-                             "kernel": "maddy::traj_kernel<1> (fused run window)",
+                             "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_PER_LAUNCH.get((args.workload, ntr_local, window)),
+                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_traj_kernel_ncu_full.txt)",
+                             "algorithmic_bytes_per_launch": B_ALG * N * ntr_local * window, "peak_source": pk_src,
+                             "kernel": "maddy::traj_kernel<1,576,2> (one fused window of `window_steps` MD steps per launch)",
                              "algorithmic_bytes_per_monomer_step": B_ALG, "terms": B_ALG_TERMS,
                              "note": "state stays on-chip across the fused steps, so DRAM traffic is far below the algorithmic bytes; "
                                      "the binding limit is SM issue/latency (see profiles/)"},

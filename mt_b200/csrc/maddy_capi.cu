@@ -30,13 +30,19 @@ struct maddy_handle {
     DevSys a;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int mpt = 1, threads = 32, nbuf = 2, near_cap = 0, shape = 0;
+    int mpt = 1, threads = 32, nbuf = 2, near_cap = 0, shape = 0, rng_smem_offset = 0;
     size_t smem = 0;
     CutTest cut_pairs, cut_force;
     std::string err;
     long long launches = 0;
     std::vector<void *> allocs;
     int *h_status = nullptr; // pinned
+    // ring of pinned staging buffers for the flag uploads: the copies are asynchronous, so the host can queue the
+    // next fused window while the GPU is still running the current one
+    static const int kStage = 4;
+    uint8_t *stage[kStage] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_done[kStage] = {nullptr, nullptr, nullptr, nullptr};
+    int stage_next = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -123,6 +129,7 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
     k.run_flags = 0;
     k.nbuf = h->nbuf;
     k.near_cap = h->near_cap;
+    k.rng_smem_offset = h->rng_smem_offset;
     {
         const float rb = fmaxf(h->p.lj_on ? h->p.ljpairscutoff : 0.f, 7.0f) + MD_CAND_SKIN;
         k.rcand2 = rb * rb;
@@ -206,6 +213,10 @@ extern "C" int maddy_destroy(maddy_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *q : h->allocs) cudaFree(q);
     if (h->h_status) cudaFreeHost(h->h_status);
+    for (int k = 0; k < maddy_handle::kStage; k++) {
+        if (h->stage[k]) cudaFreeHost(h->stage[k]);
+        if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]);
+    }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MADDY_OK;
@@ -297,7 +308,23 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             h->smem = (h->smem + 15) & ~(size_t)15;
             // small trajectories: 9-warp CTAs, two per SM (needs 2 x smem <= 227 KB)
             const char *force_shape = getenv("MADDY_SHAPE");
-            if (N <= MD_MAX_THREADS && 2 * (h->smem + 2048) <= 227 * 1024 && !(force_shape && force_shape[0] == '0')) h->shape = 1;
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, par->device);
+            // a second CTA per SM only pays when there are more trajectories than SMs (it costs registers: 56 vs 96)
+            const bool want2 = force_shape ? force_shape[0] == '1' : ntr > n_sm;
+            if (N <= MD_MAX_THREADS && want2) {
+                // two CTAs per SM: near list capped at 20 rows, RNG streams (32 B per monomer) parked in shared memory
+                const int cap2 = h->near_cap > 20 ? 20 : h->near_cap;
+                size_t sm2 = stage + tiles + (size_t)cap2 * N * 2 + N + 64;
+                sm2 = (sm2 + 15) & ~(size_t)15;
+                const size_t total = sm2 + (size_t)32 * N;
+                if (cap2 >= 12 && 2 * (total + 1792 + 1024) <= 227 * 1024) {
+                    h->shape = 1;
+                    h->near_cap = cap2;
+                    h->rng_smem_offset = (int)sm2;
+                    h->smem = total;
+                }
+            }
         }
         h->cut_pairs = make_cut(par->ljpairscutoff);
         h->cut_force = make_cut(MD_LJ_FORCE_CUTOFF);
@@ -488,37 +515,60 @@ extern "C" int maddy_upload_coords(maddy_handle *h, const float *aos)
     return MADDY_OK;
 }
 
-static int upload_bytes(maddy_handle *h, uint8_t *dst, const std::vector<uint8_t> &v)
+// next pinned staging buffer (waits only if the copy that last used it has not finished)
+static int stage_acquire(maddy_handle *h, uint8_t **buf, int *slot)
 {
     CU(h, cudaSetDevice(h->p.device));
-    CU(h, cudaMemcpyAsync(dst, v.data(), v.size(), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    const int k = h->stage_next;
+    h->stage_next = (k + 1) % maddy_handle::kStage;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    if (!h->stage[k]) {
+        CU(h, cudaMallocHost(&h->stage[k], n));
+        CU(h, cudaEventCreateWithFlags(&h->stage_done[k], cudaEventDisableTiming));
+    } else {
+        CU(h, cudaEventSynchronize(h->stage_done[k]));
+    }
+    *buf = h->stage[k];
+    *slot = k;
+    return MADDY_OK;
+}
+static int stage_submit(maddy_handle *h, uint8_t *dst, int slot)
+{
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    CU(h, cudaMemcpyAsync(dst, h->stage[slot], n, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaEventRecord(h->stage_done[slot], h->stream));
     return MADDY_OK;
 }
 extern "C" int maddy_upload_gtp(maddy_handle *h, const int *gtp)
 {
     if (!h || !gtp) return MADDY_EINVAL;
     const size_t n = (size_t)h->a.ntr * h->a.N;
-    std::vector<uint8_t> v(n);
+    uint8_t *v;
+    int slot, rc = stage_acquire(h, &v, &slot);
+    if (rc) return rc;
     for (size_t q = 0; q < n; q++) v[q] = (uint8_t)(gtp[q] == 1 ? 1 : (gtp[q] == 0 ? 0 : 2)); // kernels test == 1
-    return upload_bytes(h, h->a.gtp, v);
+    return stage_submit(h, h->a.gtp, slot);
 }
 extern "C" int maddy_upload_on_tubule(maddy_handle *h, const int *on)
 {
     if (!h || !on) return MADDY_EINVAL;
     const size_t n = (size_t)h->a.ntr * h->a.N;
-    std::vector<uint8_t> v(n);
+    uint8_t *v;
+    int slot, rc = stage_acquire(h, &v, &slot);
+    if (rc) return rc;
     for (size_t q = 0; q < n; q++) v[q] = on[q] != 0;
-    return upload_bytes(h, h->a.ontub, v);
+    return stage_submit(h, h->a.ontub, slot);
 }
 extern "C" int maddy_upload_extra(maddy_handle *h, const unsigned char *extra)
 {
     if (!h || !extra) return MADDY_EINVAL;
     const size_t n = (size_t)h->a.ntr * h->a.N;
-    std::vector<uint8_t> v(n);
+    uint8_t *v;
+    int slot, rc = stage_acquire(h, &v, &slot);
+    if (rc) return rc;
     for (size_t q = 0; q < n; q++) v[q] = extra[q] != 0;
-    if (h->a.cand_valid) cudaMemsetAsync(h->a.cand_valid, 0, (size_t)h->a.ntr * sizeof(int), h->stream); // rows of former extras are empty
-    return upload_bytes(h, h->a.extra, v);
+    if (h->a.cand_valid) CU(h, cudaMemsetAsync(h->a.cand_valid, 0, (size_t)h->a.ntr * sizeof(int), h->stream)); // rows of former extras are empty
+    return stage_submit(h, h->a.extra, slot);
 }
 
 // native bond code (j<<1 | neg) <-> reference encodings

@@ -662,15 +662,14 @@ __device__ __forceinline__ bool refresh_near(const KArgs &k, const Stage &s, con
 }
 
 // Candidate-list state of one trajectory, carried in registers through a launch (and in HBM between launches).
-template <int MPT> struct CandState {
-    float x[MPT], y[MPT], z[MPT]; // positions when the candidate list was built
-    int valid;                    // CTA-uniform
+struct CandState {
+    int valid; // CTA-uniform; the positions the list was built from live in HBM (a.cpos), read every list-update step
     bool dirty;
 };
 
 // Rebuild at a list-update step.  CTA-uniform control flow; returns whether the near list is valid.
 template <int MPT>
-__device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Near &near, CandState<MPT> &cs, int traj,
+__device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Near &near, CandState &cs, int traj,
                                               const Mono (&mo)[MPT], const int (&idx)[MPT], unsigned ops)
 {
     if (near.cap == 0) {
@@ -678,12 +677,16 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
         return false;
     }
     // has anything moved more than half the candidate skin since the candidate list was built?
+    const size_t base = (size_t)traj * k.a.N;
     bool moved = !cs.valid;
+    if (cs.valid) {
 #pragma unroll
-    for (int t = 0; t < MPT; t++) {
-        if (idx[t] < k.a.N) {
-            const float dx = mo[t].x - cs.x[t], dy = mo[t].y - cs.y[t], dz = mo[t].z - cs.z[t];
-            moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_CAND_GUARD2;
+        for (int t = 0; t < MPT; t++) {
+            if (idx[t] < k.a.N) {
+                const float4 c = k.a.cpos[base + idx[t]];
+                const float dx = mo[t].x - c.x, dy = mo[t].y - c.y, dz = mo[t].z - c.z;
+                moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_CAND_GUARD2;
+            }
         }
     }
     if (__syncthreads_or(moved)) {
@@ -698,11 +701,8 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
         }
         cs.valid = 1;
 #pragma unroll
-        for (int t = 0; t < MPT; t++) {
-            cs.x[t] = mo[t].x;
-            cs.y[t] = mo[t].y;
-            cs.z[t] = mo[t].z;
-        }
+        for (int t = 0; t < MPT; t++)
+            if (idx[t] < k.a.N) k.a.cpos[base + idx[t]] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
     }
     const bool ovf = filter_candidates<MPT>(k, s, near, traj, mo, idx, (ops & OP_REBUILD_LJ) != 0);
     if (__syncthreads_or(ovf)) { // a near list overflowed: redo everything on the general path
@@ -754,14 +754,9 @@ __device__ __forceinline__ void block_reduce_e7(E7 e, double *out7, double *scra
     }
 }
 
-template <int MPT>
-__device__ __forceinline__ void store_cand_state(const DevSys &a, const CandState<MPT> &cs, int traj, size_t base, const int (&idx)[MPT])
+__device__ __forceinline__ void store_cand_state(const DevSys &a, const CandState &cs, int traj)
 {
-    if (!cs.dirty) return;
-#pragma unroll
-    for (int t = 0; t < MPT; t++)
-        if (idx[t] < a.N) a.cpos[base + idx[t]] = make_float4(cs.x[t], cs.y[t], cs.z[t], 0.f);
-    if (threadIdx.x == 0) a.cand_valid[traj] = cs.valid;
+    if (cs.dirty && threadIdx.x == 0) a.cand_valid[traj] = cs.valid;
 }
 
 // ------------------------------------------------------------------ the trajectory kernel
@@ -793,6 +788,9 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
     near.list = reinterpret_cast<uint16_t *>(near.thi + near.ntiles);
     near.cnt = reinterpret_cast<uint8_t *>(near.list + (size_t)near.cap * N);
     near.ok = false;
+    // two-CTA shape: the HybridTaus streams (8 registers) wait in shared memory between integrator calls
+    constexpr bool kRngShared = MINB == 2;
+    uint4 *srng = reinterpret_cast<uint4 *>(smem) + (k.rng_smem_offset >> 4);
 
     Mono mo[MPT];
     int idx[MPT];
@@ -807,8 +805,13 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
             mo[t].flags = (int)a.sflags[i] | (a.gtp[base + i] == 1 ? MF_GTP : 0) | (a.ontub[base + i] ? MF_ONTUB : 0) |
                           (a.extra[base + i] ? MF_EXTRA : 0);
             if (k.ops & OP_RUN) {
-                mo[t].rx = a.rng_xyz[base + i];
-                mo[t].ra = a.rng_ang[base + i];
+                if (kRngShared) {
+                    srng[i] = a.rng_xyz[base + i];
+                    srng[N + i] = a.rng_ang[base + i];
+                } else {
+                    mo[t].rx = a.rng_xyz[base + i];
+                    mo[t].ra = a.rng_ang[base + i];
+                }
             }
         } else {
             mo[t].flags = MF_EXTRA | MF_FIXED;
@@ -816,17 +819,9 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
     }
 
     // candidate-list state (persists in HBM between launches)
-    CandState<MPT> cs;
+    CandState cs;
     cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
     cs.dirty = false;
-#pragma unroll
-    for (int t = 0; t < MPT; t++) {
-        cs.x[t] = cs.y[t] = cs.z[t] = 0.f;
-        if (cs.valid && idx[t] < N) {
-            const float4 c = a.cpos[base + idx[t]];
-            cs.x[t] = c.x; cs.y[t] = c.y; cs.z[t] = c.z;
-        }
-    }
 
     if (k.ops & OP_RUN) {
         int buf = 0;
@@ -871,7 +866,15 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
             for (int t = 0; t < MPT; t++) {
                 if (idx[t] < N && !(mo[t].flags & MF_EXTRA)) {
                     const G6 f = monomer_force(k, s, near, traj, idx[t], mo[t], ls);
+                    if (kRngShared) {
+                        mo[t].rx = srng[idx[t]];
+                        mo[t].ra = srng[N + idx[t]];
+                    }
                     integrate_monomer(p, mo[t], f);
+                    if (kRngShared && !(mo[t].flags & MF_FIXED)) {
+                        srng[idx[t]] = mo[t].rx;
+                        srng[N + idx[t]] = mo[t].ra;
+                    }
                 }
             }
             if (k.nbuf == 2) buf ^= 1;
@@ -883,11 +886,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
             if (i < N) {
                 a.pos[base + i] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
                 a.ang[base + i] = make_float4(mo[t].fi, mo[t].psi, mo[t].theta, 0.f);
-                a.rng_xyz[base + i] = mo[t].rx;
-                a.rng_ang[base + i] = mo[t].ra;
+                a.rng_xyz[base + i] = kRngShared ? srng[i] : mo[t].rx;
+                a.rng_ang[base + i] = kRngShared ? srng[N + i] : mo[t].ra;
             }
         }
-        store_cand_state<MPT>(a, cs, traj, base, idx);
+        store_cand_state(a, cs, traj);
         return;
     }
 
@@ -900,7 +903,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
 
     if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) {
         rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, k.ops);
-        store_cand_state<MPT>(a, cs, traj, base, idx);
+        store_cand_state(a, cs, traj);
     }
     near.ok = false;
 

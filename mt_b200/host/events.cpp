@@ -285,11 +285,21 @@ void compute(System &s, bool fused, ComputeStats *stats)
         for (Shard &d : sh.v) fn(d);
     };
 
+    // Host events need the device only where the reference order makes it observable:
+    //  * lists are rebuilt BEFORE the host events of a step (compute_cuda.cu:1140-1151); that only matters when an
+    //    event can move particles afterwards (constant-concentration insertion at a stride step) — otherwise the
+    //    rebuild is folded into the fused window launch;
+    //  * hydrolyse() reads only host flags from the previous stride, so the draw for the NEXT event step is made
+    //    while the GPU runs the current window (same rand() order: it follows every event of the current step).
     long long step = 0;
+    long long hydrolysed_for = -1; // event step whose hydrolysis has already been evaluated on the host
     while (step < hp.steps) {
-        // ---- list rebuild (compute_cuda.cu:1140-1151) — before the host events of this step
         const bool rebuild_now = step % par.ljpairsupdatefreq == 0;
-        if (rebuild_now) {
+        const bool stride_now = step % hp.stride == 0;
+        const bool may_teleport = stride_now && hp.tub_length && step != 0 && hp.is_const_conc;
+        // energies printed at a stride step are evaluated on the lists rebuilt at that step (compute_cuda.cu:1140-1170)
+        const bool explicit_rebuild = rebuild_now && ((stride_now && hp.out_energy) || may_teleport || par.tea_on || !fused);
+        if (explicit_rebuild) {
             for_each([&](Shard &d) {
                 if (par.lj_on) ck(maddy_rebuild_lj(d.h), d.h, "maddy_rebuild_lj");
                 if (par.is_assembly) ck(maddy_rebuild_bonds(d.h), d.h, "maddy_rebuild_bonds");
@@ -297,12 +307,12 @@ void compute(System &s, bool fused, ComputeStats *stats)
         }
         // ---- hydrolysis (compute_cuda.cu:1153-1160)
         if (hp.hydrolysis && step % hp.hydrostep == 0 && step != 0) {
-            hydrolyse(s);
+            if (hydrolysed_for != step) hydrolyse(s);
             for_each([&](Shard &d) { ck(maddy_upload_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_upload_gtp"); });
             st.h2d_bytes += (double)n;
         }
         // ---- stride block (compute_cuda.cu:1163-1226)
-        if (step % hp.stride == 0) {
+        if (stride_now) {
             if (hp.out_energy) {
                 for_each([&](Shard &d) { ck(maddy_energies(d.h, &s.energies[(size_t)d.first * 7], nullptr), d.h, "maddy_energies"); });
                 st.d2h_bytes += (double)Ntr * 7 * 8;
@@ -365,7 +375,12 @@ void compute(System &s, bool fused, ComputeStats *stats)
                 });
             }
         } else {
-            for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, rebuild_now ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u), d.h, "maddy_run"); });
+            for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, explicit_rebuild ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u), d.h, "maddy_run"); });
+        }
+        // overlap with the asynchronous window: evaluate the next hydrolysis event on the host now
+        if (hp.hydrolysis && next < hp.steps && next % hp.hydrostep == 0 && next != 0) {
+            hydrolyse(s);
+            hydrolysed_for = next;
         }
         step = next;
         st.steps += count;

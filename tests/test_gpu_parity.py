@@ -353,3 +353,25 @@ def test_drop_in_mt_executable_vs_reference_executable(rundir):
     assert np.allclose(e_own, e_ref, rtol=1e-4, atol=2e-2)
     assert re.findall(r"tubule\[\d\]: \d+", r.stdout) == re.findall(r"tubule\[\d\]: \d+", out_ref)
     assert (d_own / "result_xyz.pdb").exists() and (d_own / "mt_len.dat").read_text() == (d_ref / "mt_len.dat").read_text()
+
+
+def test_list_hierarchy_equals_all_pairs_path_on_diffusing_dimers(rundir, load_system, monkeypatch):
+    """Free dimers diffuse far enough to trip both displacement guards (near list 0.49 nm, candidate list 0.74 nm):
+    the guarded candidate/Verlet/near hierarchy must stay bit-identical to the plain all-pairs rebuild + full-list walk."""
+    d = rundir("cylinder_tea", structure=("free", 120, 14.0, 60.0, 5), runnum=3, steps=700, stride=100000, tea_on="no")
+    s = load_system(d, ["hydrolysis=no"])
+    fast = Engine(s)
+    monkeypatch.setenv("MADDY_NO_NEAR", "1")
+    slow = Engine(s)
+    monkeypatch.delenv("MADDY_NO_NEAR")
+    c0 = fast.coords()
+    for first, n in ((0, 100), (100, 250), (350, 350)):
+        fast.run(first, n)
+        slow.run(first, n)
+        assert np.array_equal(fast.coords(), slow.coords())
+        assert lists_equal(*fast.download_list(capi.LIST_LJ), *slow.download_list(capi.LIST_LJ))
+        assert lists_equal(*fast.download_list(capi.LIST_LATERAL), *slow.download_list(capi.LIST_LATERAL))
+        assert lists_equal(*fast.download_list(capi.LIST_LONGITUDINAL), *slow.download_list(capi.LIST_LONGITUDINAL))
+    assert np.array_equal(fast.rng_state(), slow.rng_state())
+    moved = np.linalg.norm(fast.coords()[..., :3] - c0[..., :3], axis=-1)
+    assert moved.max() > 0.8  # the guards did trip
