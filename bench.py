@@ -91,11 +91,11 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
 
 
-def make_system(workload: str, ntr_global: int, tmp: Path, overrides=()):
+def make_system(workload: str, ntr_global: int, tmp: Path, overrides=(), write_files=False, **config):
     from mt_b200 import HostSystem, workspace
-    workspace.make_baseline_rundir(tmp, workload, runnum=ntr_global)
+    workspace.make_baseline_rundir(tmp, workload, runnum=ntr_global, **config)
     with workspace.chdir(tmp):
-        return HostSystem("config.conf", list(overrides))
+        return HostSystem("config.conf", list(overrides), write_files=write_files)
 
 
 def cpu_baseline(workload: str, budget_s: float = 12.0):
@@ -195,21 +195,24 @@ def run_own(args):
         value = N * ntr_global * args.steps / (ms_max * 1e-3)
 
         # ---- e2e through the drop-in compute() with host buffers
+        from mt_b200 import workspace
         e2e_sys = make_system(args.workload, ntr_local, tmp / "e2e", [f"device={local}"])
         e2e_sys.compute(steps=min(args.steps, 200))  # untimed: module load / context warm-up
         e2e_sys.close()
-        e2e_sys = make_system(args.workload, ntr_local, tmp / "e2e2", [f"device={local}"])
+        # DCD frames, mt_len.dat and hydrolysis.pdb are written like the reference executable does (background writer)
+        e2e_sys = make_system(args.workload, ntr_local, tmp / "e2e2", [f"device={local}"], write_files=True, steps=args.steps)
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        st = e2e_sys.compute(steps=args.steps)
-        wall = time.perf_counter() - t0
+        with workspace.chdir(tmp / "e2e2"):
+            t0 = time.perf_counter()
+            st = e2e_sys.compute()
+            wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         e2e = {"value": N * ntr_global * args.steps / float(tw.item()), "unit": UNIT,
                "h2d_bytes_per_step": st["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st["d2h_bytes"] / args.steps,
-               "call": "mt_system_compute (drop-in compute(): create + upload, fused windows, hydrolysis uploads, stride downloads)",
+               "call": "mt_system_compute (drop-in compute(): create + upload, fused windows, hydrolysis uploads, stride downloads, DCD output)",
                "wall_s": float(tw.item())}
         e2e_sys.close()
 

@@ -42,6 +42,8 @@ int *mt_system_gtp(mt_system *s);
 int *mt_system_on_tubule(mt_system *s, int prev);
 unsigned char *mt_system_extra(mt_system *s);
 double *mt_system_energies(mt_system *s);         /* [n_tr][7] after a compute with output_energy */
+/* srand(seed) of the reference main (main.cpp:67) for this system's host events (same sequence as libc rand()) */
+int mt_system_srand(mt_system *s, unsigned seed);
 int mt_system_set_ngpus(mt_system *s, int n_gpus);
 int mt_system_set_steps(mt_system *s, long long steps);
 

@@ -6,6 +6,21 @@ Only what the hot path needs lives here:
   capi.py   ctypes bindings          api.py        HostSystem / Engine (reference vocabulary)
   structures.py  lattice generators  workspace.py  run directories of the BASELINE configs
   build.py  in-tree build of all native artefacts
+
+The bindings load lazily so that `python -m mt_b200.build` works before the libraries exist; touching
+Engine / HostSystem / capi without built libraries raises ImportError (there is no Python or CPU fallback).
 """
-from .capi import MaddyError, generate_seeds, read_dcd  # noqa: F401
-from .api import Engine, HostSystem  # noqa: F401
+import importlib
+
+_LAZY = {
+    "MaddyError": "capi", "generate_seeds": "capi", "read_dcd": "capi",
+    "Engine": "api", "HostSystem": "api",
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        return getattr(importlib.import_module(f".{_LAZY[name]}", __name__), name)
+    if name in ("capi", "api", "build", "structures", "workspace"):
+        return importlib.import_module(f".{name}", __name__)
+    raise AttributeError(name)

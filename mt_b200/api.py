@@ -152,6 +152,10 @@ class HostSystem:
             raise MaddyError(1, capi.hostlib.mt_host_last_error().decode())
         return {"steps": int(st[0]), "launches": int(st[1]), "h2d_bytes": st[2], "d2h_bytes": st[3]}
 
+    def srand(self, seed: int):
+        """srand(seed) for this system's host events (hydrolysis, insertion): same sequence as libc rand()"""
+        capi.hostlib.mt_system_srand(self._h, int(seed) & 0xffffffff)
+
     def mt_length(self, step: int) -> np.ndarray:
         out = np.zeros(self.Ntr, dtype=np.int32)
         if capi.hostlib.mt_system_mt_length(self._h, int(step), as_ptr(out, C.c_int)):

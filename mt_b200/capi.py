@@ -99,7 +99,7 @@ KERNEL_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
-    "mt_system_gtp", "mt_system_on_tubule", "mt_system_extra", "mt_system_energies", "mt_system_set_ngpus",
+    "mt_system_gtp", "mt_system_on_tubule", "mt_system_extra", "mt_system_energies", "mt_system_set_ngpus", "mt_system_srand",
     "mt_system_set_steps", "mt_system_compute", "mt_system_mt_length", "mt_system_hydrolyse", "mt_system_change_conc",
     "mt_system_save_pdb", "mt_dcd_read", "mt_pdb_count",
 ]
@@ -141,6 +141,7 @@ _sig(hostlib.mt_system_on_tubule, _pi, [_vp, _i])
 _sig(hostlib.mt_system_extra, _pu8, [_vp])
 _sig(hostlib.mt_system_energies, _pd, [_vp])
 _sig(hostlib.mt_system_set_ngpus, _i, [_vp, _i])
+_sig(hostlib.mt_system_srand, _i, [_vp, _u])
 _sig(hostlib.mt_system_set_steps, _i, [_vp, _ll])
 _sig(hostlib.mt_system_compute, _i, [_vp, _i, _pd])
 _sig(hostlib.mt_system_mt_length, _i, [_vp, _ll, _pi])

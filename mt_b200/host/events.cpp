@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <map>
 #include "mt_host.hpp"
 
 namespace mt {
@@ -94,6 +95,7 @@ void update(System &s, long long step, std::vector<int> &)
         save_coord_dcd(s);
         if (s.hp.hydrolysis && (step % (s.hp.stride * 10) == 0)) {
             if (step == 0) {
+                if (s.writer) s.writer->drain();
                 FILE *first = fopen("dcd/hydrolysis.pdb", "w");
                 if (first) fclose(first);
             }
@@ -162,8 +164,8 @@ int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len)
                     s.extra[q + 1] = 0;
                     float x, y;
                     for (;;) {
-                        x = par.rep_r - 2 * (rand() % int(par.rep_r));
-                        y = par.rep_r - 2 * (rand() % int(par.rep_r));
+                        x = par.rep_r - 2 * (s.rng.next() % int(par.rep_r));
+                        y = par.rep_r - 2 * (s.rng.next() % int(par.rep_r));
                         if (x * x + y * y <= par.rep_r * par.rep_r) { // inside the cylinder
                             if (!s.quiet) printf("New x,y coordinates for extra particle: %f  %f index: %d\n", x, y, (int)q);
                             num_of_extra -= 2;
@@ -197,28 +199,50 @@ int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len)
 // ---------------------------------------------------------------- hydrolysis (updater.cpp:229-257)
 void hydrolyse(System &s)
 {
-    const int N = s.par.n_tot, Ntr = s.par.n_tr;
-    for (int i = 0; i < N; i += 2)
+    // Same events, same draw order (dimer-outer / trajectory-inner, one draw per eligible dimer) as the reference;
+    // the eligibility test is hoisted into a memory-order pre-pass so the draw loop walks a dense byte table
+    // instead of four arrays with a stride of Ntot ints.
+    const int N = s.par.n_tot, Ntr = s.par.n_tr, nd = N / 2;
+    std::vector<unsigned char> elig((size_t)nd * Ntr);
+    for (int tr = 0; tr < Ntr; tr++) {
+        const size_t o = (size_t)tr * N;
+        for (int d = 0; d < nd; d++) {
+            const size_t q = o + 2 * d;
+            elig[(size_t)d * Ntr + tr] = s.gtp[q] == 1 && !s.extra[q] && s.on_tubule_cur[q] * s.on_tubule_prev[q] == 1;
+        }
+    }
+    const unsigned char *e = elig.data();
+    for (int d = 0; d < nd; d++)
+        for (int tr = 0; tr < Ntr; tr++, e++) {
+            if (!*e) continue;
+            double prob = s.rng.next() / (double)RAND_MAX;
+            if (prob < 0.02) {
+                const size_t q = 2 * d + (size_t)tr * N;
+                s.gtp[q] = 0;
+                s.gtp[q + 1] = 0;
+                if (!s.quiet) printf("*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", d, tr);
+            }
+        }
+    // GDP dimers that are off the tubule now and at the previous stride return to GTP (no draw)
+    if (s.quiet) {
         for (int tr = 0; tr < Ntr; tr++) {
-            const size_t q = i + (size_t)tr * N;
-            if (s.gtp[q] == 1 && !s.extra[q] && s.on_tubule_cur[q] * s.on_tubule_prev[q] == 1) {
-                double prob = rand() / (double)RAND_MAX;
-                if (prob < 0.02) {
-                    s.gtp[q] = 0;
-                    s.gtp[q + 1] = 0;
-                    if (!s.quiet) printf("*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", i / 2, tr);
+            const size_t o = (size_t)tr * N;
+            for (int d = 0; d < nd; d++) {
+                const size_t q = o + 2 * d;
+                if (s.gtp[q] == 0 && !s.extra[q] && s.on_tubule_cur[q] == 0 && s.on_tubule_prev[q] == 0) s.gtp[q] = s.gtp[q + 1] = 1;
+            }
+        }
+    } else {
+        for (int i = 0; i < N - 1; i += 2)
+            for (int tr = 0; tr < Ntr; tr++) {
+                const size_t q = i + (size_t)tr * N;
+                if (s.gtp[q] == 0 && !s.extra[q] && s.on_tubule_cur[q] == 0 && s.on_tubule_prev[q] == 0) {
+                    s.gtp[q] = 1;
+                    s.gtp[q + 1] = 1;
+                    printf("*** Transition to GTP occured to dimer # %d trajectory #%d ***\n", i / 2, tr);
                 }
             }
-        }
-    for (int i = 0; i < N; i += 2)
-        for (int tr = 0; tr < Ntr; tr++) {
-            const size_t q = i + (size_t)tr * N;
-            if (s.gtp[q] == 0 && !s.extra[q] && s.on_tubule_cur[q] == 0 && s.on_tubule_prev[q] == 0) {
-                s.gtp[q] = 1;
-                s.gtp[q + 1] = 1;
-                if (!s.quiet) printf("*** Transition to GTP occured to dimer # %d trajectory #%d ***\n", i / 2, tr);
-            }
-        }
+    }
 }
 
 // ---------------------------------------------------------------- the step loop
@@ -241,8 +265,32 @@ void ck(int rc, maddy_handle *h, const char *what)
 }
 } // namespace
 
+namespace {
+// MADDY_HOST_PROFILE=1: wall-clock breakdown of the host side of the step loop on stderr
+struct Prof {
+    bool on = getenv("MADDY_HOST_PROFILE") != nullptr;
+    std::map<std::string, double> acc;
+    double t0 = 0;
+    static double now()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    void begin() { if (on) t0 = now(); }
+    void end(const char *what) { if (on) acc[what] += now() - t0; }
+    ~Prof()
+    {
+        if (on)
+            for (auto &kv : acc) fprintf(stderr, "[maddy host profile] %-18s %8.3f ms\n", kv.first.c_str(), kv.second * 1e3);
+    }
+};
+} // namespace
+
 void compute(System &s, bool fused, ComputeStats *stats)
 {
+    Prof prof;
+    prof.begin();
     const maddy_params &par = s.par;
     const HostParams &hp = s.hp;
     const int N = par.n_tot, Ntr = par.n_tr;
@@ -277,7 +325,17 @@ void compute(System &s, bool fused, ComputeStats *stats)
         if (rc != MADDY_OK) die("maddy_create failed (%d): %s", rc, maddy_last_error(nullptr));
         st.h2d_bytes += (double)d.count * N * (7 * 4 + 32 + 3);
     }
+    prof.end("create");
     if (!s.quiet) printf("Using %d device(s), first device %d\n", G, par.device);
+    struct WriterScope { // background trajectory output for the duration of the loop
+        System &s;
+        explicit WriterScope(System &sys) : s(sys) { if (s.write_files) s.writer = std::make_shared<OutputWorker>(); }
+        ~WriterScope()
+        {
+            s.writer.reset();       // joins the thread (pending frames are written first)
+            s.writer_files.reset(); // closes the per-trajectory files
+        }
+    } writer_scope(s);
     s.energies.assign((size_t)Ntr * 7, 0.0);
 
     std::vector<int> mt_len(Ntr, 0), mt_len_prev(Ntr, 0);
@@ -299,18 +357,23 @@ void compute(System &s, bool fused, ComputeStats *stats)
         const bool may_teleport = stride_now && hp.tub_length && step != 0 && hp.is_const_conc;
         // energies printed at a stride step are evaluated on the lists rebuilt at that step (compute_cuda.cu:1140-1170)
         const bool explicit_rebuild = rebuild_now && ((stride_now && hp.out_energy) || may_teleport || par.tea_on || !fused);
+        prof.begin();
         if (explicit_rebuild) {
             for_each([&](Shard &d) {
                 if (par.lj_on) ck(maddy_rebuild_lj(d.h), d.h, "maddy_rebuild_lj");
                 if (par.is_assembly) ck(maddy_rebuild_bonds(d.h), d.h, "maddy_rebuild_bonds");
             });
         }
+        prof.end("explicit rebuild");
+        prof.begin();
         // ---- hydrolysis (compute_cuda.cu:1153-1160)
         if (hp.hydrolysis && step % hp.hydrostep == 0 && step != 0) {
             if (hydrolysed_for != step) hydrolyse(s);
             for_each([&](Shard &d) { ck(maddy_upload_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_upload_gtp"); });
             st.h2d_bytes += (double)n;
         }
+        prof.end("upload gtp");
+        prof.begin();
         // ---- stride block (compute_cuda.cu:1163-1226)
         if (stride_now) {
             if (hp.out_energy) {
@@ -353,6 +416,8 @@ void compute(System &s, bool fused, ComputeStats *stats)
                 update(s, step, mt_len);
             }
         }
+        prof.end("stride block");
+        prof.begin();
         // ---- steps up to the next host event
         long long next = hp.steps;
         next = std::min(next, (step / hp.stride + 1) * hp.stride);
@@ -377,18 +442,29 @@ void compute(System &s, bool fused, ComputeStats *stats)
         } else {
             for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, explicit_rebuild ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u), d.h, "maddy_run"); });
         }
+        prof.end("launch window");
+        prof.begin();
         // overlap with the asynchronous window: evaluate the next hydrolysis event on the host now
         if (hp.hydrolysis && next < hp.steps && next % hp.hydrostep == 0 && next != 0) {
             hydrolyse(s);
             hydrolysed_for = next;
         }
+        prof.end("hydrolyse (host)");
         step = next;
         st.steps += count;
     }
+    prof.begin();
+    if (s.writer) {
+        s.writer->drain();
+        s.writer_files.reset();
+    }
+    prof.end("drain writer");
+    prof.begin();
     for_each([&](Shard &d) {
         ck(maddy_sync(d.h), d.h, "maddy_sync");
         st.launches += maddy_launch_count(d.h);
     });
+    prof.end("final sync");
     if (stats) *stats = st;
 }
 

@@ -77,6 +77,11 @@ int *mt_system_gtp(mt_system *s) { return s->sys.gtp.data(); }
 int *mt_system_on_tubule(mt_system *s, int prev) { return prev ? s->sys.on_tubule_prev.data() : s->sys.on_tubule_cur.data(); }
 unsigned char *mt_system_extra(mt_system *s) { return s->sys.extra.data(); }
 double *mt_system_energies(mt_system *s) { return s->sys.energies.data(); }
+int mt_system_srand(mt_system *s, unsigned seed)
+{
+    s->sys.rng.seed(seed);
+    return 0;
+}
 int mt_system_set_ngpus(mt_system *s, int n)
 {
     s->sys.hp.n_gpus = n;

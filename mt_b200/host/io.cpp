@@ -9,6 +9,8 @@
  *   XYZ     src/xyzio.cpp:16-44 (read), :73-92 (write)
  */
 #include <cerrno>
+#include <charconv>
+#include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -231,15 +233,73 @@ void read_pdb(const std::string &filename, PDB &pdb, bool quiet)
     }
 }
 
+// ATOM lines, byte-identical to the reference's
+//   fprintf("ATOM  %5d %-4s%c%3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n")      (pdbio.cpp:291-345; %5x from 100000 atoms)
+// but formatted with std::to_chars (correctly rounded like printf, ~10x faster: the hydrolysis dump prints
+// Ntot*Ntr lines every 10 strides) into one buffer and written with a single fwrite.
+static char *put_fixed(char *o, double v, int width, int prec)
+{
+    char tmp[64];
+    auto res = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::fixed, prec);
+    const int len = (int)(res.ptr - tmp);
+    for (int k = len; k < width; k++) *o++ = ' ';
+    memcpy(o, tmp, len);
+    return o + len;
+}
+static char *put_int(char *o, long v, int width, int base = 10)
+{
+    char tmp[32];
+    auto res = std::to_chars(tmp, tmp + sizeof tmp, v, base);
+    const int len = (int)(res.ptr - tmp);
+    for (int k = len; k < width; k++) *o++ = ' ';
+    memcpy(o, tmp, len);
+    return o + len;
+}
 static void print_atoms(FILE *f, const PDB &pdb)
 {
     const bool hex = pdb.atoms.size() >= 100000;
+    std::vector<char> buf;
+    buf.resize(pdb.atoms.size() * 96 + 16);
+    char *o = buf.data();
     for (size_t i = 0; i < pdb.atoms.size(); i++) {
         const PDBAtom &a = pdb.atoms[i];
-        fprintf(f, hex ? "ATOM  %5x %-4s%c%3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n"
-                       : "ATOM  %5d %-4s%c%3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n",
-                (int)i + 1, a.name, a.altLoc, a.resName, a.chain, a.resid, a.x, a.y, a.z, a.occupancy, a.beta);
+        if (!std::isfinite(a.x) || !std::isfinite(a.y) || !std::isfinite(a.z) || fabs(a.x) > 1e15 || fabs(a.y) > 1e15 || fabs(a.z) > 1e15) {
+            // keep printf's spelling of nan/inf and of absurdly wide numbers
+            o += snprintf(o, 200, hex ? "ATOM  %5x %-4s%c%3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n"
+                                      : "ATOM  %5d %-4s%c%3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n",
+                          (int)i + 1, a.name, a.altLoc, a.resName, a.chain, a.resid, a.x, a.y, a.z, a.occupancy, a.beta);
+        } else {
+            memcpy(o, "ATOM  ", 6);
+            o += 6;
+            o = put_int(o, (long)i + 1, 5, hex ? 16 : 10);
+            *o++ = ' ';
+            int nl = (int)strnlen(a.name, 4);
+            memcpy(o, a.name, nl);
+            o += nl;
+            for (int k = nl; k < 4; k++) *o++ = ' ';
+            *o++ = a.altLoc;
+            int rl = (int)strnlen(a.resName, 3);
+            for (int k = rl; k < 3; k++) *o++ = ' ';
+            memcpy(o, a.resName, rl);
+            o += rl;
+            *o++ = ' ';
+            *o++ = a.chain;
+            o = put_int(o, a.resid, 4);
+            memcpy(o, "    ", 4);
+            o += 4;
+            o = put_fixed(o, a.x, 8, 3);
+            o = put_fixed(o, a.y, 8, 3);
+            o = put_fixed(o, a.z, 8, 3);
+            o = put_fixed(o, a.occupancy, 6, 2);
+            o = put_fixed(o, a.beta, 6, 2);
+            *o++ = '\n';
+        }
+        if ((size_t)(o - buf.data()) + 256 > buf.size()) { // lines longer than expected: flush
+            fwrite(buf.data(), 1, o - buf.data(), f);
+            o = buf.data();
+        }
     }
+    fwrite(buf.data(), 1, o - buf.data(), f);
 }
 void write_pdb(const std::string &filename, const PDB &pdb, bool quiet)
 {

@@ -21,7 +21,7 @@ int main(int argc, char *argv[])
         std::vector<std::string> overrides;
         for (int i = 2; i < argc; i++) overrides.emplace_back(argv[i]);
         mt::init_parameters(s, argv[1], overrides);
-        srand(s.par.rseed);
+        s.rng.seed(s.par.rseed); // srand(par.rseed) of the reference (main.cpp:67), private state
         mt::init_timer(s);
         if (s.par.is_assembly) mt::assembly_init(s);
         mt::compute(s, true, nullptr);

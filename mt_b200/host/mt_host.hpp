@@ -9,8 +9,15 @@
  * turns that into the reference's "Fatal error!" + exit(-1), the Python binding into a status).
  */
 #pragma once
+#include <condition_variable>
+#include <cstdint>
 #include <cstdio>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -95,7 +102,64 @@ struct HostParams { // scalars of `Parameters` that only the host uses
     int n_gpus = 1; // extension key `n_gpus` (default 1): shard trajectories over this many devices
 };
 
+// In-order background writer for trajectory output: the step loop hands over a snapshot of
+// the host coordinates and keeps the GPU busy while frames are formatted and appended to the per-trajectory files.
+class OutputWorker {
+  public:
+    OutputWorker();
+    ~OutputWorker();
+    void submit(std::function<void()> job); // blocks while two jobs are already pending
+    void drain();                           // waits for all jobs; rethrows the first failure
+  private:
+    void loop();
+    std::thread thread_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    bool stop_ = false, busy_ = false;
+    std::string error_;
+};
+
+// The reference's host events draw from libc rand() after srand(rseed) (main.cpp:67, updater.cpp:118,235).  This is
+// the same generator (glibc TYPE_3 additive feedback, identical sequence — checked in tests/test_events.py) held in
+// a private state: no global lock per draw (hydrolysis makes ~66 k draws per event at 256 trajectories) and no
+// interference from other users of rand() in the process.
+class HostRand {
+  public:
+    HostRand() { seed(1); }
+    // glibc srandom_r for the 31-word additive-feedback generator (TYPE_3, x^31 + x^3 + 1) that rand() uses
+    void seed(unsigned s)
+    {
+        int32_t word = s ? (int32_t)s : 1;
+        r_[0] = word;
+        for (int i = 1; i < 31; i++) { // 16807 * word mod (2^31 - 1), Schrage
+            const long hi = word / 127773, lo = word % 127773;
+            word = (int32_t)(16807 * lo - 2836 * hi);
+            if (word < 0) word += 2147483647;
+            r_[i] = word;
+        }
+        f_ = 3;
+        b_ = 0;
+        for (int i = 0; i < 310; i++) next();
+    }
+    inline int next()
+    {
+        const uint32_t v = (uint32_t)r_[f_] + (uint32_t)r_[b_];
+        r_[f_] = (int32_t)v;
+        if (++f_ >= 31) f_ = 0;
+        if (++b_ >= 31) b_ = 0;
+        return (int)(v >> 1);
+    }
+
+  private:
+    int32_t r_[31];
+    int f_ = 3, b_ = 0;
+};
+
 struct System {
+    HostRand rng;
+    std::shared_ptr<OutputWorker> writer; // set by compute() while the loop runs; null = synchronous output
+    std::shared_ptr<void> writer_files;   // append-mode handles the writer keeps open during the loop
     maddy_params par{};
     HostParams hp;
     ParamTable table;

@@ -7,6 +7,7 @@
  * REPLACES the table), derived constants (gamma, var, barrier widths, hydrostep) evaluated with
  * the reference's float/double mix, and the topology rules.
  */
+#include <cerrno>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -346,43 +347,178 @@ void save_coord_pdb(System &s, const std::string &xyz, const std::string &ang)
     write_pdb(ang, out, s.quiet);
 }
 
-void save_coord_dcd(System &s)
+// ------------------------------------------------------------------ background output
+OutputWorker::OutputWorker() : thread_([this] { loop(); }) {}
+OutputWorker::~OutputWorker()
 {
-    // one frame per trajectory into <dcd_xyz> (x,y,z) and <dcd_ang> (fi,psi,theta)
-    const int N = s.par.n_tot;
-    std::vector<float> X(N), Y(N), Z(N);
-    for (int t = 0; t < s.par.n_tr; t++) {
-        for (int pass = 0; pass < 2; pass++) {
-            for (int i = 0; i < N; i++) {
-                const float *c = &s.r[((size_t)t * N + i) * 7];
-                X[i] = pass ? c[3] : c[0];
-                Y[i] = pass ? c[5] : c[1];
-                Z[i] = pass ? c[4] : c[2];
+    {
+        std::lock_guard<std::mutex> g(m_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    if (thread_.joinable()) thread_.join();
+}
+void OutputWorker::loop()
+{
+    for (;;) {
+        std::function<void()> job;
+        {
+            std::unique_lock<std::mutex> g(m_);
+            cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+            if (q_.empty()) return;
+            job = std::move(q_.front());
+            q_.pop_front();
+            busy_ = true;
+        }
+        try {
+            job();
+        } catch (const std::exception &e) {
+            std::lock_guard<std::mutex> g(m_);
+            if (error_.empty()) error_ = e.what();
+        }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            busy_ = false;
+        }
+        cv_.notify_all();
+    }
+}
+void OutputWorker::submit(std::function<void()> job)
+{
+    std::unique_lock<std::mutex> g(m_);
+    cv_.wait(g, [this] { return q_.size() < 2; });
+    q_.push_back(std::move(job));
+    cv_.notify_all();
+}
+void OutputWorker::drain()
+{
+    std::unique_lock<std::mutex> g(m_);
+    cv_.wait(g, [this] { return q_.empty() && !busy_; });
+    if (!error_.empty()) {
+        std::string e = error_;
+        error_.clear();
+        throw Fatal(e);
+    }
+}
+
+// Append-mode file handles kept open across strides (the reference re-opens and closes 2*Ntr files per stride:
+// at 256 trajectories that is ~15 ms of syscalls per stride).  Falls back to open/close when descriptors run out.
+class AppendFiles {
+  public:
+    ~AppendFiles() { close_all(); }
+    void append(const std::string &name, const void *data, size_t bytes)
+    {
+        FILE *f = nullptr;
+        auto it = open_.find(name);
+        if (it != open_.end()) f = it->second;
+        else {
+            f = fopen(name.c_str(), "a");
+            if (!f && (errno == EMFILE || errno == ENFILE)) {
+                close_all();
+                f = fopen(name.c_str(), "a");
             }
-            const std::string &name = pass ? s.hp.dcd_ang[t] : s.hp.dcd_xyz[t];
-            FILE *f = fopen(name.c_str(), "a");
             if (!f) die("Opening file '%s'", name.c_str());
-            dcd_write_frame(f, N, X.data(), Y.data(), Z.data());
-            fclose(f);
+            if (open_.size() < kMaxOpen) open_[name] = f;
+            else transient_ = f;
+        }
+        const bool ok = fwrite(data, 1, bytes, f) == bytes && fflush(f) == 0;
+        if (transient_) {
+            fclose(transient_);
+            transient_ = nullptr;
+        }
+        if (!ok) die("Writing file '%s'", name.c_str());
+    }
+    void close_all()
+    {
+        for (auto &kv : open_) fclose(kv.second);
+        open_.clear();
+    }
+
+  private:
+    static constexpr size_t kMaxOpen = 768;
+    std::map<std::string, FILE *> open_;
+    FILE *transient_ = nullptr;
+};
+
+// one frame per trajectory appended to <dcd_xyz> (x,y,z) and <dcd_ang> (fi,psi,theta); each frame is assembled in
+// memory and written with a single fwrite (the reference does open / 9 small fwrites / close per file)
+static void write_dcd_frames(const std::vector<float> &r, int N, int Ntr, const std::vector<std::string> &xyz,
+                             const std::vector<std::string> &ang, AppendFiles *files = nullptr)
+{
+    AppendFiles local;
+    if (!files) files = &local;
+    const size_t frame_bytes = 3 * ((size_t)N * 4 + 8);
+    std::vector<char> buf(frame_bytes);
+    const int len = N * 4;
+    for (int t = 0; t < Ntr; t++) {
+        for (int pass = 0; pass < 2; pass++) {
+            static const int col[2][3] = {{0, 1, 2}, {3, 5, 4}};
+            char *o = buf.data();
+            for (int k = 0; k < 3; k++) {
+                memcpy(o, &len, 4);
+                o += 4;
+                float *dst = reinterpret_cast<float *>(o);
+                const float *src = &r[(size_t)t * N * 7 + col[pass][k]];
+                for (int i = 0; i < N; i++) dst[i] = src[(size_t)i * 7];
+                o += (size_t)N * 4;
+                memcpy(o, &len, 4);
+                o += 4;
+            }
+            files->append(pass ? ang[t] : xyz[t], buf.data(), frame_bytes);
         }
     }
 }
 
-void append_coord_pdb(System &s)
+void save_coord_dcd(System &s)
 {
-    const int N = s.par.n_tot;
-    for (int t = 0; t < s.par.n_tr; t++)
+    if (s.writer) {
+        auto snap = std::make_shared<std::vector<float>>(s.r);
+        const int N = s.par.n_tot, Ntr = s.par.n_tr;
+        const HostParams *hp = &s.hp;
+        auto files = std::static_pointer_cast<AppendFiles>(s.writer_files);
+        if (!files) {
+            files = std::make_shared<AppendFiles>();
+            s.writer_files = files;
+        }
+        s.writer->submit([snap, N, Ntr, hp, files] { write_dcd_frames(*snap, N, Ntr, hp->dcd_xyz, hp->dcd_ang, files.get()); });
+    } else {
+        write_dcd_frames(s.r, s.par.n_tot, s.par.n_tr, s.hp.dcd_xyz, s.hp.dcd_ang);
+    }
+}
+
+// dcd/hydrolysis.pdb: every monomer of every trajectory with occupancy = GTP flag, beta = trajectory
+// (preparator.cpp:604-636); formatted from snapshots so that it can run on the output thread
+static void write_hydrolysis_pdb(const PDB &tmpl, const std::vector<float> &r, const std::vector<int> &gtp, int N, int Ntr, bool quiet)
+{
+    PDB out;
+    out.atoms.resize((size_t)N * Ntr);
+    for (int t = 0; t < Ntr; t++)
         for (int i = 0; i < N; i++) {
             const size_t q = (size_t)t * N + i;
-            PDBAtom &a = s.coordspdb.atoms[q];
-            a.x = s.r[q * 7 + 0];
-            a.y = s.r[q * 7 + 1];
-            a.z = s.r[q * 7 + 2];
+            PDBAtom a = tmpl.atoms[i];
+            a.x = r[q * 7 + 0];
+            a.y = r[q * 7 + 1];
+            a.z = r[q * 7 + 2];
             a.id = (int)q;
             a.beta = (double)t;
-            a.occupancy = (double)s.gtp[q];
+            a.occupancy = (double)gtp[q];
+            out.atoms[q] = a;
         }
-    append_pdb("dcd/hydrolysis.pdb", s.coordspdb, s.quiet);
+    append_pdb("dcd/hydrolysis.pdb", out, quiet);
+}
+
+void append_coord_pdb(System &s)
+{
+    const int N = s.par.n_tot, Ntr = s.par.n_tr;
+    if (s.writer) {
+        auto r = std::make_shared<std::vector<float>>(s.r);
+        auto g = std::make_shared<std::vector<int>>(s.gtp);
+        const PDB *tmpl = &s.pdb;
+        const bool quiet = s.quiet;
+        s.writer->submit([r, g, tmpl, N, Ntr, quiet] { write_hydrolysis_pdb(*tmpl, *r, *g, N, Ntr, quiet); });
+    } else {
+        write_hydrolysis_pdb(s.pdb, s.r, s.gtp, N, Ntr, s.quiet);
+    }
 }
 
 void read_restart(System &s)

@@ -25,7 +25,7 @@ def test_hydrolysis_uses_libc_rand_in_reference_order(rundir, load_system):
     s.on_tubule_cur[:] = 1
     s.on_tubule_prev[:] = 1
     s.on_tubule_cur[2, 100:104] = 0   # not on tubule now -> not a candidate (and consumes no rand())
-    libc.srand(1234567)
+    s.srand(1234567)
     s.hydrolyse()
     got = s.gtp.copy()
     # replay the stream
@@ -43,7 +43,7 @@ def test_hydrolysis_uses_libc_rand_in_reference_order(rundir, load_system):
     s.on_tubule_cur[idx[0], idx[1] - idx[1] % 2] = 0
     s.on_tubule_prev[idx[0], idx[1] - idx[1] % 2] = 0
     before = (s.gtp == 0).sum()
-    libc.srand(1)
+    s.srand(1)
     s.hydrolyse()
     assert s.gtp[idx[0], idx[1]] == 1
 
@@ -53,7 +53,7 @@ def test_change_conc_inserts_reserve_dimers(rundir, load_system):
     s = load_system(d, ["is_const_conc=yes", "conc=30", "rep_r=20", "rep_h=60", "repulsive_walls=yes"])
     assert s.extra.sum() == 2 * 78
     mt_len = np.array([260, 260], dtype=np.int32)
-    libc.srand(7)
+    s.srand(7)
     changed = s.change_conc(np.zeros(2, dtype=np.int32), mt_len)
     # V = 3.14 r^2 h ; dimers wanted: conc * V * 6e-7
     want = int(np.ceil(30 * 3.14 * 20 * 20 * 60 * 6e-7))

@@ -21,11 +21,9 @@ def test_host_compute_sharded_equals_single_gpu(rundir, load_system):
     d = rundir("mt40_single", runnum=5, steps=250, stride=100)
     a = load_system(d)
     b = load_system(d)
-    import ctypes
-    libc = ctypes.CDLL("libc.so.6")
-    libc.srand(1234567)
+    a.srand(1234567)
     a.compute(n_gpus=1)
-    libc.srand(1234567)
+    b.srand(1234567)
     b.compute(n_gpus=2)
     assert np.array_equal(a.coords, b.coords) and np.array_equal(a.gtp, b.gtp)
     assert np.array_equal(a.energies, b.energies)

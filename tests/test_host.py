@@ -115,3 +115,28 @@ def test_dcd_and_pdb_writers_roundtrip(tmp_path):
     assert raw[100:100 + 26] == b"REMARKS CREATED BY dcdio.c"
     assert mt_b200.read_dcd(d / "dcd" / "run_0.dcd").shape == (0, 520, 3)
     s.close()
+
+
+def test_pdb_writer_matches_printf_formatting(tmp_path):
+    """The fast ATOM-line formatter (std::to_chars) must be byte-identical to the reference's fprintf format."""
+    from mt_b200 import capi
+    d = workspace.make_baseline_rundir(tmp_path / "r", "mt40_single", runnum=1)
+    with workspace.chdir(d):
+        s = HostSystem("config.conf")
+    rng = np.random.default_rng(0)
+    c = s.coords
+    c[0, :, :3] = rng.normal(0, 90, (520, 3)).astype(np.float32)
+    c[0, :10, 0] = [0.0005, -0.0005, 1.0005, 2.5, -0.0, 999.9995, -99.9995, 0.0015, 0.0025, 1e-9]
+    c[0, :, 3:6] = rng.normal(0, 3, (520, 3)).astype(np.float32)
+    assert capi.hostlib.mt_system_save_pdb(s._h, str(d / "x.pdb").encode(), str(d / "a.pdb").encode()) == 0
+    xyz = (d / "x.pdb").read_text().split("\n")
+    ang = (d / "a.pdb").read_text().split("\n")
+    assert xyz[520] == "END" and len(xyz) == 521
+    for i in range(520):
+        x, y, z, fi, theta, psi = (float(v) for v in c[0, i, :6])
+        name = "CA" if i % 2 == 0 else "CB"
+        chain = chr(ord("A") + i // 40)
+        head = "ATOM  %5d %-4s%c%3s %c%4d    " % (i + 1, name, " ", "ALA", chain, (i % 40) // 2 + 1)
+        assert xyz[i] == head + "%8.3f%8.3f%8.3f%6.2f%6.2f" % (x, y, z, 0.0, 8.12)
+        assert ang[i] == head + "%8.3f%8.3f%8.3f%6.2f%6.2f" % (fi, psi, theta, 0.0, 8.12)
+    s.close()
