@@ -358,6 +358,9 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             pool_req(&a.tea_ci, n);
             pool_req(&a.tea_eps, n);
             pool_req(&a.tea_beta, (size_t)ntr);
+            pool_req(&a.tea_co, n);
+            pool_req(&a.tea_mf, n);
+            pool_req(&a.tea_rf, n);
         }
         CK(pool_commit(h, reqs));
         CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
@@ -727,7 +730,7 @@ extern "C" int maddy_tea_update(maddy_handle *h, long long step)
     CU(h, cudaSetDevice(h->p.device));
     cudaError_t e = launch_tea_kernels(kargs(h, OP_TEA_EPS), 0, step, h->stream);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "TEA epsilon kernel: %s", cudaGetErrorString(e));
-    h->launches++;
+    h->launches += 3;
     // the reference aborts the process on capricious violations (bdhitea.cu:89-107): surface them here
     CU(h, cudaMemcpyAsync(h->h_status, h->a.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -745,7 +748,7 @@ extern "C" int maddy_tea_integrate(maddy_handle *h)
     CU(h, cudaSetDevice(h->p.device));
     cudaError_t e = launch_tea_kernels(kargs(h, 0), 1, 0, h->stream);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "TEA integrate kernel: %s", cudaGetErrorString(e));
-    h->launches++;
+    h->launches += 2;
     return MADDY_OK;
 }
 

@@ -60,6 +60,7 @@ struct DevSys {
     float4 *tea_ci;
     float *tea_eps;
     float *tea_beta;
+    float4 *tea_co, *tea_mf, *tea_rf; // per-step snapshots: coordinates (+extra in .w), molecular force, random force
 };
 
 // Near list (shared memory, fused loop only): all j != i with centre distance < MD_NEAR_R at the last
