@@ -30,7 +30,7 @@ struct maddy_handle {
     DevSys a;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int mpt = 1, threads = 32, nbuf = 2, near_cap = 0, shape = 0, rng_smem_offset = 0;
+    int mpt = 1, threads = 32, nbuf = 2, near_cap = 0, shape = 0, rng_smem_offset = 0, topo_smem_offset = -1;
     size_t smem = 0;
     CutTest cut_pairs, cut_force;
     std::string err;
@@ -130,6 +130,7 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
     k.nbuf = h->nbuf;
     k.near_cap = h->near_cap;
     k.rng_smem_offset = h->rng_smem_offset;
+    k.topo_smem_offset = h->topo_smem_offset;
     {
         const float rb = fmaxf(h->p.lj_on ? h->p.ljpairscutoff : 0.f, 7.0f) + MD_CAND_SKIN;
         k.rcand2 = rb * rb;
@@ -314,16 +315,23 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             const bool want2 = force_shape ? force_shape[0] == '1' : ntr > n_sm;
             if (N <= MD_MAX_THREADS && want2) {
                 // two CTAs per SM: near list capped at 20 rows, RNG streams (32 B per monomer) parked in shared memory
-                const int cap2 = h->near_cap > 20 ? 20 : h->near_cap;
+                // two CTAs per SM: near list capped at 16 rows, RNG streams (32 B per monomer) and the packed
+                // topology words (16 B per monomer) parked in shared memory
+                const int cap2 = h->near_cap > 16 ? 16 : h->near_cap;
                 size_t sm2 = stage + tiles + (size_t)cap2 * N * 2 + N + 64;
                 sm2 = (sm2 + 15) & ~(size_t)15;
-                const size_t total = sm2 + (size_t)32 * N;
+                const size_t total = sm2 + (size_t)48 * N;
                 if (cap2 >= 12 && 2 * (total + 1792 + 1024) <= 227 * 1024) {
                     h->shape = 1;
                     h->near_cap = cap2;
                     h->rng_smem_offset = (int)sm2;
+                    h->topo_smem_offset = (int)(sm2 + (size_t)32 * N);
                     h->smem = total;
                 }
+            }
+            if (h->shape == 0 && h->smem + (size_t)16 * N + 2048 <= 225 * 1024) { // one CTA per SM: topology words if they fit
+                h->topo_smem_offset = (int)h->smem;
+                h->smem += (size_t)16 * N;
             }
         }
         h->cut_pairs = make_cut(par->ljpairscutoff);

@@ -51,7 +51,37 @@ struct Near { // shared-memory near list of the fused loop (see MD_NEAR_R2 in ma
     float4 *tlo, *thi; // bounding boxes of tiles of MD_TILE consecutive monomers
     int cap, ntiles;
     bool ok;        // CTA-uniform: the near list is valid for this step
+    uint4 *topo;    // [N] packed topology words (see load_topo), or nullptr: read the lists from HBM
 };
+
+// Per-monomer topology words the force evaluation needs every step, packed so that one LDS.128 from the
+// thread's own shared-memory slot replaces six dependent global loads (they change only at list rebuilds):
+//   x = first harmonic entry (raw, signed)        y = harmonic count | longitudinal count << 8 | lateral count << 16
+//   z = longitudinal codes 0,1 (16 bit each)      w = lateral codes 0,1
+// Entries beyond these (rare) are read from the lists in HBM.
+__device__ __forceinline__ uint4 load_topo(const DevSys &a, int traj, int i)
+{
+    const uint16_t *bl = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
+    const uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
+    const unsigned nh = (unsigned)a.harm_count[i], nlong = bc[0], nlat = bc[a.Npad];
+    uint4 t;
+    t.x = (unsigned)a.harm[a.maxH * i];
+    t.y = (nh & 0xffu) | (nlong << 8) | (nlat << 16);
+    t.z = (nlong > 0 ? (unsigned)bl[0] : 0u) | (nlong > 1 ? (unsigned)bl[a.Npad] << 16 : 0u);
+    t.w = (nlat > 0 ? (unsigned)bl[(size_t)a.capLong * a.Npad] : 0u) | (nlat > 1 ? (unsigned)bl[(size_t)(a.capLong + 1) * a.Npad] << 16 : 0u);
+    return t;
+}
+__device__ __forceinline__ int topo_harm(const DevSys &a, const uint4 &t, int i, int k) { return k == 0 ? (int)t.x : a.harm[a.maxH * i + k]; }
+__device__ __forceinline__ unsigned topo_long(const DevSys &a, const uint4 &t, int traj, int i, int k)
+{
+    if (k < 2) return (t.z >> (16 * k)) & 0xffffu;
+    return a.bl[((size_t)traj * (a.capLong + a.capLat) + k) * a.Npad + i];
+}
+__device__ __forceinline__ unsigned topo_lat(const DevSys &a, const uint4 &t, int traj, int i, int k)
+{
+    if (k < 2) return (t.w >> (16 * k)) & 0xffffu;
+    return a.bl[((size_t)traj * (a.capLong + a.capLat) + a.capLong + k) * a.Npad + i];
+}
 
 struct Mono { // register-resident state of one monomer
     float x, y, z, fi, psi, theta;
@@ -90,10 +120,12 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
     const bool gtp_i = (m.flags & MF_GTP) != 0;
     const bool ontub_i = (m.flags & MF_ONTUB) != 0;
 
+    const uint4 tw = near.topo ? near.topo[i] : load_topo(a, traj, i);
+
     // ---- harmonic intra-dimer bond + bending (compute_cuda.cu:70-182)
-    const int nh = a.harm_count[i];
+    const int nh = tw.y & 0xff;
     for (int kk = 0; kk < nh; kk++) {
-        int raw = a.harm[a.maxH * i + kk];
+        const int raw = topo_harm(a, tw, i, kk);
         const float sg = raw < 0 ? 1.0f : -1.0f; // R_MON / r_mon
         const int j = raw < 0 ? -raw : raw;
         const float4 Pj = s.P[j], Ej = s.E[j];
@@ -120,13 +152,10 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         }
     }
 
-    const uint16_t *bl = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
-    const uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
-
     // ---- longitudinal Morse (+ barrier) + bending (compute_cuda.cu:189-299)
-    const int nlong = bc[0];
+    const int nlong = (tw.y >> 8) & 0xff;
     for (int kk = 0; kk < nlong; kk++) {
-        const unsigned code = bl[(size_t)kk * a.Npad];
+        const unsigned code = topo_long(a, tw, traj, i, kk);
         const int j = code >> 1;
         const float sg = (code & 1u) ? 1.0f : -1.0f;
         const float4 Pj = s.P[j], Ej = s.E[j];
@@ -164,12 +193,12 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
     }
 
     // ---- lateral Morse (+ barrier), seam scaling (compute_cuda.cu:304-466)
-    const int nlat = bc[a.Npad];
+    const int nlat = (tw.y >> 16) & 0xff;
     if (nlat > 0) {
         const float4 L1i = s.L1[i], L2i = s.L2[i];
         const int type_i = MF_TYPE(m.flags);
         for (int kk = 0; kk < nlat; kk++) {
-            const unsigned code = bl[(size_t)(a.capLong + kk) * a.Npad];
+            const unsigned code = topo_lat(a, tw, traj, i, kk);
             const int j = code >> 1;
             const bool neg = (code & 1u) != 0;
             // negative entry: i interacts through p1, j through p2; positive: i through p2, j through p1
@@ -791,6 +820,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
     // two-CTA shape: the HybridTaus streams (8 registers) wait in shared memory between integrator calls
     constexpr bool kRngShared = MINB == 2;
     uint4 *srng = reinterpret_cast<uint4 *>(smem) + (k.rng_smem_offset >> 4);
+    near.topo = (k.topo_smem_offset >= 0 && (k.ops & OP_RUN)) ? reinterpret_cast<uint4 *>(smem) + (k.topo_smem_offset >> 4) : nullptr;
 
     Mono mo[MPT];
     int idx[MPT];
@@ -824,6 +854,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
     cs.dirty = false;
 
     if (k.ops & OP_RUN) {
+        if (near.topo) {
+#pragma unroll
+            for (int t = 0; t < MPT; t++)
+                if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
+        }
         int buf = 0;
         int near_state = 0; // 0: not built, 1: valid, 2: overflowed (full list until the next rebuild)
         float gx[MPT], gy[MPT], gz[MPT]; // positions when the near list was formed (displacement guard)
@@ -848,6 +883,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
             if (do_rebuild) {
                 near_state = rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, rops) ? 1 : 2;
                 formed = true;
+                if (near.topo) { // own rows were just rewritten by this thread
+#pragma unroll
+                    for (int t = 0; t < MPT; t++)
+                        if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
+                }
             } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
                 const bool ovf = refresh_near<MPT>(k, s, near, traj, mo, idx);
                 near_state = __syncthreads_or(ovf) ? 2 : 1;

@@ -90,6 +90,7 @@ struct KArgs {
     int nbuf;          // 1 or 2 shared-memory stage buffers
     int near_cap;      // rows of the shared-memory near list (0: fast path disabled)
     int rng_smem_offset; // byte offset of the shared-memory RNG area (two-CTA shape only)
+    int topo_smem_offset; // byte offset of the packed per-monomer topology words, or -1
     float rcand2;      // squared candidate radius: (max(LJ pairs cut-off, near radius) + MD_CAND_SKIN)^2
     CutTest cut_pairs; // LJ list cut-off (ljpairscutoff)
     CutTest cut_force; // LJ force cut-off (6.0)
