@@ -18,20 +18,26 @@
 #include "maddy_kernels.cuh"
 
 namespace maddy {
-cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int shape, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_run_kernel(const KArgs &k, int mpt, int ctas_per_sm, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_phase_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 } // namespace maddy
 
 using namespace maddy;
 
+struct LaunchCfg {
+    int mpt = 1, threads = 32, ctas = 1, nbuf = 1, near_cap = 0, rng_off = 0, topo_off = -1;
+    size_t smem = 0;
+};
+
 struct maddy_handle {
     maddy_params p;
     DevSys a;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int mpt = 1, threads = 32, nbuf = 2, near_cap = 0, shape = 0, rng_smem_offset = 0, topo_smem_offset = -1;
-    size_t smem = 0;
+    LaunchCfg phase, run; // step-granular phase kernel / fused run kernel
+    std::vector<uint16_t> amap, fmap;
     CutTest cut_pairs, cut_force;
     std::string err;
     long long launches = 0;
@@ -127,10 +133,11 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
     k.n_steps = 0;
     k.ops = ops;
     k.run_flags = 0;
-    k.nbuf = h->nbuf;
-    k.near_cap = h->near_cap;
-    k.rng_smem_offset = h->rng_smem_offset;
-    k.topo_smem_offset = h->topo_smem_offset;
+    const LaunchCfg &c = (ops & OP_RUN) ? h->run : h->phase;
+    k.nbuf = c.nbuf;
+    k.near_cap = c.near_cap;
+    k.rng_smem_offset = c.rng_off;
+    k.topo_smem_offset = c.topo_off;
     {
         const float rb = fmaxf(h->p.lj_on ? h->p.ljpairscutoff : 0.f, 7.0f) + MD_CAND_SKIN;
         k.rcand2 = rb * rb;
@@ -164,7 +171,8 @@ static int sync_and_check(maddy_handle *h)
 static int launch(maddy_handle *h, const KArgs &k)
 {
     CU(h, cudaSetDevice(h->p.device));
-    cudaError_t e = launch_traj_kernel(k, h->mpt, h->shape, h->threads, h->smem, h->stream);
+    cudaError_t e = (k.ops & OP_RUN) ? launch_run_kernel(k, h->run.mpt, h->run.ctas, h->run.threads, h->run.smem, h->stream)
+                                     : launch_phase_kernel(k, h->phase.mpt, h->phase.threads, h->phase.smem, h->stream);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "trajectory kernel launch (ops=%u): %s", k.ops, cudaGetErrorString(e));
     h->launches++;
     return MADDY_OK;
@@ -287,51 +295,74 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         a.capLat = par->max_lateral;
         const size_t n = (size_t)ntr * N;
 
-        // launch geometry: MPT monomers per thread, <= MD_MAX_THREADS threads, 64 B of stage per monomer
-        h->mpt = (N + MD_MAX_THREADS - 1) / MD_MAX_THREADS;
-        if (h->mpt > MD_MAX_MPT) {
-            rc = fail(h, MADDY_EINVAL, "n_tot=%d needs %d monomers per thread (max %d)", N, h->mpt, MD_MAX_MPT);
+        // ---- launch geometry.  64 B of stage per monomer; near list 2 B per row and monomer.
+        const bool no_near = getenv("MADDY_NO_NEAR") != nullptr;
+        const size_t tiles = (size_t)2 * 16 * ((N + MD_TILE - 1) / MD_TILE);
+        auto layout = [&](LaunchCfg &c, int nbuf, int cap, bool rng, bool topo) {
+            c.nbuf = nbuf;
+            c.near_cap = no_near ? 0 : cap;
+            size_t sm = (size_t)nbuf * 64 * N + tiles + (size_t)c.near_cap * N * 2 + N + 64;
+            sm = (sm + 15) & ~(size_t)15;
+            c.rng_off = rng ? (int)sm : 0;
+            if (rng) sm += (size_t)32 * N;
+            c.topo_off = topo ? (int)sm : -1;
+            if (topo) sm += (size_t)16 * N;
+            c.smem = sm;
+        };
+        auto best_cap = [&](int nbuf, size_t extra, size_t budget) {
+            const size_t fixed = (size_t)nbuf * 64 * N + tiles + N + 80 + extra;
+            if (fixed + (size_t)12 * 2 * N > budget) return 0; // too little room: all-pairs path, lists from HBM only
+            size_t cap = (budget - fixed) / ((size_t)2 * N);
+            return (int)(cap > 32 ? 32 : cap);
+        };
+        // (1) phase kernel (step-granular entry points): every monomer owns a thread, one stage buffer
+        h->phase.mpt = (N + MD_MAX_THREADS - 1) / MD_MAX_THREADS;
+        if (h->phase.mpt > MD_MAX_MPT) {
+            rc = fail(h, MADDY_EINVAL, "n_tot=%d needs %d monomers per thread (max %d)", N, h->phase.mpt, MD_MAX_MPT);
             goto bad;
         }
-        h->threads = (((N + h->mpt - 1) / h->mpt) + 31) & ~31;
-        h->shape = 0;
-        // shared memory: stage (64 B per monomer, double-buffered when small), tile boxes, near list
+        h->phase.threads = (((N + h->phase.mpt - 1) / h->phase.mpt) + 31) & ~31;
+        layout(h->phase, 1, best_cap(1, 0, 200 * 1024), false, false);
+        // (2) run kernel (fused loop): threads for the monomers that can move
         {
-            const size_t budget = 200 * 1024;
-            const size_t tiles = (size_t)2 * 16 * ((N + MD_TILE - 1) / MD_TILE);
-            h->nbuf = ((size_t)2 * 64 * N <= 100 * 1024) ? 2 : 1;
-            const size_t stage = (size_t)h->nbuf * 64 * N;
-            size_t cap = (budget - stage - tiles - N - 64) / ((size_t)2 * N);
-            if (cap > 32) cap = 32;
-            h->near_cap = cap >= 12 ? (int)cap : 0; // too little room: all-pairs path, lists from HBM only
-            if (getenv("MADDY_NO_NEAR")) h->near_cap = 0;
-            h->smem = stage + tiles + (size_t)h->near_cap * N * 2 + N + 64;
-            h->smem = (h->smem + 15) & ~(size_t)15;
-            // small trajectories: 9-warp CTAs, two per SM (needs 2 x smem <= 227 KB)
-            const char *force_shape = getenv("MADDY_SHAPE");
+            std::vector<uint16_t> amap, fmap;
+            for (int i = 0; i < N; i++) (top->fixed[i] ? fmap : amap).push_back((uint16_t)i);
+            if (fmap.size() > 256 || getenv("MADDY_NO_COMPACT")) { // unusual: give every monomer a thread
+                amap.resize(N);
+                for (int i = 0; i < N; i++) amap[i] = (uint16_t)i;
+                fmap.clear();
+            }
+            h->amap = amap;
+            h->fmap = fmap;
+            a.n_active = (int)amap.size();
+            a.n_fixed = (int)fmap.size();
+            const int na = a.n_active > 0 ? a.n_active : 1;
+            h->run.mpt = (na + MD_RUN_THREADS - 1) / MD_RUN_THREADS;
+            if (h->run.mpt > MD_RUN_MAX_MPT) {
+                rc = fail(h, MADDY_EINVAL, "n_tot=%d needs %d monomers per thread in the fused loop (max %d)", N, h->run.mpt, MD_RUN_MAX_MPT);
+                goto bad;
+            }
+            h->run.threads = (((na + h->run.mpt - 1) / h->run.mpt) + 31) & ~31;
+            if (h->run.threads < a.n_fixed) h->run.threads = (a.n_fixed + 31) & ~31;
             int n_sm = 148;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, par->device);
-            // a second CTA per SM only pays when there are more trajectories than SMs (it costs registers: 56 vs 96)
-            const bool want2 = force_shape ? force_shape[0] == '1' : ntr > n_sm;
-            if (N <= MD_MAX_THREADS && want2) {
-                // two CTAs per SM: near list capped at 20 rows, RNG streams (32 B per monomer) parked in shared memory
-                // two CTAs per SM: near list capped at 16 rows, RNG streams (32 B per monomer) and the packed
-                // topology words (16 B per monomer) parked in shared memory
-                const int cap2 = h->near_cap > 16 ? 16 : h->near_cap;
-                size_t sm2 = stage + tiles + (size_t)cap2 * N * 2 + N + 64;
-                sm2 = (sm2 + 15) & ~(size_t)15;
-                const size_t total = sm2 + (size_t)48 * N;
-                if (cap2 >= 12 && 2 * (total + 1792 + 1024) <= 227 * 1024) {
-                    h->shape = 1;
-                    h->near_cap = cap2;
-                    h->rng_smem_offset = (int)sm2;
-                    h->topo_smem_offset = (int)(sm2 + (size_t)32 * N);
-                    h->smem = total;
+            const char *force = getenv("MADDY_CTAS_PER_SM");
+            // a second CTA per SM pays when there are more trajectories than SMs (it halves the register budget)
+            const bool want2 = h->run.mpt == 1 && (force ? force[0] == '2' : ntr > n_sm);
+            h->run.ctas = 1;
+            if (want2) {
+                // per CTA: double-buffered stage, near list of <= 16 rows, RNG streams and topology words in SMEM
+                const size_t per_cta = (227 * 1024) / 2 - 1792 - 1024;
+                const int cap = best_cap(2, (size_t)48 * N, per_cta);
+                if (cap >= 12 || no_near) {
+                    layout(h->run, 2, cap > 16 ? 16 : cap, true, true);
+                    if (h->run.smem <= per_cta) h->run.ctas = 2;
                 }
             }
-            if (h->shape == 0 && h->smem + (size_t)16 * N + 2048 <= 225 * 1024) { // one CTA per SM: topology words if they fit
-                h->topo_smem_offset = (int)h->smem;
-                h->smem += (size_t)16 * N;
+            if (h->run.ctas == 1) {
+                const int nbuf = ((size_t)2 * 64 * N <= 100 * 1024) ? 2 : 1;
+                const bool topo = (size_t)nbuf * 64 * N + tiles + (size_t)12 * 2 * N + (size_t)17 * N + 2048 <= 200 * 1024;
+                layout(h->run, nbuf, best_cap(nbuf, topo ? (size_t)16 * N : 0, 200 * 1024), false, topo);
             }
         }
         h->cut_pairs = make_cut(par->ljpairscutoff);
@@ -355,7 +386,9 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         pool_req(&a.bcnt, (size_t)ntr * 2 * a.Npad);
         pool_req(&a.lj, par->lj_on ? (size_t)ntr * MADDY_LJ_CAPACITY * a.Npad : 1);
         pool_req(&a.ljcnt, (size_t)ntr * a.Npad);
-        pool_req(&a.cand, h->near_cap > 0 ? (size_t)ntr * MD_CAND_CAPACITY * a.Npad : 1);
+        pool_req(&a.cand, (h->run.near_cap > 0 || h->phase.near_cap > 0) ? (size_t)ntr * MD_CAND_CAPACITY * a.Npad : 1);
+        pool_req(const_cast<uint16_t **>(&a.amap), h->amap.size());
+        pool_req(const_cast<uint16_t **>(&a.fmap), h->fmap.size());
         pool_req(&a.candcnt, (size_t)ntr * a.Npad);
         pool_req(&a.cpos, n);
         pool_req(&a.cand_valid, (size_t)ntr);
@@ -389,6 +422,8 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         std::vector<uint8_t> sflags(N);
         for (int i = 0; i < N; i++) sflags[i] = (uint8_t)((top->fixed[i] ? 1 : 0) | ((top->mon_type[i] & 0x7f) << 1));
         CUK(cudaMemcpyAsync((void *)a.sflags, sflags.data(), N, cudaMemcpyHostToDevice, h->stream));
+        if (!h->amap.empty()) CUK(cudaMemcpyAsync((void *)a.amap, h->amap.data(), h->amap.size() * 2, cudaMemcpyHostToDevice, h->stream));
+        if (!h->fmap.empty()) CUK(cudaMemcpyAsync((void *)a.fmap, h->fmap.data(), h->fmap.size() * 2, cudaMemcpyHostToDevice, h->stream));
         CUK(cudaMemcpyAsync((void *)a.harm, top->harmonic, (size_t)N * a.maxH * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CUK(cudaMemcpyAsync((void *)a.harm_count, top->harmonic_count, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         for (int i = 0; i < N; i++) {

@@ -788,27 +788,11 @@ __device__ __forceinline__ void store_cand_state(const DevSys &a, const CandStat
     if (cs.dirty && threadIdx.x == 0) a.cand_valid[traj] = cs.valid;
 }
 
-// ------------------------------------------------------------------ the trajectory kernel
-// Threads per CTA never exceed MD_MAX_THREADS (the host picks MPT = ceil(N / MD_MAX_THREADS)),
-// which leaves ptxas up to 112 registers per thread for the fused loop.
-// Dynamic shared memory: [nbuf][4][N] float4 stage | 2*ntiles float4 tile boxes | near list u16[cap][N] | u8[N] counts
-// Two launch shapes: <MPT, 576, 1> (one CTA per SM, 96 registers) and <1, 576, 2> (two CTAs per SM at 56
-// registers, N <= 576): the second CTA fills the issue slots the first one leaves idle at its per-step
-// barrier and during MUFU / LDS latencies.
-// Register budget (the SM allocates registers per 4-warp group): 18 warps -> 20 slots -> 96 registers for one
-// CTA per SM; two 17-warp CTAs per SM need <= 56 registers per thread.
-template <int MPT, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_kernel(const __grid_constant__ KArgs k)
+// ------------------------------------------------------------------ the trajectory kernels
+// Dynamic shared memory (both kernels): [nbuf][4][N] float4 stage | 2*ntiles float4 tile boxes |
+// near list u16[cap][N] | u8[N] counts | (run kernel) RNG streams uint4[2][N] | topology words uint4[N]
+__device__ __forceinline__ Near carve_near(float4 *smem, const KArgs &k, int N)
 {
-    extern __shared__ float4 smem[];
-    __shared__ double red_scratch[32 * 7];
-    const maddy_params &p = k.p;
-    const DevSys &a = k.a;
-    const int N = a.N;
-    const int traj = blockIdx.x;
-    const size_t base = (size_t)traj * N;
-    const LatSite ls = lateral_site();
-
     Near near;
     near.cap = k.near_cap;
     near.ntiles = (N + MD_TILE - 1) / MD_TILE;
@@ -817,10 +801,167 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
     near.list = reinterpret_cast<uint16_t *>(near.thi + near.ntiles);
     near.cnt = reinterpret_cast<uint8_t *>(near.list + (size_t)near.cap * N);
     near.ok = false;
-    // two-CTA shape: the HybridTaus streams (8 registers) wait in shared memory between integrator calls
+    near.topo = nullptr;
+    return near;
+}
+
+__device__ __forceinline__ void load_mono(const DevSys &a, size_t base, int i, Mono &m)
+{
+    const float4 P = a.pos[base + i], A = a.ang[base + i];
+    m.x = P.x; m.y = P.y; m.z = P.z;
+    m.fi = A.x; m.psi = A.y; m.theta = A.z;
+    m.flags = (int)a.sflags[i] | (a.gtp[base + i] == 1 ? MF_GTP : 0) | (a.ontub[base + i] ? MF_ONTUB : 0) | (a.extra[base + i] ? MF_EXTRA : 0);
+}
+
+/*
+ * run_kernel<MPT, MINB> — the fused step loop (OP_RUN).
+ *
+ * Threads are handed out to the monomers that can MOVE: a.amap lists the non-fixed monomers (the bottom ring of a
+ * seeded microtubule, `fix`, never moves: its force is computed and discarded by the reference, compute_cuda.cu:949).
+ * Fixed monomers are published once into both stage buffers and get their list rows rebuilt by threads
+ * 0..n_fixed-1 as one extra monomer per thread.  For the 520-monomer seed that leaves 494 movers = 16 warps exactly,
+ * which is what lets TWO CTAs share an SM at 64 registers each (registers are allocated per 4-warp group).
+ * MINB = 2: HybridTaus streams wait in shared memory between integrator calls; MINB = 1: up to 128 registers.
+ */
+template <int MPT, int MINB>
+__global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_constant__ KArgs k)
+{
+    extern __shared__ float4 smem[];
+    const maddy_params &p = k.p;
+    const DevSys &a = k.a;
+    const int N = a.N;
+    const int traj = blockIdx.x;
+    const size_t base = (size_t)traj * N;
+    const LatSite ls = lateral_site();
+
+    Near near = carve_near(smem, k, N);
     constexpr bool kRngShared = MINB == 2;
     uint4 *srng = reinterpret_cast<uint4 *>(smem) + (k.rng_smem_offset >> 4);
-    near.topo = (k.topo_smem_offset >= 0 && (k.ops & OP_RUN)) ? reinterpret_cast<uint4 *>(smem) + (k.topo_smem_offset >> 4) : nullptr;
+    if (k.topo_smem_offset >= 0) near.topo = reinterpret_cast<uint4 *>(smem) + (k.topo_smem_offset >> 4);
+
+    // movers: MPT per thread; slot MPT of the arrays is the (at most one) fixed monomer this thread looks after
+    Mono mo[MPT + 1];
+    int idx[MPT + 1];
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int slot = threadIdx.x + t * blockDim.x;
+        const int i = slot < a.n_active ? (int)a.amap[slot] : N;
+        idx[t] = i;
+        mo[t].flags = MF_EXTRA | MF_FIXED;
+        if (i < N) {
+            load_mono(a, base, i, mo[t]);
+            if (kRngShared) {
+                srng[i] = a.rng_xyz[base + i];
+                srng[N + i] = a.rng_ang[base + i];
+            } else {
+                mo[t].rx = a.rng_xyz[base + i];
+                mo[t].ra = a.rng_ang[base + i];
+            }
+            if (near.topo) near.topo[i] = load_topo(a, traj, i);
+        }
+    }
+    idx[MPT] = (int)threadIdx.x < a.n_fixed ? (int)a.fmap[threadIdx.x] : N;
+    mo[MPT].flags = MF_EXTRA | MF_FIXED;
+    if (idx[MPT] < N) {
+        load_mono(a, base, idx[MPT], mo[MPT]);
+        publish(stage_at(smem, N, 0), idx[MPT], mo[MPT], ls);
+        if (k.nbuf == 2) publish(stage_at(smem, N, 1), idx[MPT], mo[MPT], ls);
+    }
+
+    CandState cs; // candidate-list state (persists in HBM between launches)
+    cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
+    cs.dirty = false;
+
+    int buf = 0;
+    int near_state = 0; // 0: not built, 1: valid, 2: overflowed (full list until the next rebuild)
+    float gx[MPT], gy[MPT], gz[MPT]; // positions when the near list was formed (displacement guard)
+#pragma unroll
+    for (int t = 0; t < MPT; t++) gx[t] = gy[t] = gz[t] = 0.f;
+    const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
+
+    for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
+        const Stage s = stage_at(smem, N, buf);
+        bool moved = false;
+#pragma unroll
+        for (int t = 0; t < MPT; t++) {
+            if (idx[t] < N) {
+                publish(s, idx[t], mo[t], ls);
+                const float dx = mo[t].x - gx[t], dy = mo[t].y - gy[t], dz = mo[t].z - gz[t];
+                moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_NEAR_GUARD2;
+            }
+        }
+        const bool any_moved = __syncthreads_or(moved && near_state == 1) != 0;
+        const bool do_rebuild = rops != 0 && step % p.ljpairsupdatefreq == 0 &&
+                                !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
+        bool formed = false;
+        if (do_rebuild) {
+            near_state = rebuild_lists<MPT + 1>(k, s, near, cs, traj, mo, idx, rops) ? 1 : 2;
+            formed = true;
+            if (near.topo) { // own rows were just rewritten by this thread
+#pragma unroll
+                for (int t = 0; t < MPT; t++)
+                    if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
+            }
+        } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
+            const bool ovf = refresh_near<MPT + 1>(k, s, near, traj, mo, idx);
+            near_state = __syncthreads_or(ovf) ? 2 : 1;
+            formed = true;
+        }
+        if (formed) {
+#pragma unroll
+            for (int t = 0; t < MPT; t++) {
+                gx[t] = mo[t].x;
+                gy[t] = mo[t].y;
+                gz[t] = mo[t].z;
+            }
+        }
+        near.ok = near.cap > 0 && near_state == 1;
+#pragma unroll
+        for (int t = 0; t < MPT; t++) {
+            if (idx[t] < N && !(mo[t].flags & (MF_EXTRA | MF_FIXED))) {
+                const G6 f = monomer_force(k, s, near, traj, idx[t], mo[t], ls);
+                if (kRngShared) {
+                    mo[t].rx = srng[idx[t]];
+                    mo[t].ra = srng[N + idx[t]];
+                }
+                integrate_monomer(p, mo[t], f);
+                if (kRngShared) {
+                    srng[idx[t]] = mo[t].rx;
+                    srng[N + idx[t]] = mo[t].ra;
+                }
+            }
+        }
+        if (k.nbuf == 2) buf ^= 1;
+        else __syncthreads();
+    }
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int i = idx[t];
+        if (i < N) {
+            a.pos[base + i] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
+            a.ang[base + i] = make_float4(mo[t].fi, mo[t].psi, mo[t].theta, 0.f);
+            a.rng_xyz[base + i] = kRngShared ? srng[i] : mo[t].rx;
+            a.rng_ang[base + i] = kRngShared ? srng[N + i] : mo[t].ra;
+        }
+    }
+    store_cand_state(a, cs, traj);
+}
+
+/*
+ * phase_kernel<MPT> — one phase of the step for EVERY monomer (the step-granular entry points: one call per
+ * reference launch).  Same device functions as the fused loop, lists read from HBM, so results are bit-identical.
+ */
+template <int MPT>
+__global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_constant__ KArgs k)
+{
+    extern __shared__ float4 smem[];
+    __shared__ double red_scratch[32 * 7];
+    const DevSys &a = k.a;
+    const int N = a.N;
+    const int traj = blockIdx.x;
+    const size_t base = (size_t)traj * N;
+    const LatSite ls = lateral_site();
+    Near near = carve_near(smem, k, N);
 
     Mono mo[MPT];
     int idx[MPT];
@@ -828,113 +969,9 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
     for (int t = 0; t < MPT; t++) {
         const int i = threadIdx.x + t * blockDim.x;
         idx[t] = i;
-        if (i < N) {
-            const float4 P = a.pos[base + i], A = a.ang[base + i];
-            mo[t].x = P.x; mo[t].y = P.y; mo[t].z = P.z;
-            mo[t].fi = A.x; mo[t].psi = A.y; mo[t].theta = A.z;
-            mo[t].flags = (int)a.sflags[i] | (a.gtp[base + i] == 1 ? MF_GTP : 0) | (a.ontub[base + i] ? MF_ONTUB : 0) |
-                          (a.extra[base + i] ? MF_EXTRA : 0);
-            if (k.ops & OP_RUN) {
-                if (kRngShared) {
-                    srng[i] = a.rng_xyz[base + i];
-                    srng[N + i] = a.rng_ang[base + i];
-                } else {
-                    mo[t].rx = a.rng_xyz[base + i];
-                    mo[t].ra = a.rng_ang[base + i];
-                }
-            }
-        } else {
-            mo[t].flags = MF_EXTRA | MF_FIXED;
-        }
+        mo[t].flags = MF_EXTRA | MF_FIXED;
+        if (i < N) load_mono(a, base, i, mo[t]);
     }
-
-    // candidate-list state (persists in HBM between launches)
-    CandState cs;
-    cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
-    cs.dirty = false;
-
-    if (k.ops & OP_RUN) {
-        if (near.topo) {
-#pragma unroll
-            for (int t = 0; t < MPT; t++)
-                if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
-        }
-        int buf = 0;
-        int near_state = 0; // 0: not built, 1: valid, 2: overflowed (full list until the next rebuild)
-        float gx[MPT], gy[MPT], gz[MPT]; // positions when the near list was formed (displacement guard)
-#pragma unroll
-        for (int t = 0; t < MPT; t++) gx[t] = gy[t] = gz[t] = 0.f;
-        const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
-        for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
-            const Stage s = stage_at(smem, N, buf);
-            bool moved = false;
-#pragma unroll
-            for (int t = 0; t < MPT; t++) {
-                if (idx[t] < N) {
-                    publish(s, idx[t], mo[t], ls);
-                    const float dx = mo[t].x - gx[t], dy = mo[t].y - gy[t], dz = mo[t].z - gz[t];
-                    moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_NEAR_GUARD2;
-                }
-            }
-            const bool any_moved = __syncthreads_or(moved && near_state == 1) != 0;
-            const bool do_rebuild = rops != 0 && step % p.ljpairsupdatefreq == 0 &&
-                                    !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
-            bool formed = false;
-            if (do_rebuild) {
-                near_state = rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, rops) ? 1 : 2;
-                formed = true;
-                if (near.topo) { // own rows were just rewritten by this thread
-#pragma unroll
-                    for (int t = 0; t < MPT; t++)
-                        if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
-                }
-            } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
-                const bool ovf = refresh_near<MPT>(k, s, near, traj, mo, idx);
-                near_state = __syncthreads_or(ovf) ? 2 : 1;
-                formed = true;
-            }
-            if (formed) {
-#pragma unroll
-                for (int t = 0; t < MPT; t++) {
-                    gx[t] = mo[t].x;
-                    gy[t] = mo[t].y;
-                    gz[t] = mo[t].z;
-                }
-            }
-            near.ok = near.cap > 0 && near_state == 1;
-#pragma unroll
-            for (int t = 0; t < MPT; t++) {
-                if (idx[t] < N && !(mo[t].flags & MF_EXTRA)) {
-                    const G6 f = monomer_force(k, s, near, traj, idx[t], mo[t], ls);
-                    if (kRngShared) {
-                        mo[t].rx = srng[idx[t]];
-                        mo[t].ra = srng[N + idx[t]];
-                    }
-                    integrate_monomer(p, mo[t], f);
-                    if (kRngShared && !(mo[t].flags & MF_FIXED)) {
-                        srng[idx[t]] = mo[t].rx;
-                        srng[N + idx[t]] = mo[t].ra;
-                    }
-                }
-            }
-            if (k.nbuf == 2) buf ^= 1;
-            else __syncthreads();
-        }
-#pragma unroll
-        for (int t = 0; t < MPT; t++) {
-            const int i = idx[t];
-            if (i < N) {
-                a.pos[base + i] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
-                a.ang[base + i] = make_float4(mo[t].fi, mo[t].psi, mo[t].theta, 0.f);
-                a.rng_xyz[base + i] = kRngShared ? srng[i] : mo[t].rx;
-                a.rng_ang[base + i] = kRngShared ? srng[N + i] : mo[t].ra;
-            }
-        }
-        store_cand_state(a, cs, traj);
-        return;
-    }
-
-    // ---- single-phase modes (step-granular API): same device functions, full lists from HBM
     const Stage s = stage_at(smem, N, 0);
 #pragma unroll
     for (int t = 0; t < MPT; t++)
@@ -942,6 +979,9 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MINB == 2 ? 56 : 96) traj_ke
     __syncthreads();
 
     if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) {
+        CandState cs;
+        cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
+        cs.dirty = false;
         rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, k.ops);
         store_cand_state(a, cs, traj);
     }
@@ -1005,29 +1045,48 @@ __global__ void __launch_bounds__(256) integrate_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ launch helpers (called from the C-ABI)
-template <int MPT, int MAXT, int MINB>
-static cudaError_t launch_traj(const KArgs &k, int threads, size_t smem, cudaStream_t st)
+template <int MPT, int MINB>
+static cudaError_t launch_run(const KArgs &k, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(traj_kernel<MPT, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(run_kernel<MPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    traj_kernel<MPT, MAXT, MINB><<<k.a.ntr, threads, smem, st>>>(k);
+    run_kernel<MPT, MINB><<<k.a.ntr, threads, smem, st>>>(k);
+    return cudaGetLastError();
+}
+template <int MPT>
+static cudaError_t launch_phase(const KArgs &k, int threads, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(phase_kernel<MPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    phase_kernel<MPT><<<k.a.ntr, threads, smem, st>>>(k);
     return cudaGetLastError();
 }
 
-// shape 0: <= MD_MAX_THREADS threads, 1 CTA/SM; shape 1: <= MD_SMALL_THREADS threads, 2 CTAs/SM
-cudaError_t launch_traj_kernel(const KArgs &k, int mpt, int shape, int threads, size_t smem, cudaStream_t st)
+// fused loop; ctas_per_sm = 2 only with mpt == 1
+cudaError_t launch_run_kernel(const KArgs &k, int mpt, int ctas_per_sm, int threads, size_t smem, cudaStream_t st)
 {
-    if (shape == 1) {
-        if (mpt != 1) return cudaErrorInvalidValue;
-        return launch_traj<1, MD_MAX_THREADS, 2>(k, threads, smem, st);
-    }
+    if (ctas_per_sm == 2) return mpt == 1 ? launch_run<1, 2>(k, threads, smem, st) : cudaErrorInvalidValue;
     switch (mpt) {
-    case 1: return launch_traj<1, MD_MAX_THREADS, 1>(k, threads, smem, st);
-    case 2: return launch_traj<2, MD_MAX_THREADS, 1>(k, threads, smem, st);
-    case 3: return launch_traj<3, MD_MAX_THREADS, 1>(k, threads, smem, st);
-    case 4: return launch_traj<4, MD_MAX_THREADS, 1>(k, threads, smem, st);
-    case 5: return launch_traj<5, MD_MAX_THREADS, 1>(k, threads, smem, st);
-    case 6: return launch_traj<6, MD_MAX_THREADS, 1>(k, threads, smem, st);
+    case 1: return launch_run<1, 1>(k, threads, smem, st);
+    case 2: return launch_run<2, 1>(k, threads, smem, st);
+    case 3: return launch_run<3, 1>(k, threads, smem, st);
+    case 4: return launch_run<4, 1>(k, threads, smem, st);
+    case 5: return launch_run<5, 1>(k, threads, smem, st);
+    case 6: return launch_run<6, 1>(k, threads, smem, st);
+    case 7: return launch_run<7, 1>(k, threads, smem, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_phase_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st)
+{
+    switch (mpt) {
+    case 1: return launch_phase<1>(k, threads, smem, st);
+    case 2: return launch_phase<2>(k, threads, smem, st);
+    case 3: return launch_phase<3>(k, threads, smem, st);
+    case 4: return launch_phase<4>(k, threads, smem, st);
+    case 5: return launch_phase<5>(k, threads, smem, st);
+    case 6: return launch_phase<6>(k, threads, smem, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -11,7 +11,8 @@ namespace maddy {
 
 #define MD_MAX_THREADS 576 // threads per trajectory CTA (18 warps)
 #define MD_MAX_MPT 6
-#define MD_SMALL_THREADS 288 // launch shape 1: two CTAs per SM (N <= 2 * 288)
+#define MD_RUN_THREADS 512 // fused loop: 16 warps per CTA (registers are allocated per 4-warp group)
+#define MD_RUN_MAX_MPT 7
 
 // operation mask of the trajectory kernel
 enum : unsigned {
@@ -44,6 +45,9 @@ struct DevSys {
     const int *harm;       // [N*maxH] signed, reference encoding
     const int *harm_count; // [N]
     const uint8_t *sflags; // [N] bit0 fixed, bits1.. mon_type
+    const uint16_t *amap;  // [n_active] monomers that own a thread in the fused loop (all non-fixed ones)
+    const uint16_t *fmap;  // [n_fixed]  fixed monomers looked after by threads 0..n_fixed-1
+    int n_active, n_fixed;
     uint8_t *extra, *gtp, *ontub;
     uint16_t *bl;
     uint8_t *bcnt;
