@@ -54,12 +54,22 @@ def build_kernels(force=False, verbose_ptxas=False):
     if not force and not _stale(LIB_KERNELS, deps):
         return LIB_KERNELS
     # -use_fast_math: the reference is built with it (CMakeLists.txt:62) and the MUFU lowering of
-    # sinf/cosf/expf/logf/sqrtf and `/` is part of the arithmetic contract
-    cmd = [NVCC, "-shared", "-Xcompiler", "-fPIC", *ARCH, "-lineinfo", "-O3", "-use_fast_math", "-std=c++17",
-           f"-I{ROOT / 'include'}", f"-I{CSRC}", "-o", LIB_KERNELS, *srcs, "-ldl"]
+    # sinf/cosf/expf/logf/sqrtf and `/` is part of the arithmetic contract.
+    # maddy_kernels.cu additionally gets -fmad=false: its device functions are shared by several kernels (fused
+    # loop, step-granular phases) that must round identically, so every FMA there is an explicit fmaf().
+    common = [*ARCH, "-lineinfo", "-O3", "-use_fast_math", "-std=c++17", "-Xcompiler", "-fPIC", f"-I{ROOT / 'include'}", f"-I{CSRC}"]
     if verbose_ptxas:
-        cmd += ["-Xptxas", "-v"]
-    _run(cmd)
+        common += ["-Xptxas", "-v"]
+    objdir = PKG / "_build"
+    objdir.mkdir(exist_ok=True)
+    objs = []
+    for src in srcs:
+        obj = objdir / (src.stem + ".o")
+        extra = ["-fmad=false"] if src.name == "maddy_kernels.cu" else []
+        if force or _stale(obj, deps):
+            _run([NVCC, "-c", *common, *extra, "-o", obj, src])
+        objs.append(obj)
+    _run([NVCC, "-shared", *ARCH, "-o", LIB_KERNELS, *objs, "-ldl"])
     return LIB_KERNELS
 
 

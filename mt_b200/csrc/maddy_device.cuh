@@ -39,7 +39,10 @@ namespace maddy {
 
 struct F3 { float x, y, z; };
 __device__ __forceinline__ F3 mk3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ float dot3(const F3 &a, const F3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Arithmetic in the kernels that share these functions is pinned: maddy_kernels.cu is compiled with -fmad=false and
+// every fused multiply-add is written out as fmaf(), so the fused loop and the step-granular kernels (different
+// instantiations, different register budgets) round identically and stay bit-for-bit interchangeable.
+__device__ __forceinline__ float dot3(const F3 &a, const F3 &b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 
 // generalized force / coordinate of one monomer: x,y,z,fi,psi,theta
 struct G6 { float x, y, z, fi, psi, theta; };
@@ -72,8 +75,8 @@ __device__ __forceinline__ Frame make_frame(float fi, float psi, float theta)
     f.sp = sinf(psi);   f.cp = cosf(psi);
     f.st = sinf(theta); f.ct = cosf(theta);
     f.e1 = mk3(f.cp * f.ct, f.sp * f.ct, -f.st);
-    f.e2 = mk3(f.cp * f.sf * f.st - f.cf * f.sp, f.cf * f.cp + f.sf * f.sp * f.st, f.ct * f.sf);
-    f.e3 = mk3(f.sf * f.sp + f.cf * f.cp * f.st, -f.cp * f.sf + f.cf * f.sp * f.st, f.cf * f.ct);
+    f.e2 = mk3(fmaf(f.cp * f.sf, f.st, -(f.cf * f.sp)), fmaf(f.sf * f.sp, f.st, f.cf * f.cp), f.ct * f.sf);
+    f.e3 = mk3(fmaf(f.cf * f.cp, f.st, f.sf * f.sp), fmaf(f.cf * f.sp, f.st, -(f.cp * f.sf)), f.cf * f.ct);
     f.g = mk3(f.cp * f.st, f.sp * f.st, f.ct);
     return f;
 }
@@ -84,7 +87,7 @@ __device__ __forceinline__ void site_offsets(const Frame &f, const LatSite &ls, 
     a = mk3(MD_R_MON * f.e3.x, MD_R_MON * f.e3.y, MD_R_MON * f.e3.z);
     // u = xp*e1, v = yp*e2 + zp*e3 ; l1 = u + v, l2 = u - v
     F3 u = mk3(ls.xp * f.e1.x, ls.xp * f.e1.y, ls.xp * f.e1.z);
-    F3 v = mk3(ls.yp * f.e2.x + ls.zp * f.e3.x, ls.yp * f.e2.y + ls.zp * f.e3.y, ls.yp * f.e2.z + ls.zp * f.e3.z);
+    F3 v = mk3(fmaf(ls.yp, f.e2.x, ls.zp * f.e3.x), fmaf(ls.yp, f.e2.y, ls.zp * f.e3.y), fmaf(ls.yp, f.e2.z, ls.zp * f.e3.z));
     l1 = mk3(u.x + v.x, u.y + v.y, u.z + v.z);
     l2 = mk3(u.x - v.x, u.y - v.y, u.z - v.z);
 }
@@ -135,15 +138,15 @@ __device__ __forceinline__ float barr(float a, float r, float w, float x)
 __device__ __forceinline__ void bond_accumulate(G6 &f, float k, const F3 &d, const F3 &o, float xp, float yp, float zp,
                                                 const Frame &fr)
 {
-    f.x += k * d.x;
-    f.y += k * d.y;
-    f.z += k * d.z;
-    F3 dfi = mk3(yp * fr.e3.x - zp * fr.e2.x, yp * fr.e3.y - zp * fr.e2.y, yp * fr.e3.z - zp * fr.e2.z);
-    float c = yp * fr.sf + zp * fr.cf;
-    F3 dth = mk3(c * fr.e1.x - xp * fr.g.x, c * fr.e1.y - xp * fr.g.y, c * fr.e1.z - xp * fr.g.z);
-    f.fi += k * dot3(d, dfi);
-    f.psi += k * (d.y * o.x - d.x * o.y);
-    f.theta += k * dot3(d, dth);
+    f.x = fmaf(k, d.x, f.x);
+    f.y = fmaf(k, d.y, f.y);
+    f.z = fmaf(k, d.z, f.z);
+    F3 dfi = mk3(fmaf(yp, fr.e3.x, -(zp * fr.e2.x)), fmaf(yp, fr.e3.y, -(zp * fr.e2.y)), fmaf(yp, fr.e3.z, -(zp * fr.e2.z)));
+    float c = fmaf(yp, fr.sf, zp * fr.cf);
+    F3 dth = mk3(fmaf(c, fr.e1.x, -(xp * fr.g.x)), fmaf(c, fr.e1.y, -(xp * fr.g.y)), fmaf(c, fr.e1.z, -(xp * fr.g.z)));
+    f.fi = fmaf(k, dot3(d, dfi), f.fi);
+    f.psi = fmaf(k, fmaf(d.y, o.x, -(d.x * o.y)), f.psi);
+    f.theta = fmaf(k, dot3(d, dth), f.theta);
 }
 
 // ---------------------------------------------------------------- HybridTaus RNG

@@ -130,9 +130,9 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         const int j = raw < 0 ? -raw : raw;
         const float4 Pj = s.P[j], Ej = s.E[j];
         F3 d;
-        d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
-        d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
-        d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+        d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
+        d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
+        d.z = fmaf(-sg, Ej.z, fmaf(-sg, Ei.z, Pj.z - zi));
         const float dr = site_distance(d);
         bond_accumulate(f, p.C, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), 0.f, 0.f, sg * MD_R_MON, fr);
         if (dr < MD_ANGLE_CUTOFF) {
@@ -141,13 +141,13 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
             const float thetaji = s.L1[j].w - m.theta;
             const float th0 = gtp_i ? p.theta0_gtp : p.theta0_gdp;
             if (sg > 0) {
-                f.psi += p.B_psi * sinf(psiji - p.psi_0);
-                f.fi += p.B_fi * sinf(fiji - p.fi_0);
-                f.theta += p.B_theta * sinf(thetaji - th0);
+                f.psi = fmaf(p.B_psi, sinf(psiji - p.psi_0), f.psi);
+                f.fi = fmaf(p.B_fi, sinf(fiji - p.fi_0), f.fi);
+                f.theta = fmaf(p.B_theta, sinf(thetaji - th0), f.theta);
             } else {
-                f.psi -= p.B_psi * sinf(-psiji - p.psi_0);
-                f.fi -= p.B_fi * sinf(-fiji - p.fi_0);
-                f.theta -= p.B_theta * sinf(-thetaji - th0);
+                f.psi = fmaf(-p.B_psi, sinf(-psiji - p.psi_0), f.psi);
+                f.fi = fmaf(-p.B_fi, sinf(-fiji - p.fi_0), f.fi);
+                f.theta = fmaf(-p.B_theta, sinf(-thetaji - th0), f.theta);
             }
         }
     }
@@ -162,9 +162,9 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         const float4 L2j = s.L2[j];
         const int jf = __float_as_int(L2j.w);
         F3 d;
-        d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
-        d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
-        d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+        d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
+        d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
+        d.z = fmaf(-sg, Ej.z, fmaf(-sg, Ei.z, Pj.z - zi));
         const float dr = site_distance(d);
         float dUdr;
         if (dr == 0) dUdr = 0.0f;
@@ -181,13 +181,13 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
             const bool gtp_last = (zi > Pj.z) ? gtp_i : ((jf & MF_GTP) != 0);
             const float th0 = gtp_last ? p.theta0_gtp : p.theta0_gdp;
             if (sg > 0) {
-                f.psi += p.B_psi * sinf(psiji - p.psi_0);
-                f.fi += p.B_fi * sinf(fiji - p.fi_0);
-                f.theta += p.B_theta * sinf(thetaji - th0);
+                f.psi = fmaf(p.B_psi, sinf(psiji - p.psi_0), f.psi);
+                f.fi = fmaf(p.B_fi, sinf(fiji - p.fi_0), f.fi);
+                f.theta = fmaf(p.B_theta, sinf(thetaji - th0), f.theta);
             } else {
-                f.psi -= p.B_psi * sinf(-psiji - p.psi_0);
-                f.fi -= p.B_fi * sinf(-fiji - p.fi_0);
-                f.theta -= p.B_theta * sinf(-thetaji - th0);
+                f.psi = fmaf(-p.B_psi, sinf(-psiji - p.psi_0), f.psi);
+                f.fi = fmaf(-p.B_fi, sinf(-fiji - p.fi_0), f.fi);
+                f.theta = fmaf(-p.B_theta, sinf(-thetaji - th0), f.theta);
             }
         }
     }
@@ -242,9 +242,9 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
                     const float inv = 1.0f / sf;
                     const float inv2 = inv * inv;
                     const float c = amp * (6.0f * (inv2 * inv2)); // 6 / dr^8
-                    fx += c * dx;
-                    fy += c * dy;
-                    fz += c * dz;
+                    fx = fmaf(c, dx, fx);
+                    fy = fmaf(c, dy, fy);
+                    fz = fmaf(c, dz, fz);
                 }
             }
         } else {
@@ -260,9 +260,9 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
                     const float inv = 1.0f / sf;
                     const float inv2 = inv * inv;
                     const float c = amp * (6.0f * (inv2 * inv2)); // 6 / dr^8
-                    fx += c * dx;
-                    fy += c * dy;
-                    fz += c * dz;
+                    fx = fmaf(c, dx, fx);
+                    fy = fmaf(c, dy, fy);
+                    fz = fmaf(c, dz, fz);
                 }
             }
         }
@@ -309,9 +309,9 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
             const int j = raw < 0 ? -raw : raw;
             const float4 Pj = s.P[j], Ej = s.E[j];
             F3 d;
-            d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
-            d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
-            d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+            d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
+            d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
+            d.z = fmaf(-sg, Ej.z, fmaf(-sg, Ei.z, Pj.z - zi));
             const float dr = site_distance_d(d);
             U_harm = (float)((double)U_harm + (double)(p.C / 2) * ((double)dr * (double)dr));
             if (dr < MD_ANGLE_CUTOFF) {
@@ -334,9 +334,9 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
             const float4 Pj = s.P[j], Ej = s.E[j];
             const int jf = __float_as_int(s.L2[j].w);
             F3 d;
-            d.x = (Pj.x - xi) - sg * Ei.x - sg * Ej.x;
-            d.y = (Pj.y - yi) - sg * Ei.y - sg * Ej.y;
-            d.z = (Pj.z - zi) - sg * Ei.z - sg * Ej.z;
+            d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
+            d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
+            d.z = fmaf(-sg, Ej.z, fmaf(-sg, Ei.z, Pj.z - zi));
             // dr2 is rounded to float before the sqrt here (compute_cuda.cu:783-791)
             double s2 = (double)d.z * (double)d.z;
             s2 += (double)d.x * (double)d.x;
@@ -412,43 +412,126 @@ struct BondOut {
     uint16_t *col; // &bl[traj][0][i]
     int nlong, nlat, status;
 };
-__device__ __forceinline__ void bond_candidates(const DevSys &a, const Stage &s, int i, int j, const Mono &m, int hraw, const float4 &Pj,
-                                                const float4 &Ei, const float4 &L1i, const float4 &L2i, BondOut &o)
+// bit0: longitudinal hit, bit1: lateral (i:p1, j:p2) hit, bit2: lateral (i:p2, j:p1) hit
+__device__ __forceinline__ unsigned bond_tests(const Stage &s, float xi, float yi, float zi, int type_i, int j, int hraw, const float4 &Pj,
+                                               const float4 &Ei, const float4 &L1i, const float4 &L2i)
 {
     const float4 Ej = s.E[j], L1j = s.L1[j], L2j = s.L2[j];
     const int jf = __float_as_int(L2j.w);
-    if (MF_TYPE(m.flags) != (jf & 0x7f)) {
+    unsigned hit = 0;
+    if (type_i != (jf & 0x7f)) {
         const float sg = hraw < 0 ? -1.0f : 1.0f; // R_MON / r_mon (compute_cuda.cu:548-551)
         F3 d;
-        d.x = (Pj.x - m.x) - sg * Ei.x - sg * Ej.x;
-        d.y = (Pj.y - m.y) - sg * Ei.y - sg * Ej.y;
-        d.z = (Pj.z - m.z) - sg * Ei.z - sg * Ej.z;
-        if (site_distance(d) < MD_PAIR_CUTOFF) {
-            // stored as +j when harmonic < 0, -j otherwise; -0 == 0 loses its sign (compute_cuda.cu:588-592)
-            const unsigned neg = (hraw < 0 || j == 0) ? 0u : 1u;
-            if (o.nlong < a.capLong) o.col[(size_t)o.nlong * a.Npad] = (uint16_t)((j << 1) | neg);
-            else o.status |= ST_LONG_OVERFLOW;
-            o.nlong++;
-        }
+        d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
+        d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
+        d.z = fmaf(-sg, Ej.z, fmaf(-sg, Ei.z, Pj.z - zi));
+        if (site_distance(d) < MD_PAIR_CUTOFF) hit |= 1u;
     }
     // lateral: (i:p1, j:p2) stored negative, then (i:p2, j:p1) stored positive (compute_cuda.cu:612-661)
     F3 d;
-    d.x = (Pj.x - m.x) - L1i.x + L2j.x;
-    d.y = (Pj.y - m.y) - L1i.y + L2j.y;
-    d.z = (Pj.z - m.z) - L1i.z + L2j.z;
-    if (site_distance(d) < MD_PAIR_CUTOFF) {
+    d.x = (Pj.x - xi) - L1i.x + L2j.x;
+    d.y = (Pj.y - yi) - L1i.y + L2j.y;
+    d.z = (Pj.z - zi) - L1i.z + L2j.z;
+    if (site_distance(d) < MD_PAIR_CUTOFF) hit |= 2u;
+    d.x = (Pj.x - xi) - L2i.x + L1j.x;
+    d.y = (Pj.y - yi) - L2i.y + L1j.y;
+    d.z = (Pj.z - zi) - L2i.z + L1j.z;
+    if (site_distance(d) < MD_PAIR_CUTOFF) hit |= 4u;
+    return hit;
+}
+// longitudinal entries are stored as +j when harmonic < 0, -j otherwise; -0 == 0 loses its sign (compute_cuda.cu:588-592)
+__device__ __forceinline__ uint16_t long_code(int j, int hraw) { return (uint16_t)((j << 1) | ((hraw < 0 || j == 0) ? 0u : 1u)); }
+
+__device__ __forceinline__ void bond_candidates(const DevSys &a, const Stage &s, int i, int j, const Mono &m, int hraw, const float4 &Pj,
+                                                const float4 &Ei, const float4 &L1i, const float4 &L2i, BondOut &o)
+{
+    const unsigned hit = bond_tests(s, m.x, m.y, m.z, MF_TYPE(m.flags), j, hraw, Pj, Ei, L1i, L2i);
+    if (hit & 1u) {
+        if (o.nlong < a.capLong) o.col[(size_t)o.nlong * a.Npad] = long_code(j, hraw);
+        else o.status |= ST_LONG_OVERFLOW;
+        o.nlong++;
+    }
+    if (hit & 2u) {
         if (o.nlat < a.capLat) o.col[(size_t)(a.capLong + o.nlat) * a.Npad] = (uint16_t)((j << 1) | 1u);
         else o.status |= ST_LAT_OVERFLOW;
         o.nlat++;
     }
-    d.x = (Pj.x - m.x) - L2i.x + L1j.x;
-    d.y = (Pj.y - m.y) - L2i.y + L1j.y;
-    d.z = (Pj.z - m.z) - L2i.z + L1j.z;
-    if (site_distance(d) < MD_PAIR_CUTOFF) {
+    if (hit & 4u) {
         if (o.nlat < a.capLat) o.col[(size_t)(a.capLong + o.nlat) * a.Npad] = (uint16_t)(j << 1);
         else o.status |= ST_LAT_OVERFLOW;
         o.nlat++;
     }
+}
+
+// Warp-cooperative rebuild of ONE monomer's rows from its candidate list: 32 lanes test 32 candidates at a time and
+// the hits are compacted in candidate (= ascending j) order with ballots.  Used for the fixed monomers of the fused
+// loop, which own no thread: every warp looks after one or two of them, so no warp pays a whole extra pass.
+__device__ __forceinline__ void rebuild_row_cooperative(const KArgs &k, const Stage &s, int traj, int i, unsigned ops)
+{
+    const DevSys &a = k.a;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool do_lj = (ops & OP_REBUILD_LJ) != 0, do_b = (ops & OP_REBUILD_BONDS) != 0;
+    const float4 Pi = s.P[i], Ei = s.E[i], L1i = s.L1[i], L2i = s.L2[i];
+    const int fl = __float_as_int(L2i.w);
+    const int hraw = a.harm[a.maxH * i];
+    const int hp = hraw < 0 ? -hraw : hraw;
+    const bool extra = (fl & MF_EXTRA) != 0;
+    const int n = extra ? 0 : (int)a.candcnt[(size_t)traj * a.Npad + i];
+    const uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
+    uint16_t *lp = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+    uint16_t *bp = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
+    int nlj = 0, nlong = 0, nlat = 0, status = 0;
+    for (int b0 = 0; b0 < n; b0 += 32) {
+        const int kk = b0 + lane;
+        const bool valid = kk < n;
+        const int j = valid ? (int)cp[(size_t)kk * a.Npad] : 0;
+        const float4 Pj = s.P[j];
+        const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+        const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (do_lj) {
+            const bool in = valid && inside_cut(k.cut_pairs, dx, dy, dz, sf);
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const int pos = nlj + __popc(m & lt);
+                if (pos < MADDY_LJ_CAPACITY) lp[(size_t)pos * a.Npad] = (uint16_t)j;
+                else status |= ST_LJ_OVERFLOW;
+            }
+            nlj += __popc(m);
+        }
+        if (do_b) {
+            unsigned hit = 0;
+            if (valid && sf < MD_BOND_PREFILTER2 && hp != j) hit = bond_tests(s, Pi.x, Pi.y, Pi.z, fl & 0x7f, j, hraw, Pj, Ei, L1i, L2i);
+            const unsigned ml = __ballot_sync(0xffffffffu, hit & 1u), m1 = __ballot_sync(0xffffffffu, hit & 2u),
+                           m2 = __ballot_sync(0xffffffffu, hit & 4u);
+            if (hit & 1u) {
+                const int pos = nlong + __popc(ml & lt);
+                if (pos < a.capLong) bp[(size_t)pos * a.Npad] = long_code(j, hraw);
+                else status |= ST_LONG_OVERFLOW;
+            }
+            const int before = nlat + __popc(m1 & lt) + __popc(m2 & lt);
+            if (hit & 2u) {
+                if (before < a.capLat) bp[(size_t)(a.capLong + before) * a.Npad] = (uint16_t)((j << 1) | 1u);
+                else status |= ST_LAT_OVERFLOW;
+            }
+            if (hit & 4u) {
+                const int pos = before + ((hit & 2u) ? 1 : 0);
+                if (pos < a.capLat) bp[(size_t)(a.capLong + pos) * a.Npad] = (uint16_t)(j << 1);
+                else status |= ST_LAT_OVERFLOW;
+            }
+            nlong += __popc(ml);
+            nlat += __popc(m1) + __popc(m2);
+        }
+    }
+    if (lane == 0) {
+        if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj, MADDY_LJ_CAPACITY);
+        if (do_b) {
+            uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
+            bc[0] = (uint8_t)min(nlong, a.capLong);
+            bc[a.Npad] = (uint8_t)min(nlat, a.capLat);
+        }
+    }
+    if (status) atomicOr(a.status, status);
 }
 
 // General path: one pass over ALL j for the MPT monomers of this thread (LJ Verlet list,
@@ -697,48 +780,73 @@ struct CandState {
 };
 
 // Rebuild at a list-update step.  CTA-uniform control flow; returns whether the near list is valid.
+// with_fixed (fused loop): the fixed monomers own no thread.  On the common path (valid candidate lists) every warp
+// rebuilds one or two of their rows cooperatively; on the rare paths (candidate scan, overflow fallback) thread f
+// handles fixed monomer f with the per-thread functions.
 template <int MPT>
 __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Near &near, CandState &cs, int traj,
-                                              const Mono (&mo)[MPT], const int (&idx)[MPT], unsigned ops)
+                                              const Mono (&mo)[MPT], const int (&idx)[MPT], unsigned ops, bool with_fixed)
 {
+    const DevSys &a = k.a;
+    const int N = a.N;
+    Mono fm[1];
+    int fi[1] = {N};
+    fm[0].flags = MF_EXTRA | MF_FIXED;
+    if (with_fixed && (int)threadIdx.x < a.n_fixed) {
+        fi[0] = (int)a.fmap[threadIdx.x];
+        const float4 P = s.P[fi[0]];
+        const int jf = __float_as_int(s.L2[fi[0]].w);
+        fm[0].x = P.x; fm[0].y = P.y; fm[0].z = P.z;
+        fm[0].flags = MF_FIXED | ((jf & 0x7f) << 1) | (jf & (MF_GTP | MF_ONTUB | MF_EXTRA));
+    }
     if (near.cap == 0) {
         rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
+        if (with_fixed) rebuild_lists_all_pairs<1>(k, s, traj, fm, fi, ops);
         return false;
     }
     // has anything moved more than half the candidate skin since the candidate list was built?
-    const size_t base = (size_t)traj * k.a.N;
+    const size_t base = (size_t)traj * N;
     bool moved = !cs.valid;
     if (cs.valid) {
 #pragma unroll
         for (int t = 0; t < MPT; t++) {
-            if (idx[t] < k.a.N) {
-                const float4 c = k.a.cpos[base + idx[t]];
+            if (idx[t] < N) {
+                const float4 c = a.cpos[base + idx[t]];
                 const float dx = mo[t].x - c.x, dy = mo[t].y - c.y, dz = mo[t].z - c.z;
                 moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_CAND_GUARD2;
             }
         }
     }
     if (__syncthreads_or(moved)) {
-        compute_tiles(s, near, k.a.N);
+        compute_tiles(s, near, N);
         __syncthreads();
-        const bool covf = scan_candidates<MPT>(k, s, near, traj, mo, idx);
+        bool covf = scan_candidates<MPT>(k, s, near, traj, mo, idx);
+        if (with_fixed) covf |= scan_candidates<1>(k, s, near, traj, fm, fi);
         cs.dirty = true;
         if (__syncthreads_or(covf)) { // more candidates than MD_CAND_CAPACITY: general path, candidates stay invalid
             cs.valid = 0;
             rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
+            if (with_fixed) rebuild_lists_all_pairs<1>(k, s, traj, fm, fi, ops);
             return false;
         }
         cs.valid = 1;
 #pragma unroll
         for (int t = 0; t < MPT; t++)
-            if (idx[t] < k.a.N) k.a.cpos[base + idx[t]] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
+            if (idx[t] < N) a.cpos[base + idx[t]] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
+        if (fi[0] < N) a.cpos[base + fi[0]] = make_float4(fm[0].x, fm[0].y, fm[0].z, 0.f);
+        __syncthreads(); // candidate rows of the fixed monomers are read by other threads below
     }
     const bool ovf = filter_candidates<MPT>(k, s, near, traj, mo, idx, (ops & OP_REBUILD_LJ) != 0);
     if (__syncthreads_or(ovf)) { // a near list overflowed: redo everything on the general path
         rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
+        if (with_fixed) rebuild_lists_all_pairs<1>(k, s, traj, fm, fi, ops);
         return false;
     }
     if (ops & OP_REBUILD_BONDS) bonds_from_near<MPT>(k, s, near, traj, mo, idx);
+    if (with_fixed) {
+        const int nwarp = blockDim.x >> 5;
+        for (int f = threadIdx.x >> 5; f < a.n_fixed; f += nwarp) rebuild_row_cooperative(k, s, traj, (int)a.fmap[f], ops);
+    }
     return (ops & OP_REBUILD_LJ) != 0 || !k.p.lj_on;
 }
 
@@ -748,12 +856,15 @@ __device__ __forceinline__ void integrate_monomer(const maddy_params &p, Mono &m
     if (!(m.flags & MF_FIXED) && !(m.flags & MF_EXTRA)) {
         const float4 rf_xyz = rforce(m.rx);
         const float4 rf_ang = rforce(m.ra);
-        m.x += (p.dt / p.gammaR) * f.x + p.varR * rf_xyz.x;
-        m.y += (p.dt / p.gammaR) * f.y + p.varR * rf_xyz.y;
-        m.z += (p.dt / p.gammaR) * f.z + p.varR * rf_xyz.z;
-        m.fi += (p.dt / (p.gammaTheta * p.alpha)) * f.fi + (p.varTheta * sqrtf(p.freeze_temp / p.alpha)) * rf_ang.x;
-        m.psi += (p.dt / (p.gammaTheta * p.alpha)) * f.psi + (p.varTheta * sqrtf(p.freeze_temp / p.alpha)) * rf_ang.y;
-        m.theta += (p.dt / p.gammaTheta) * f.theta + p.varTheta * rf_ang.z;
+        // same shape as the reference's SASS: noise * var (FMUL), force * (dt/gamma) + that (FFMA), coordinate + that (FADD)
+        const float aR = p.dt / p.gammaR, aA = p.dt / (p.gammaTheta * p.alpha), aT = p.dt / p.gammaTheta;
+        const float vA = p.varTheta * sqrtf(p.freeze_temp / p.alpha);
+        m.x += fmaf(f.x, aR, p.varR * rf_xyz.x);
+        m.y += fmaf(f.y, aR, p.varR * rf_xyz.y);
+        m.z += fmaf(f.z, aR, p.varR * rf_xyz.z);
+        m.fi += fmaf(f.fi, aA, vA * rf_ang.x);
+        m.psi += fmaf(f.psi, aA, vA * rf_ang.y);
+        m.theta += fmaf(f.theta, aT, p.varTheta * rf_ang.z);
     }
 }
 
@@ -839,9 +950,8 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     uint4 *srng = reinterpret_cast<uint4 *>(smem) + (k.rng_smem_offset >> 4);
     if (k.topo_smem_offset >= 0) near.topo = reinterpret_cast<uint4 *>(smem) + (k.topo_smem_offset >> 4);
 
-    // movers: MPT per thread; slot MPT of the arrays is the (at most one) fixed monomer this thread looks after
-    Mono mo[MPT + 1];
-    int idx[MPT + 1];
+    Mono mo[MPT];
+    int idx[MPT];
 #pragma unroll
     for (int t = 0; t < MPT; t++) {
         const int slot = threadIdx.x + t * blockDim.x;
@@ -860,12 +970,12 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
             if (near.topo) near.topo[i] = load_topo(a, traj, i);
         }
     }
-    idx[MPT] = (int)threadIdx.x < a.n_fixed ? (int)a.fmap[threadIdx.x] : N;
-    mo[MPT].flags = MF_EXTRA | MF_FIXED;
-    if (idx[MPT] < N) {
-        load_mono(a, base, idx[MPT], mo[MPT]);
-        publish(stage_at(smem, N, 0), idx[MPT], mo[MPT], ls);
-        if (k.nbuf == 2) publish(stage_at(smem, N, 1), idx[MPT], mo[MPT], ls);
+    if ((int)threadIdx.x < a.n_fixed) { // fixed monomers never move: published once, into both stage buffers
+        const int i = (int)a.fmap[threadIdx.x];
+        Mono fm;
+        load_mono(a, base, i, fm);
+        publish(stage_at(smem, N, 0), i, fm, ls);
+        if (k.nbuf == 2) publish(stage_at(smem, N, 1), i, fm, ls);
     }
 
     CandState cs; // candidate-list state (persists in HBM between launches)
@@ -895,7 +1005,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                                 !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
         bool formed = false;
         if (do_rebuild) {
-            near_state = rebuild_lists<MPT + 1>(k, s, near, cs, traj, mo, idx, rops) ? 1 : 2;
+            near_state = rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, rops, true) ? 1 : 2;
             formed = true;
             if (near.topo) { // own rows were just rewritten by this thread
 #pragma unroll
@@ -903,7 +1013,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                     if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
             }
         } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
-            const bool ovf = refresh_near<MPT + 1>(k, s, near, traj, mo, idx);
+            const bool ovf = refresh_near<MPT>(k, s, near, traj, mo, idx);
             near_state = __syncthreads_or(ovf) ? 2 : 1;
             formed = true;
         }
@@ -982,7 +1092,7 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
         CandState cs;
         cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
         cs.dirty = false;
-        rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, k.ops);
+        rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, k.ops, false);
         store_cand_state(a, cs, traj);
     }
     near.ok = false;
