@@ -61,35 +61,36 @@ __device__ __forceinline__ LatSite lateral_site()
     return s;
 }
 
-// Orientation frame of one monomer.
+// What the force evaluation needs of a monomer's orientation R = Rz(psi) Ry(theta) Rx(fi): the body x axis
+// e1 = R x^ and (sin psi, cos psi).  Every derivative of a site offset o = R p is a cross product with the
+// instantaneous rotation axis of the angle:   d o/d fi = e1 x o,   d o/d psi = z^ x o,   d o/d theta = (-sp, cp, 0) x o,
+// so no other trigonometric value has to stay alive between publish() and the bond loops (five registers).
 struct Frame {
-    float sf, cf, sp, cp, st, ct;
-    F3 e1, e2, e3; // columns of R = Rz(psi) Ry(theta) Rx(fi)
-    F3 g;          // -d(e1)/d(theta)
+    float e1x, e1y, e1z, sp, cp;
 };
 
-__device__ __forceinline__ Frame make_frame(float fi, float psi, float theta)
+// Evaluates the frame once per step: the six MUFU sin/cos, the site offsets staged for neighbours
+// (a = r_mon*e3: "end" sites are +-a;  l1 = R*p1, l2 = R*p2) and the five values the force loops keep.
+__device__ __forceinline__ Frame make_frame(float fi, float psi, float theta, const LatSite &ls, F3 &a, F3 &l1, F3 &l2)
 {
-    Frame f;
-    f.sf = sinf(fi);    f.cf = cosf(fi);
-    f.sp = sinf(psi);   f.cp = cosf(psi);
-    f.st = sinf(theta); f.ct = cosf(theta);
-    f.e1 = mk3(f.cp * f.ct, f.sp * f.ct, -f.st);
-    f.e2 = mk3(fmaf(f.cp * f.sf, f.st, -(f.cf * f.sp)), fmaf(f.sf * f.sp, f.st, f.cf * f.cp), f.ct * f.sf);
-    f.e3 = mk3(fmaf(f.cf * f.cp, f.st, f.sf * f.sp), fmaf(f.cf * f.sp, f.st, -(f.cp * f.sf)), f.cf * f.ct);
-    f.g = mk3(f.cp * f.st, f.sp * f.st, f.ct);
-    return f;
-}
-
-// Site offsets staged for neighbours: a = r_mon*e3 ("end" sites are +-a), l1 = R*p1, l2 = R*p2
-__device__ __forceinline__ void site_offsets(const Frame &f, const LatSite &ls, F3 &a, F3 &l1, F3 &l2)
-{
-    a = mk3(MD_R_MON * f.e3.x, MD_R_MON * f.e3.y, MD_R_MON * f.e3.z);
+    const float sf = sinf(fi), cf = cosf(fi);
+    const float sp = sinf(psi), cp = cosf(psi);
+    const float st = sinf(theta), ct = cosf(theta);
+    const F3 e1 = mk3(cp * ct, sp * ct, -st);
+    const F3 e2 = mk3(fmaf(cp * sf, st, -(cf * sp)), fmaf(sf * sp, st, cf * cp), ct * sf);
+    const F3 e3 = mk3(fmaf(cf * cp, st, sf * sp), fmaf(cf * sp, st, -(cp * sf)), cf * ct);
+    a = mk3(MD_R_MON * e3.x, MD_R_MON * e3.y, MD_R_MON * e3.z);
     // u = xp*e1, v = yp*e2 + zp*e3 ; l1 = u + v, l2 = u - v
-    F3 u = mk3(ls.xp * f.e1.x, ls.xp * f.e1.y, ls.xp * f.e1.z);
-    F3 v = mk3(fmaf(ls.yp, f.e2.x, ls.zp * f.e3.x), fmaf(ls.yp, f.e2.y, ls.zp * f.e3.y), fmaf(ls.yp, f.e2.z, ls.zp * f.e3.z));
+    const F3 u = mk3(ls.xp * e1.x, ls.xp * e1.y, ls.xp * e1.z);
+    const F3 v = mk3(fmaf(ls.yp, e2.x, ls.zp * e3.x), fmaf(ls.yp, e2.y, ls.zp * e3.y), fmaf(ls.yp, e2.z, ls.zp * e3.z));
     l1 = mk3(u.x + v.x, u.y + v.y, u.z + v.z);
     l2 = mk3(u.x - v.x, u.y - v.y, u.z - v.z);
+    Frame f;
+    f.e1x = e1.x; f.e1y = e1.y; f.e1z = e1.z; f.sp = sp; f.cp = cp;
+    // keep these five in registers: under pressure the compiler would otherwise re-issue the MUFU sin/cos at every
+    // use (the XU pipe is the scarcest one in this kernel)
+    asm volatile("" : "+f"(f.e1x), "+f"(f.e1y), "+f"(f.e1z), "+f"(f.sp), "+f"(f.cp));
+    return f;
 }
 
 // |d| as the reference forms it: fp64 sum of squares (order z,x,y), rounded to float,
@@ -131,22 +132,20 @@ __device__ __forceinline__ float barr(float a, float r, float w, float x)
 }
 
 // Accumulate the generalized force of one bond on monomer i.
-//   d   = site_j - site_i
-//   k   = -U'(dr)/dr * (-1) ... i.e. F_xyz += k*d,  F_q += k * d . d(site_i)/dq
-//   o   = own site offset R_i*p,  (xp,yp,zp) = p (own local site)
-// d(Rp)/dfi = yp*e3 - zp*e2 ; d(Rp)/dpsi = (-o.y, o.x, 0) ; d(Rp)/dtheta = -xp*g + (yp*sf+zp*cf)*e1
-__device__ __forceinline__ void bond_accumulate(G6 &f, float k, const F3 &d, const F3 &o, float xp, float yp, float zp,
-                                                const Frame &fr)
+//   d = site_j - site_i,  k = U'(dr)/dr:   F_xyz += k d,   F_q += k d . d(site_i)/dq,   o = own site offset R_i p
+__device__ __forceinline__ void bond_accumulate(G6 &f, float k, const F3 &d, const F3 &o, const Frame &fr)
 {
     f.x = fmaf(k, d.x, f.x);
     f.y = fmaf(k, d.y, f.y);
     f.z = fmaf(k, d.z, f.z);
-    F3 dfi = mk3(fmaf(yp, fr.e3.x, -(zp * fr.e2.x)), fmaf(yp, fr.e3.y, -(zp * fr.e2.y)), fmaf(yp, fr.e3.z, -(zp * fr.e2.z)));
-    float c = fmaf(yp, fr.sf, zp * fr.cf);
-    F3 dth = mk3(fmaf(c, fr.e1.x, -(xp * fr.g.x)), fmaf(c, fr.e1.y, -(xp * fr.g.y)), fmaf(c, fr.e1.z, -(xp * fr.g.z)));
-    f.fi = fmaf(k, dot3(d, dfi), f.fi);
+    // d . (e1 x o)
+    const float tfi = fmaf(d.z, fmaf(fr.e1x, o.y, -(fr.e1y * o.x)),
+                           fmaf(d.y, fmaf(fr.e1z, o.x, -(fr.e1x * o.z)), d.x * fmaf(fr.e1y, o.z, -(fr.e1z * o.y))));
+    // d . ((-sp, cp, 0) x o) = o.z (cp d.x + sp d.y) - d.z (sp o.y + cp o.x)
+    const float tth = fmaf(o.z, fmaf(fr.cp, d.x, fr.sp * d.y), -(d.z * fmaf(fr.sp, o.y, fr.cp * o.x)));
+    f.fi = fmaf(k, tfi, f.fi);
     f.psi = fmaf(k, fmaf(d.y, o.x, -(d.x * o.y)), f.psi);
-    f.theta = fmaf(k, dot3(d, dth), f.theta);
+    f.theta = fmaf(k, tth, f.theta);
 }
 
 // ---------------------------------------------------------------- HybridTaus RNG

@@ -94,27 +94,26 @@ struct Mono { // register-resident state of one monomer
 #define MF_ONTUB 0x200
 #define MF_EXTRA 0x400
 
-__device__ __forceinline__ void publish(const Stage &s, int i, const Mono &m, const LatSite &ls)
+__device__ __forceinline__ Frame publish(const Stage &s, int i, const Mono &m, const LatSite &ls)
 {
-    Frame fr = make_frame(m.fi, m.psi, m.theta);
     F3 a, l1, l2;
-    site_offsets(fr, ls, a, l1, l2);
+    const Frame fr = make_frame(m.fi, m.psi, m.theta, ls, a, l1, l2);
     s.P[i] = make_float4(m.x, m.y, m.z, m.fi);
     s.E[i] = make_float4(a.x, a.y, a.z, m.psi);
     s.L1[i] = make_float4(l1.x, l1.y, l1.z, m.theta);
     int jf = MF_TYPE(m.flags) | (m.flags & (MF_GTP | MF_ONTUB | MF_EXTRA));
     s.L2[i] = make_float4(l2.x, l2.y, l2.z, __int_as_float(jf));
+    return fr;
 }
 
 // ------------------------------------------------------------------ forces
 // Generalized force on monomer i (non-extra) from the staged trajectory.
 __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, const Near &near, int traj, int i, const Mono &m,
-                                            const LatSite &ls)
+                                            const Frame &fr)
 {
     const maddy_params &p = k.p;
     const DevSys &a = k.a;
     G6 f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const Frame fr = make_frame(m.fi, m.psi, m.theta);
     const float4 Ei = s.E[i];
     const float xi = m.x, yi = m.y, zi = m.z;
     const bool gtp_i = (m.flags & MF_GTP) != 0;
@@ -134,21 +133,16 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
         d.z = fmaf(-sg, Ej.z, fmaf(-sg, Ei.z, Pj.z - zi));
         const float dr = site_distance(d);
-        bond_accumulate(f, p.C, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), 0.f, 0.f, sg * MD_R_MON, fr);
+        bond_accumulate(f, p.C, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), fr);
         if (dr < MD_ANGLE_CUTOFF) {
             const float psiji = Ej.w - m.psi;
             const float fiji = Pj.w - m.fi;
             const float thetaji = s.L1[j].w - m.theta;
             const float th0 = gtp_i ? p.theta0_gtp : p.theta0_gdp;
-            if (sg > 0) {
-                f.psi = fmaf(p.B_psi, sinf(psiji - p.psi_0), f.psi);
-                f.fi = fmaf(p.B_fi, sinf(fiji - p.fi_0), f.fi);
-                f.theta = fmaf(p.B_theta, sinf(thetaji - th0), f.theta);
-            } else {
-                f.psi = fmaf(-p.B_psi, sinf(-psiji - p.psi_0), f.psi);
-                f.fi = fmaf(-p.B_fi, sinf(-fiji - p.fi_0), f.fi);
-                f.theta = fmaf(-p.B_theta, sinf(-thetaji - th0), f.theta);
-            }
+            // +B sin(q_j - q_i - q0) on the R_MON > 0 side, -B sin(q_i - q_j - q0) on the other: sg (q_j - q_i) - q0, scaled by sg B
+            f.psi = fmaf(sg * p.B_psi, sinf(fmaf(sg, psiji, -p.psi_0)), f.psi);
+            f.fi = fmaf(sg * p.B_fi, sinf(fmaf(sg, fiji, -p.fi_0)), f.fi);
+            f.theta = fmaf(sg * p.B_theta, sinf(fmaf(sg, thetaji, -th0)), f.theta);
         }
     }
 
@@ -172,7 +166,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) {
             if (dr != 0.0f) dUdr += dbarr(p.a_barr_long, p.r_barr_long, p.w_barr_long, dr) / dr;
         }
-        bond_accumulate(f, dUdr, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), 0.f, 0.f, sg * MD_R_MON, fr);
+        bond_accumulate(f, dUdr, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), fr);
         if (dr < MD_ANGLE_CUTOFF) {
             const float psiji = Ej.w - m.psi;
             const float fiji = Pj.w - m.fi;
@@ -180,15 +174,10 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
             // the dimer closer to the plus end rules theta0 (compute_cuda.cu:282-283)
             const bool gtp_last = (zi > Pj.z) ? gtp_i : ((jf & MF_GTP) != 0);
             const float th0 = gtp_last ? p.theta0_gtp : p.theta0_gdp;
-            if (sg > 0) {
-                f.psi = fmaf(p.B_psi, sinf(psiji - p.psi_0), f.psi);
-                f.fi = fmaf(p.B_fi, sinf(fiji - p.fi_0), f.fi);
-                f.theta = fmaf(p.B_theta, sinf(thetaji - th0), f.theta);
-            } else {
-                f.psi = fmaf(-p.B_psi, sinf(-psiji - p.psi_0), f.psi);
-                f.fi = fmaf(-p.B_fi, sinf(-fiji - p.fi_0), f.fi);
-                f.theta = fmaf(-p.B_theta, sinf(-thetaji - th0), f.theta);
-            }
+            // +B sin(q_j - q_i - q0) on the R_MON > 0 side, -B sin(q_i - q_j - q0) on the other: sg (q_j - q_i) - q0, scaled by sg B
+            f.psi = fmaf(sg * p.B_psi, sinf(fmaf(sg, psiji, -p.psi_0)), f.psi);
+            f.fi = fmaf(sg * p.B_fi, sinf(fmaf(sg, fiji, -p.fi_0)), f.fi);
+            f.theta = fmaf(sg * p.B_theta, sinf(fmaf(sg, thetaji, -th0)), f.theta);
         }
     }
 
@@ -219,8 +208,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
             if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) {
                 if (dr != 0.0f) dUdr += dbarr(p.a_barr_lat, p.r_barr_lat, p.w_barr_lat, dr) / dr;
             }
-            const float ysg = neg ? 1.0f : -1.0f;
-            bond_accumulate(f, dUdr, d, oi, ls.xp, ysg * ls.yp, ysg * ls.zp, fr);
+            bond_accumulate(f, dUdr, d, oi, fr);
         }
     }
 
@@ -992,10 +980,11 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
         const Stage s = stage_at(smem, N, buf);
         bool moved = false;
+        Frame fr[MPT];
 #pragma unroll
         for (int t = 0; t < MPT; t++) {
             if (idx[t] < N) {
-                publish(s, idx[t], mo[t], ls);
+                fr[t] = publish(s, idx[t], mo[t], ls);
                 const float dx = mo[t].x - gx[t], dy = mo[t].y - gy[t], dz = mo[t].z - gz[t];
                 moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_NEAR_GUARD2;
             }
@@ -1029,7 +1018,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
 #pragma unroll
         for (int t = 0; t < MPT; t++) {
             if (idx[t] < N && !(mo[t].flags & (MF_EXTRA | MF_FIXED))) {
-                const G6 f = monomer_force(k, s, near, traj, idx[t], mo[t], ls);
+                const G6 f = monomer_force(k, s, near, traj, idx[t], mo[t], fr[t]);
                 if (kRngShared) {
                     mo[t].rx = srng[idx[t]];
                     mo[t].ra = srng[N + idx[t]];
@@ -1083,9 +1072,10 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
         if (i < N) load_mono(a, base, i, mo[t]);
     }
     const Stage s = stage_at(smem, N, 0);
+    Frame fr[MPT];
 #pragma unroll
     for (int t = 0; t < MPT; t++)
-        if (idx[t] < N) publish(s, idx[t], mo[t], ls);
+        if (idx[t] < N) fr[t] = publish(s, idx[t], mo[t], ls);
     __syncthreads();
 
     if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) {
@@ -1103,7 +1093,7 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
             const int i = idx[t];
             if (i < N && !(mo[t].flags & MF_EXTRA)) {
                 // extras keep the zero written by the integrator (compute_cuda.cu:55, :966-972)
-                const G6 f = monomer_force(k, s, near, traj, i, mo[t], ls);
+                const G6 f = monomer_force(k, s, near, traj, i, mo[t], fr[t]);
                 a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
                 a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
             }
