@@ -21,6 +21,7 @@ namespace maddy {
 cudaError_t launch_run_kernel(const KArgs &k, int mpt, int ctas_per_sm, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_phase_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st);
+cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 } // namespace maddy
 
@@ -37,6 +38,7 @@ struct maddy_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     LaunchCfg phase, run; // step-granular phase kernel / fused run kernel
+    StepConsts consts{};
     std::vector<uint16_t> amap, fmap;
     CutTest cut_pairs, cut_force;
     std::string err;
@@ -129,6 +131,9 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
     KArgs k;
     k.p = h->p;
     k.a = h->a;
+    k.c = h->consts;
+    k.barr_long_on = h->p.barrier && h->p.a_barr_long != 0.0f;
+    k.barr_lat_on = h->p.barrier && h->p.a_barr_lat != 0.0f;
     k.first_step = 0;
     k.n_steps = 0;
     k.ops = ops;
@@ -443,6 +448,18 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         CK(maddy_upload_on_tubule(h, top->on_tubule_cur));
         if (a.capLong > 0 && top->longitudinal) CK(maddy_upload_list(h, MADDY_LIST_LONGITUDINAL, top->longitudinal_count, top->longitudinal));
         if (a.capLat > 0 && top->lateral) CK(maddy_upload_list(h, MADDY_LIST_LATERAL, top->lateral_count, top->lateral));
+
+        // per-run constants, evaluated on the device (fast-math division / sqrt)
+        {
+            StepConsts *d_c = reinterpret_cast<StepConsts *>(a.en_traj); // scratch: not yet in use
+            cudaError_t ec = launch_consts_kernel(*par, d_c, h->stream);
+            if (ec != cudaSuccess) {
+                rc = fail(h, MADDY_ECUDA, "consts kernel: %s", cudaGetErrorString(ec));
+                goto bad;
+            }
+            CUK(cudaMemcpyAsync(&h->consts, d_c, sizeof(StepConsts), cudaMemcpyDeviceToHost, h->stream));
+            CUK(cudaStreamSynchronize(h->stream));
+        }
 
         // RNG: the GLOBAL table of 2*Ntot*Ntr states, sliced (HybridTaus.cu:21-31, compute_cuda.cu:1097)
         {

@@ -163,7 +163,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         float dUdr;
         if (dr == 0) dUdr = 0.0f;
         else dUdr = dmorse(p.D_long, p.A_long, dr) / dr;
-        if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) {
+        if (k.barr_long_on && !ontub_i && !(jf & MF_ONTUB)) {
             if (dr != 0.0f) dUdr += dbarr(p.a_barr_long, p.r_barr_long, p.w_barr_long, dr) / dr;
         }
         bond_accumulate(f, dUdr, d, mk3(sg * Ei.x, sg * Ei.y, sg * Ei.z), fr);
@@ -203,9 +203,9 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
             const float dr = site_distance(d);
             float dUdr;
             if (dr == 0) dUdr = 0.0f;
-            else if (type_i != (jf & 0x7f)) dUdr = dmorse(p.D_lat / p.seam_coeff, p.A_lat, dr) / dr;
+            else if (type_i != (jf & 0x7f)) dUdr = dmorse(k.c.D_lat_seam, p.A_lat, dr) / dr;
             else dUdr = dmorse(p.D_lat, p.A_lat, dr) / dr;
-            if (p.barrier && !ontub_i && !(jf & MF_ONTUB)) {
+            if (k.barr_lat_on && !ontub_i && !(jf & MF_ONTUB)) {
                 if (dr != 0.0f) dUdr += dbarr(p.a_barr_lat, p.r_barr_lat, p.w_barr_lat, dr) / dr;
             }
             bond_accumulate(f, dUdr, d, oi, fr);
@@ -839,14 +839,14 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
 }
 
 // ------------------------------------------------------------------ integrator (compute_cuda.cu:943-975)
-__device__ __forceinline__ void integrate_monomer(const maddy_params &p, Mono &m, const G6 &f)
+__device__ __forceinline__ void integrate_monomer(const KArgs &k, Mono &m, const G6 &f)
 {
+    const maddy_params &p = k.p;
     if (!(m.flags & MF_FIXED) && !(m.flags & MF_EXTRA)) {
         const float4 rf_xyz = rforce(m.rx);
         const float4 rf_ang = rforce(m.ra);
         // same shape as the reference's SASS: noise * var (FMUL), force * (dt/gamma) + that (FFMA), coordinate + that (FADD)
-        const float aR = p.dt / p.gammaR, aA = p.dt / (p.gammaTheta * p.alpha), aT = p.dt / p.gammaTheta;
-        const float vA = p.varTheta * sqrtf(p.freeze_temp / p.alpha);
+        const float aR = k.c.aR, aA = k.c.aA, aT = k.c.aT, vA = k.c.vA;
         m.x += fmaf(f.x, aR, p.varR * rf_xyz.x);
         m.y += fmaf(f.y, aR, p.varR * rf_xyz.y);
         m.z += fmaf(f.z, aR, p.varR * rf_xyz.z);
@@ -1023,7 +1023,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                     mo[t].rx = srng[idx[t]];
                     mo[t].ra = srng[N + idx[t]];
                 }
-                integrate_monomer(p, mo[t], f);
+                integrate_monomer(k, mo[t], f);
                 if (kRngShared) {
                     srng[idx[t]] = mo[t].rx;
                     srng[N + idx[t]] = mo[t].ra;
@@ -1118,6 +1118,23 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
     }
 }
 
+// Evaluates StepConsts with the device's fast-math arithmetic (the expressions of compute_cuda.cu:955-961, :448).
+__global__ void consts_kernel(maddy_params p, StepConsts *out)
+{
+    StepConsts c;
+    c.aR = p.dt / p.gammaR;
+    c.aA = p.dt / (p.gammaTheta * p.alpha);
+    c.aT = p.dt / p.gammaTheta;
+    c.vA = p.varTheta * sqrtf(p.freeze_temp / p.alpha);
+    c.D_lat_seam = p.D_lat / p.seam_coeff;
+    *out = c;
+}
+cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st)
+{
+    consts_kernel<<<1, 1, 0, st>>>(p, d_out);
+    return cudaGetLastError();
+}
+
 // Stand-alone integrator over forces stored in HBM (step-granular maddy_integrate).
 __global__ void __launch_bounds__(256) integrate_kernel(const __grid_constant__ KArgs k)
 {
@@ -1133,7 +1150,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(const __grid_constant__ 
             m.rx = a.rng_xyz[q];
             m.ra = a.rng_ang[q];
             G6 f = {FP.x, FP.y, FP.z, FA.x, FA.y, FA.z};
-            integrate_monomer(k.p, m, f);
+            integrate_monomer(k, m, f);
             a.pos[q] = make_float4(m.x, m.y, m.z, 0.f);
             a.ang[q] = make_float4(m.fi, m.psi, m.theta, 0.f);
             a.rng_xyz[q] = m.rx;

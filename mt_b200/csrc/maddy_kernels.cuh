@@ -85,8 +85,20 @@ struct DevSys {
 #define MD_CAND_GUARD2 0.5476f // 0.74^2 (< (MD_CAND_SKIN/2)^2)
 #define MD_CAND_CAPACITY 320
 
+// Per-run constants evaluated ONCE on the device (consts_kernel) with the same fast-math float expressions the
+// reference evaluates in every thread of every step (approximate division / sqrt), then passed by value.
+struct StepConsts {
+    float aR;         // dt / gammaR
+    float aA;         // dt / (gammaTheta * alpha)
+    float aT;         // dt / gammaTheta
+    float vA;         // varTheta * sqrt(freeze_temp / alpha)
+    float D_lat_seam; // D_lat / seam_coeff
+};
+
 struct KArgs {
     maddy_params p;
+    StepConsts c;
+    int barr_long_on, barr_lat_on; // barrier term present AND its amplitude non-zero (a zero amplitude adds exactly -0)
     DevSys a;
     long long first_step, n_steps;
     unsigned ops;
