@@ -199,22 +199,28 @@ def run_own(args):
         e2e_sys = make_system(args.workload, ntr_local, tmp / "e2e", [f"device={local}"])
         e2e_sys.compute(steps=min(args.steps, 200))  # untimed: module load / context warm-up
         e2e_sys.close()
-        # DCD frames, mt_len.dat and hydrolysis.pdb are written like the reference executable does (background writer)
-        e2e_sys = make_system(args.workload, ntr_local, tmp / "e2e2", [f"device={local}"], write_files=True, steps=args.steps)
-        if world > 1:
-            dist.barrier()
-        with workspace.chdir(tmp / "e2e2"):
-            t0 = time.perf_counter()
-            st = e2e_sys.compute()
-            wall = time.perf_counter() - t0
+        # DCD frames, mt_len.dat and hydrolysis.pdb are written like the reference executable does (background writer).
+        # The host side (file system, scheduler) makes single runs noisy: three runs, the median is reported.
+        walls = []
+        for rep in range(3):
+            e2e_sys = make_system(args.workload, ntr_local, tmp / f"e2e_{rep}", [f"device={local}"], write_files=True, steps=args.steps)
+            e2e_sys.srand(e2e_sys.par.rseed)
+            if world > 1:
+                dist.barrier()
+            with workspace.chdir(tmp / f"e2e_{rep}"):
+                t0 = time.perf_counter()
+                st = e2e_sys.compute()
+                walls.append(time.perf_counter() - t0)
+            e2e_sys.close()
+            shutil.rmtree(tmp / f"e2e_{rep}", ignore_errors=True)
+        wall = sorted(walls)[1]
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         e2e = {"value": N * ntr_global * args.steps / float(tw.item()), "unit": UNIT,
                "h2d_bytes_per_step": st["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st["d2h_bytes"] / args.steps,
                "call": "mt_system_compute (drop-in compute(): create + upload, fused windows, hydrolysis uploads, stride downloads, DCD output)",
-               "wall_s": float(tw.item())}
-        e2e_sys.close()
+               "wall_s": float(tw.item()), "wall_s_runs": [round(w, 4) for w in walls], "statistic": "median of 3 runs"}
 
         if rank == 0:
             achieved = value / world * B_ALG / 1e9  # per-GPU algorithmic GB/s of the dominant (only) kernel

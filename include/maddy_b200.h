@@ -157,11 +157,23 @@ int maddy_tea_integrate(maddy_handle *h);              /* integrateTea, bdhitea.
  * Observationally identical to n_steps x (rebuild?; force; integrate). Asynchronous. */
 int maddy_run(maddy_handle *h, long long first_step, long long n_steps, unsigned flags);
 
+/* ---- GTP schedule (folds the hydrolysis uploads into the fused window).
+ * hydrolyse() (updater.cpp:229-257) reads only host flags that change at stride steps, so the host can evaluate
+ * every hydrolysis event up to the next stride in advance (same rand() order) and hand the resulting GTP flags over
+ * in one call: slot k (gtp_slots + k * n_tr_local * n_tot ints, same layout as maddy_upload_gtp) becomes the
+ * current GTP state at the START of step first_event + k * period, exactly as if maddy_upload_gtp had been called
+ * before that step.  A following maddy_run may then span those steps in ONE launch.  The schedule is consumed by
+ * the runs that cover it; maddy_upload_gtp clears it.  n_slots = 0 clears it. */
+int maddy_schedule_gtp(maddy_handle *h, long long first_event, long long period, int n_slots, const int *gtp_slots);
+
 /* ---- energies: energy_kernel + OutputAllEnergies (compute_cuda.cu:676-911,
  * updater.cpp:3-43).  out_per_traj: [n_tr_local][7] doubles (harm,long,lat,psi,fi,teta,lj);
  * out_per_monomer (may be NULL): [n_tr_local*n_tot][7] doubles in the reference's
  * `Energies` field order (U_harm,U_long,U_lat,U_psi,U_fi,U_teta,U_lj; mt.h:94-102). */
 int maddy_energies(maddy_handle *h, double *out_per_traj, double *out_per_monomer);
+/* The stride block of the reference loop rebuilds the lists and then evaluates the energies (compute_cuda.cu:1140-1170):
+ * same as maddy_rebuild_lj + maddy_rebuild_bonds + maddy_energies, in ONE launch. */
+int maddy_rebuild_and_energies(maddy_handle *h, double *out_per_traj, double *out_per_monomer);
 /* device-resident result of the last maddy_energies call: [n_tr_local][7] doubles */
 void *maddy_energies_device(maddy_handle *h);
 

@@ -252,6 +252,12 @@ class Engine:
         self._ck(capi.lib.maddy_energies(self._h, as_ptr(out, C.c_double), as_ptr(mono, C.c_double) if per_monomer else None))
         return (out, mono) if per_monomer else out
 
+    def rebuild_and_energies(self):
+        """list rebuild + energies of the reference's stride block in one launch"""
+        out = np.empty((self.ntr, 7), dtype=np.float64)
+        self._ck(capi.lib.maddy_rebuild_and_energies(self._h, as_ptr(out, C.c_double), None))
+        return out
+
     @property
     def energies_device_ptr(self) -> int:
         return capi.lib.maddy_energies_device(self._h) or 0
@@ -273,6 +279,12 @@ class Engine:
     def upload_gtp(self, g):
         g = np.ascontiguousarray(g, dtype=np.int32)
         self._ck(capi.lib.maddy_upload_gtp(self._h, as_ptr(g, C.c_int)))
+
+    def schedule_gtp(self, first_event: int, period: int, slots):
+        """slots[k] ([ntr, N] ints) becomes the GTP state at the start of step first_event + k*period (see maddy_schedule_gtp)"""
+        g = np.ascontiguousarray(slots, dtype=np.int32)
+        n = 0 if g.size == 0 else g.reshape(-1, self.ntr * self.N).shape[0]
+        self._ck(capi.lib.maddy_schedule_gtp(self._h, int(first_event), int(period), n, as_ptr(g, C.c_int) if n else None))
 
     def upload_on_tubule(self, g):
         g = np.ascontiguousarray(g, dtype=np.int32)

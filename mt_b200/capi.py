@@ -95,7 +95,7 @@ KERNEL_SYMBOLS = [
     "maddy_energies", "maddy_energies_device", "maddy_download_coords", "maddy_download_forces", "maddy_upload_coords",
     "maddy_upload_gtp", "maddy_upload_on_tubule", "maddy_upload_extra", "maddy_download_list", "maddy_upload_list",
     "maddy_download_rng", "maddy_upload_rng", "maddy_generate_seeds", "maddy_tea_beta", "maddy_ensemble_allreduce",
-    "maddy_launch_count",
+    "maddy_launch_count", "maddy_schedule_gtp", "maddy_rebuild_and_energies",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
@@ -115,6 +115,7 @@ _sig(lib.maddy_tea_update, _i, [_vp, _ll])
 _sig(lib.maddy_run, _i, [_vp, _ll, _ll, _u])
 _sig(lib.maddy_energies, _i, [_vp, _pd, _pd])
 _sig(lib.maddy_energies_device, _vp, [_vp])
+_sig(lib.maddy_rebuild_and_energies, _i, [_vp, _pd, _pd])
 _sig(lib.maddy_download_coords, _i, [_vp, _pf])
 _sig(lib.maddy_download_forces, _i, [_vp, _pf])
 _sig(lib.maddy_upload_coords, _i, [_vp, _pf])
@@ -129,6 +130,7 @@ _sig(lib.maddy_generate_seeds, None, [C.POINTER(C.c_uint), _i, _ll])
 _sig(lib.maddy_tea_beta, _i, [C.c_double, _i, _i, C.c_float, C.c_float, _pf, _pd])
 _sig(lib.maddy_ensemble_allreduce, _i, [C.POINTER(_vp), _i, C.POINTER(_pd), _i])
 _sig(lib.maddy_launch_count, _ll, [_vp])
+_sig(lib.maddy_schedule_gtp, _i, [_vp, _ll, _ll, _i, _pi])
 
 _sig(hostlib.mt_host_last_error, C.c_char_p, [])
 _sig(hostlib.mt_system_load, _i, [C.c_char_p, _i, C.POINTER(C.c_char_p), _u, C.POINTER(_vp)])

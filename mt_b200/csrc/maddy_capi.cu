@@ -39,6 +39,11 @@ struct maddy_handle {
     bool own_stream = false;
     LaunchCfg phase, run; // step-granular phase kernel / fused run kernel
     StepConsts consts{};
+    // GTP schedule (maddy_schedule_gtp)
+    uint8_t *d_sched = nullptr;
+    size_t sched_capacity = 0;
+    long long sched_first = 0, sched_period = 1;
+    int sched_slots = 0;
     std::vector<uint16_t> amap, fmap;
     CutTest cut_pairs, cut_force;
     std::string err;
@@ -136,6 +141,10 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
     k.barr_lat_on = h->p.barrier && h->p.a_barr_lat != 0.0f;
     k.first_step = 0;
     k.n_steps = 0;
+    k.sched_first = h->sched_first;
+    k.sched_period = h->sched_period;
+    k.sched_slots = (ops & OP_RUN) ? h->sched_slots : 0;
+    k.a.gtp_sched = h->d_sched;
     k.ops = ops;
     k.run_flags = 0;
     const LaunchCfg &c = (ops & OP_RUN) ? h->run : h->phase;
@@ -227,6 +236,7 @@ extern "C" int maddy_destroy(maddy_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *q : h->allocs) cudaFree(q);
     if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->d_sched) cudaFree(h->d_sched);
     for (int k = 0; k < maddy_handle::kStage; k++) {
         if (h->stage[k]) cudaFreeHost(h->stage[k]);
         if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]);
@@ -522,10 +532,21 @@ extern "C" int maddy_run(maddy_handle *h, long long first_step, long long n_step
     return launch(h, k);
 }
 
+static int energies_impl(maddy_handle *h, unsigned ops, double *out_per_traj, double *out_per_monomer);
 extern "C" int maddy_energies(maddy_handle *h, double *out_per_traj, double *out_per_monomer)
 {
     if (!h) return MADDY_EINVAL;
-    int rc = launch(h, kargs(h, OP_ENERGY));
+    return energies_impl(h, OP_ENERGY, out_per_traj, out_per_monomer);
+}
+extern "C" int maddy_rebuild_and_energies(maddy_handle *h, double *out_per_traj, double *out_per_monomer)
+{
+    if (!h) return MADDY_EINVAL;
+    const unsigned ops = OP_ENERGY | (h->p.lj_on ? OP_REBUILD_LJ : 0u) | (h->p.is_assembly ? OP_REBUILD_BONDS : 0u);
+    return energies_impl(h, ops, out_per_traj, out_per_monomer);
+}
+static int energies_impl(maddy_handle *h, unsigned ops, double *out_per_traj, double *out_per_monomer)
+{
+    int rc = launch(h, kargs(h, ops));
     if (rc) return rc;
     const size_t n = (size_t)h->a.ntr * h->a.N;
     if (out_per_traj)
@@ -602,9 +623,36 @@ static int stage_submit(maddy_handle *h, uint8_t *dst, int slot)
     CU(h, cudaEventRecord(h->stage_done[slot], h->stream));
     return MADDY_OK;
 }
+extern "C" int maddy_schedule_gtp(maddy_handle *h, long long first_event, long long period, int n_slots, const int *gtp_slots)
+{
+    if (!h || n_slots < 0 || (n_slots > 0 && (!gtp_slots || period <= 0))) return MADDY_EINVAL;
+    h->sched_slots = 0;
+    if (n_slots == 0) return MADDY_OK;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N, bytes = n * (size_t)n_slots;
+    if (bytes > h->sched_capacity) {
+        CU(h, cudaStreamSynchronize(h->stream)); // a running window may still read the old buffer
+        if (h->d_sched) cudaFree(h->d_sched);
+        h->d_sched = nullptr;
+        h->sched_capacity = 0;
+        cudaError_t e = cudaMalloc(&h->d_sched, bytes);
+        if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "cudaMalloc(%zu bytes) for the GTP schedule: %s", bytes, cudaGetErrorString(e));
+        h->sched_capacity = bytes;
+    }
+    std::vector<uint8_t> v(bytes);
+    for (size_t q = 0; q < bytes; q++) v[q] = (uint8_t)(gtp_slots[q] == 1 ? 1 : (gtp_slots[q] == 0 ? 0 : 2));
+    CU(h, cudaMemcpyAsync(h->d_sched, v.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream)); // v goes out of scope
+    h->sched_first = first_event;
+    h->sched_period = period;
+    h->sched_slots = n_slots;
+    return MADDY_OK;
+}
+
 extern "C" int maddy_upload_gtp(maddy_handle *h, const int *gtp)
 {
     if (!h || !gtp) return MADDY_EINVAL;
+    h->sched_slots = 0; // an explicit upload supersedes any schedule
     const size_t n = (size_t)h->a.ntr * h->a.N;
     uint8_t *v;
     int slot, rc = stage_acquire(h, &v, &slot);

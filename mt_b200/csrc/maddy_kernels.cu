@@ -977,8 +977,33 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     for (int t = 0; t < MPT; t++) gx[t] = gy[t] = gz[t] = 0.f;
     const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
 
+    int fixed_flags_dirty = 0; // stage buffers whose copy of a fixed monomer's GTP bit is stale
+    bool gtp_changed = false;
     for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
         const Stage s = stage_at(smem, N, buf);
+        // scheduled hydrolysis event: the GTP flags uploaded for this step become current (maddy_schedule_gtp)
+        if (k.sched_slots > 0 && step >= k.sched_first && (step - k.sched_first) % k.sched_period == 0) {
+            const long long slot = (step - k.sched_first) / k.sched_period;
+            if (slot < k.sched_slots) {
+                const uint8_t *g = a.gtp_sched + (size_t)slot * a.ntr * N + base;
+#pragma unroll
+                for (int t = 0; t < MPT; t++)
+                    if (idx[t] < N) mo[t].flags = (mo[t].flags & ~MF_GTP) | (g[idx[t]] == 1 ? MF_GTP : 0);
+                fixed_flags_dirty = k.nbuf; // fixed monomers are staged once: patch their flag word in each buffer in turn
+                gtp_changed = true;
+            }
+        }
+        if (fixed_flags_dirty > 0) {
+            if ((int)threadIdx.x < a.n_fixed) {
+                const long long slot = (step - k.sched_first) / k.sched_period; // latest slot at or before this step
+                const uint8_t *g = a.gtp_sched + (size_t)slot * a.ntr * N + base;
+                const int i = (int)a.fmap[threadIdx.x];
+                int jf = __float_as_int(s.L2[i].w);
+                jf = (jf & ~MF_GTP) | (g[i] == 1 ? MF_GTP : 0);
+                s.L2[i].w = __int_as_float(jf);
+            }
+            fixed_flags_dirty--;
+        }
         bool moved = false;
         Frame fr[MPT];
 #pragma unroll
@@ -1041,7 +1066,15 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
             a.ang[base + i] = make_float4(mo[t].fi, mo[t].psi, mo[t].theta, 0.f);
             a.rng_xyz[base + i] = kRngShared ? srng[i] : mo[t].rx;
             a.rng_ang[base + i] = kRngShared ? srng[N + i] : mo[t].ra;
+            if (gtp_changed) a.gtp[base + i] = (mo[t].flags & MF_GTP) ? 1 : 0;
         }
+    }
+    if (gtp_changed && (int)threadIdx.x < a.n_fixed) { // fixed monomers: last slot applied in this launch
+        const long long last = k.first_step + k.n_steps - 1;
+        long long slot = (last - k.sched_first) / k.sched_period;
+        if (slot >= k.sched_slots) slot = k.sched_slots - 1;
+        const int i = (int)a.fmap[threadIdx.x];
+        a.gtp[base + i] = a.gtp_sched[(size_t)slot * a.ntr * N + base + i] == 1 ? 1 : 0;
     }
     store_cand_state(a, cs, traj);
 }

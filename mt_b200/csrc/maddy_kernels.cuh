@@ -49,6 +49,7 @@ struct DevSys {
     const uint16_t *fmap;  // [n_fixed]  fixed monomers looked after by threads 0..n_fixed-1
     int n_active, n_fixed;
     uint8_t *extra, *gtp, *ontub;
+    const uint8_t *gtp_sched; // scheduled GTP states (maddy_schedule_gtp), or nullptr
     uint16_t *bl;
     uint8_t *bcnt;
     uint16_t *lj;
@@ -101,6 +102,9 @@ struct KArgs {
     int barr_long_on, barr_lat_on; // barrier term present AND its amplitude non-zero (a zero amplitude adds exactly -0)
     DevSys a;
     long long first_step, n_steps;
+    // GTP schedule: slot k of gtp_sched ([n_slots][n] bytes) becomes current at the start of step sched_first + k*sched_period
+    long long sched_first, sched_period;
+    int sched_slots;
     unsigned ops;
     unsigned run_flags;
     int nbuf;          // 1 or 2 shared-memory stage buffers

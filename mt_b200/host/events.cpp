@@ -358,7 +358,8 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // energies printed at a stride step are evaluated on the lists rebuilt at that step (compute_cuda.cu:1140-1170)
         const bool explicit_rebuild = rebuild_now && ((stride_now && hp.out_energy) || may_teleport || par.tea_on || !fused);
         prof.begin();
-        if (explicit_rebuild) {
+        const bool fused_stride_energy = explicit_rebuild && stride_now && hp.out_energy; // rebuild + energies in one launch below
+        if (explicit_rebuild && !fused_stride_energy) {
             for_each([&](Shard &d) {
                 if (par.lj_on) ck(maddy_rebuild_lj(d.h), d.h, "maddy_rebuild_lj");
                 if (par.is_assembly) ck(maddy_rebuild_bonds(d.h), d.h, "maddy_rebuild_bonds");
@@ -374,10 +375,17 @@ void compute(System &s, bool fused, ComputeStats *stats)
         }
         prof.end("upload gtp");
         prof.begin();
-        // ---- stride block (compute_cuda.cu:1163-1226)
+        // ---- stride block (compute_cuda.cu:1163-1226).  Everything the device needs (energies, downloads, on-tubule
+        // and insertion uploads) happens here; the output part (update(): stdout, DCD frames) is deferred until the next
+        // window has been queued, so the GPU does not wait for host formatting.
+        int deferred_output = 0;
         if (stride_now) {
             if (hp.out_energy) {
-                for_each([&](Shard &d) { ck(maddy_energies(d.h, &s.energies[(size_t)d.first * 7], nullptr), d.h, "maddy_energies"); });
+                for_each([&](Shard &d) {
+                    double *out = &s.energies[(size_t)d.first * 7];
+                    if (fused_stride_energy) ck(maddy_rebuild_and_energies(d.h, out, nullptr), d.h, "maddy_rebuild_and_energies");
+                    else ck(maddy_energies(d.h, out, nullptr), d.h, "maddy_energies");
+                });
                 st.d2h_bytes += (double)Ntr * 7 * 8;
             }
             if (hp.out_force) {
@@ -407,13 +415,12 @@ void compute(System &s, bool fused, ComputeStats *stats)
                             st.h2d_bytes += (double)n * 33;
                         }
                     }
-                    update(s, step, mt_len);
+                    deferred_output = 1;
                 } else {
-                    update(s, step, mt_len);
-                    mt_length(s, step, mt_len);
+                    deferred_output = 2; // step 0: update() first, then mt_length() (host flags only, nothing is uploaded)
                 }
             } else {
-                update(s, step, mt_len);
+                deferred_output = 1;
             }
         }
         prof.end("stride block");
@@ -421,9 +428,14 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // ---- steps up to the next host event
         long long next = hp.steps;
         next = std::min(next, (step / hp.stride + 1) * hp.stride);
-        if (hp.hydrolysis && hp.hydrostep > 0) next = std::min(next, (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
+        const bool stepwise = par.tea_on || !fused;
+        const bool hydro = hp.hydrolysis && hp.hydrostep > 0;
+        // One window per hydrolysis period: hydrolyse() for the NEXT event is evaluated on the host while the GPU runs
+        // the current window (see below), so the events cost no GPU idle time.  (maddy_schedule_gtp can fold several
+        // events into one launch, but their evaluation would then sit between two windows instead of beside one.)
+        if (hydro) next = std::min(next, (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
         const long long count = next - step;
-        if (par.tea_on || !fused) {
+        if (stepwise) {
             for (long long q = step; q < next; q++) {
                 for_each([&](Shard &d) {
                     if (q != step && q % par.ljpairsupdatefreq == 0) {
@@ -444,8 +456,14 @@ void compute(System &s, bool fused, ComputeStats *stats)
         }
         prof.end("launch window");
         prof.begin();
-        // overlap with the asynchronous window: evaluate the next hydrolysis event on the host now
-        if (hp.hydrolysis && next < hp.steps && next % hp.hydrostep == 0 && next != 0) {
+        if (deferred_output) {
+            update(s, step, mt_len);
+            if (deferred_output == 2) mt_length(s, step, mt_len);
+        }
+        prof.end("stride output");
+        prof.begin();
+        // overlap with the asynchronous window: evaluate the hydrolysis event AT the window end on the host now
+        if (hydro && next < hp.steps && next % hp.hydrostep == 0 && next != 0) {
             hydrolyse(s);
             hydrolysed_for = next;
         }

@@ -330,7 +330,9 @@ def test_drop_in_mt_executable_vs_reference_executable(rundir):
     if not refprobe.REF_MT.exists():
         pytest.skip("oracle/_ref/mt did not travel with the tree")
     mine_bin = ROOT / "mt_b200" / "mt"
-    d_ref = rundir("mt40_single", runnum=2, steps=300, stride=100)
+    # stride 350 with hydrolysis every 100 steps: events at 400, 500, 600 fall INSIDE a stride and are applied
+    # in-kernel from the GTP schedule; 350 and 700 are not multiples of the hydrolysis period
+    d_ref = rundir("mt40_single", runnum=2, steps=800, stride=350)
     d_own = d_ref.parent / (d_ref.name + "_own")
     shutil.copytree(d_ref, d_own)
     _, out_ref = refprobe.run_reference_mt(d_ref)
@@ -340,7 +342,7 @@ def test_drop_in_mt_executable_vs_reference_executable(rundir):
         for suffix, tol in ((".dcd", 1e-3), (".dcd_ang", 1e-4)):
             a = mt_b200.read_dcd(d_own / "dcd" / f"run_{t}{suffix}")
             b = mt_b200.read_dcd(d_ref / "dcd" / f"run_{t}{suffix}")
-            assert a.shape == b.shape == (3, 520, 3)
+            assert a.shape == b.shape == (3, 520, 3)  # frames at steps 0, 350, 700
             assert np.abs(a - b).max() < tol, (t, suffix, np.abs(a - b).max())
         # DCD headers are byte-identical up to the date remark (bytes 180..260)
         ha = (d_own / "dcd" / f"run_{t}.dcd").read_bytes()[:276]
@@ -350,6 +352,7 @@ def test_drop_in_mt_executable_vs_reference_executable(rundir):
     e_own = [[float(x) for x in m.group(2).split()] for m in map(pat.match, r.stdout.splitlines()) if m]
     e_ref = [[float(x) for x in m.group(2).split()] for m in map(pat.match, out_ref.splitlines()) if m]
     assert len(e_own) == len(e_ref) == 6
+    assert "Hydrolysis occured" in out_ref and re.findall(r"\*\*\* .* \*\*\*", r.stdout) == re.findall(r"\*\*\* .* \*\*\*", out_ref)
     assert np.allclose(e_own, e_ref, rtol=1e-4, atol=2e-2)
     assert re.findall(r"tubule\[\d\]: \d+", r.stdout) == re.findall(r"tubule\[\d\]: \d+", out_ref)
     assert (d_own / "result_xyz.pdb").exists() and (d_own / "mt_len.dat").read_text() == (d_ref / "mt_len.dat").read_text()
@@ -375,3 +378,30 @@ def test_list_hierarchy_equals_all_pairs_path_on_diffusing_dimers(rundir, load_s
     assert np.array_equal(fast.rng_state(), slow.rng_state())
     moved = np.linalg.norm(fast.coords()[..., :3] - c0[..., :3], axis=-1)
     assert moved.max() > 0.8  # the guards did trip
+
+
+def test_gtp_schedule_equals_explicit_uploads(rundir, load_system):
+    """maddy_schedule_gtp: GTP states applied in-kernel at scheduled steps == maddy_upload_gtp between shorter windows."""
+    s = load_system(rundir("mt40_ensemble", runnum=5), ["hydrolysis=no"])
+    rng = np.random.default_rng(3)
+    g = [(rng.random((5, s.Ntot // 2)) > p).astype(np.int32).repeat(2, axis=1) for p in (0.2, 0.5, 0.1)]
+    a, b = Engine(s), Engine(s)
+    a.run(0, 30)
+    a.upload_gtp(g[0])
+    a.run(30, 25)
+    a.upload_gtp(g[1])
+    a.run(55, 25)
+    a.upload_gtp(g[2])
+    a.run(80, 40)
+    b.schedule_gtp(30, 25, np.stack(g))
+    b.run(0, 120)
+    assert np.array_equal(a.coords(), b.coords()) and np.array_equal(a.rng_state(), b.rng_state())
+    assert np.array_equal(a.energies(), b.energies())  # the energy kernel sees the last scheduled GTP state
+    # a schedule is superseded by an explicit upload
+    c = Engine(s)
+    c.schedule_gtp(10, 10, np.stack(g))
+    c.upload_gtp(np.ones((5, s.Ntot), dtype=np.int32))
+    d = Engine(s)
+    c.run(0, 40)
+    d.run(0, 40)
+    assert np.array_equal(c.coords(), d.coords())
