@@ -247,7 +247,7 @@ def run_own(args):
             }
             if world == 1 and not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline(args.workload)
-            print(json.dumps(line), flush=True)
+            emit(line)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
         if world > 1:
@@ -262,7 +262,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     ref = ROOT / "oracle" / "_ref" / "mt"
     if not ref.exists():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/mt not built (needs /root/reference at build time)"}), flush=True)
+        emit({"impl": "reference", "unavailable": "oracle/_ref/mt not built (needs /root/reference at build time)"})
         return
     from mt_b200 import workspace
     ntr = min(args.ntr, REF_NTR_LIMIT)
@@ -301,12 +301,27 @@ def run_reference(args):
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                                  "sample": "the reference has no CPU implementation of the step loop; " + cores_note},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """Writes the one JSON line to the process's ORIGINAL stdout (see main())."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    # stdout carries exactly one line, the JSON result: anything a library prints on fd 1 while the run is in flight
+    # (NCCL's version banner, for one) is sent to stderr instead
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100000, help="MD steps to time (default: the 1e5-step run length of the BASELINE configs)")
