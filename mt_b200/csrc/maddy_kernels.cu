@@ -662,27 +662,31 @@ __device__ __forceinline__ bool filter_candidates(const KArgs &k, const Stage &s
             uint16_t *np = near.list + i;
             const int n = a.candcnt[(size_t)traj * a.Npad + i];
             const float x = mo[t].x, y = mo[t].y, z = mo[t].z;
-            for (int kk = 0; kk < n; kk++, cp += a.Npad) {
-                const unsigned j = *cp;
-                const float4 Pj = s.P[j];
-                const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
-                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                const bool inlj = do_lj && inside_cut(k.cut_pairs, dx, dy, dz, sf);
-                if (inlj) {
-                    if (nlj < MADDY_LJ_CAPACITY) {
-                        *lp = (uint16_t)j;
-                        lp += a.Npad;
-                    } else status |= ST_LJ_OVERFLOW;
-                    nlj++;
-                }
-                if (sf < MD_NEAR_R2) {
-                    if (nn < near.cap) {
-                        *np = (uint16_t)(j | (inlj ? MD_NEAR_LJ_FLAG : 0u));
-                        np += N;
-                    }
-                    nn++;
+            const size_t row = a.Npad;
+            // candidates are fetched MD_FILTER_BATCH at a time so the L2 latency of the index loads is paid once per
+            // batch instead of once per candidate; the list writes are predicated stores, no divergent branches
+            for (int k0 = 0; k0 < n; k0 += MD_FILTER_BATCH, cp += MD_FILTER_BATCH * row) {
+                unsigned jj[MD_FILTER_BATCH];
+#pragma unroll
+                for (int u = 0; u < MD_FILTER_BATCH; u++) jj[u] = k0 + u < n ? (unsigned)cp[u * row] : 0u;
+#pragma unroll
+                for (int u = 0; u < MD_FILTER_BATCH; u++) {
+                    const bool live = k0 + u < n;
+                    const unsigned j = jj[u];
+                    const float4 Pj = s.P[j];
+                    const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
+                    const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const bool inlj = live && do_lj && inside_cut(k.cut_pairs, dx, dy, dz, sf);
+                    if (inlj && nlj < MADDY_LJ_CAPACITY) *lp = (uint16_t)j;
+                    lp += inlj ? row : 0;
+                    nlj += inlj;
+                    const bool innear = live && sf < MD_NEAR_R2;
+                    if (innear && nn < near.cap) *np = (uint16_t)(j | (inlj ? MD_NEAR_LJ_FLAG : 0u));
+                    np += innear ? N : 0;
+                    nn += innear;
                 }
             }
+            if (nlj > MADDY_LJ_CAPACITY) status |= ST_LJ_OVERFLOW;
         }
         if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj, MADDY_LJ_CAPACITY);
         near.cnt[i] = (uint8_t)min(nn, near.cap);

@@ -85,6 +85,7 @@ struct DevSys {
 #define MD_CAND_SKIN 1.5f
 #define MD_CAND_GUARD2 0.5476f // 0.74^2 (< (MD_CAND_SKIN/2)^2)
 #define MD_CAND_CAPACITY 320
+#define MD_FILTER_BATCH 8 // candidate indices fetched per round trip in filter_candidates
 
 // Per-run constants evaluated ONCE on the device (consts_kernel) with the same fast-math float expressions the
 // reference evaluates in every thread of every step (approximate division / sqrt), then passed by value.

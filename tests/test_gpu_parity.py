@@ -405,3 +405,34 @@ def test_gtp_schedule_equals_explicit_uploads(rundir, load_system):
     c.run(0, 40)
     d.run(0, 40)
     assert np.array_equal(c.coords(), d.coords())
+
+
+def test_drop_in_const_conc_vs_reference_executable(rundir):
+    """BASELINE configs[2] shape (long MT + reserve dimers, walls, constant concentration): the insertion events of
+    change_conc() consume the libc rand() stream interleaved with hydrolysis; both executables must print the same
+    insertions and concentrations and write the same frames."""
+    import re
+    import shutil
+    import subprocess
+    import mt_b200
+    from oracle import refprobe
+    if not refprobe.REF_MT.exists():
+        pytest.skip("oracle/_ref/mt did not travel with the tree")
+    mine_bin = ROOT / "mt_b200" / "mt"
+    d_ref = rundir("mt120_constconc", runnum=2, steps=450, stride=200)
+    d_own = d_ref.parent / (d_ref.name + "_own")
+    shutil.copytree(d_ref, d_own)
+    _, out_ref = refprobe.run_reference_mt(d_ref)
+    r = subprocess.run([str(mine_bin), "config.conf"], cwd=str(d_own), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ins = re.compile(r"New x,y coordinates for extra particle: .*")
+    assert ins.findall(out_ref) and ins.findall(r.stdout) == ins.findall(out_ref)
+    conc = re.compile(r"Concentration for tajectory\[\d+\]: .*")
+    assert conc.findall(r.stdout) == conc.findall(out_ref)
+    assert re.findall(r"tubule\[\d\]: \d+", r.stdout) == re.findall(r"tubule\[\d\]: \d+", out_ref)
+    for t in range(2):
+        for suffix, tol in ((".dcd", 1e-3), (".dcd_ang", 1e-4)):
+            a = mt_b200.read_dcd(d_own / "dcd" / f"run_{t}{suffix}")
+            b = mt_b200.read_dcd(d_ref / "dcd" / f"run_{t}{suffix}")
+            assert a.shape == b.shape and a.shape[0] == 3
+            assert np.abs(a - b).max() < tol, (t, suffix, np.abs(a - b).max())
