@@ -641,6 +641,15 @@ __device__ __forceinline__ bool scan_candidates(const KArgs &k, const Stage &s, 
     return ovf;
 }
 
+__device__ __forceinline__ float4 lds_f4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v)); }
+__device__ __forceinline__ void stg_u16(const uint16_t *p, unsigned short v) { asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(v)); }
+
 // Fast path, phase 1b (every list-update step): the reference's Verlet list = candidates that pass the exact
 // cut-off test (HBM, k-major); near list (SMEM) = candidates within MD_NEAR_R.  Returns near-list overflow.
 template <int MPT>
@@ -658,32 +667,38 @@ __device__ __forceinline__ bool filter_candidates(const KArgs &k, const Stage &s
         int nlj = 0, nn = 0;
         if (!(mo[t].flags & MF_EXTRA)) {
             const uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
-            uint16_t *lp = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
-            uint16_t *np = near.list + i;
+            const uint16_t *lj_col = (const uint16_t *)__cvta_generic_to_global(a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i);
+            asm volatile("" : "+l"(lj_col)); // keep the column base in registers (otherwise re-derived at every store)
+            const unsigned P_s = (unsigned)__cvta_generic_to_shared(s.P);
+            unsigned near_s = (unsigned)__cvta_generic_to_shared(near.list + i);
+            const unsigned near_end = near_s + (unsigned)(near.cap * N) * 2u, near_step = (unsigned)N * 2u;
             const int n = a.candcnt[(size_t)traj * a.Npad + i];
             const float x = mo[t].x, y = mo[t].y, z = mo[t].z;
-            const size_t row = a.Npad;
+            const int row = a.Npad;
+            const float lo = do_lj ? k.cut_pairs.lo : -1.f, hi = do_lj ? k.cut_pairs.hi : -1.f;
+            int lj_off = 0; // element offset of the next free slot in this monomer's Verlet-list column
+            const int lj_end = MADDY_LJ_CAPACITY * row;
             // candidates are fetched MD_FILTER_BATCH at a time so the L2 latency of the index loads is paid once per
-            // batch instead of once per candidate; the list writes are predicated stores, no divergent branches
-            for (int k0 = 0; k0 < n; k0 += MD_FILTER_BATCH, cp += MD_FILTER_BATCH * row) {
+            // batch instead of once per candidate; list writes are predicated stores
+            for (int k0 = 0; k0 < n; k0 += MD_FILTER_BATCH, cp += MD_FILTER_BATCH * (size_t)row) {
                 unsigned jj[MD_FILTER_BATCH];
 #pragma unroll
-                for (int u = 0; u < MD_FILTER_BATCH; u++) jj[u] = k0 + u < n ? (unsigned)cp[u * row] : 0u;
+                for (int u = 0; u < MD_FILTER_BATCH; u++) jj[u] = k0 + u < n ? (unsigned)cp[u * (size_t)row] : 0u;
 #pragma unroll
                 for (int u = 0; u < MD_FILTER_BATCH; u++) {
-                    const bool live = k0 + u < n;
-                    const unsigned j = jj[u];
-                    const float4 Pj = s.P[j];
+                    const float4 Pj = lds_f4(P_s + jj[u] * 16u);
                     const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
-                    const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    const bool inlj = live && do_lj && inside_cut(k.cut_pairs, dx, dy, dz, sf);
-                    if (inlj && nlj < MADDY_LJ_CAPACITY) *lp = (uint16_t)j;
-                    lp += inlj ? row : 0;
-                    nlj += inlj;
-                    const bool innear = live && sf < MD_NEAR_R2;
-                    if (innear && nn < near.cap) *np = (uint16_t)(j | (inlj ? MD_NEAR_LJ_FLAG : 0u));
-                    np += innear ? N : 0;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const float sf = k0 + u < n ? d2 : 3.0e38f; // slots past the end of the list are outside every radius
+                    bool inlj = sf < lo;
+                    if (sf >= lo && sf <= hi) inlj = dist2_exact(dx, dy, dz) < k.cut_pairs.t; // +-1e-6 band: practically never
+                    if (inlj && lj_off < lj_end) stg_u16(lj_col + lj_off, (unsigned short)jj[u]);
+                    lj_off += inlj ? row : 0;
+                    const bool innear = sf < MD_NEAR_R2;
+                    if (innear && near_s < near_end) sts_u16(near_s, (unsigned short)(jj[u] | (inlj ? MD_NEAR_LJ_FLAG : 0u)));
+                    near_s += innear ? near_step : 0u;
                     nn += innear;
+                    nlj += inlj;
                 }
             }
             if (nlj > MADDY_LJ_CAPACITY) status |= ST_LJ_OVERFLOW;
