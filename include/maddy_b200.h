@@ -174,6 +174,18 @@ int maddy_energies(maddy_handle *h, double *out_per_traj, double *out_per_monome
 /* The stride block of the reference loop rebuilds the lists and then evaluates the energies (compute_cuda.cu:1140-1170):
  * same as maddy_rebuild_lj + maddy_rebuild_bonds + maddy_energies, in ONE launch. */
 int maddy_rebuild_and_energies(maddy_handle *h, double *out_per_traj, double *out_per_monomer);
+
+/* ---- asynchronous stride snapshot.  What the reference loop reads back at a stride step (energies :1163-1170,
+ * coordinates :1173, forces :1177) without stalling the stream: maddy_snapshot_begin enqueues [list rebuild +] energy
+ * evaluation and device -> pinned-host copies behind the work already queued and returns at once; work queued afterwards
+ * (the next maddy_run window) runs while the host waits in maddy_snapshot_end, which blocks only until THOSE copies
+ * have landed and converts them into the caller's arrays (any of which may be NULL).  One snapshot in flight per handle. */
+#define MADDY_SNAP_COORDS 1u
+#define MADDY_SNAP_FORCES 2u
+#define MADDY_SNAP_ENERGIES 4u
+#define MADDY_SNAP_REBUILD 8u /* with ENERGIES: rebuild the lists first, as maddy_rebuild_and_energies does */
+int maddy_snapshot_begin(maddy_handle *h, unsigned what);
+int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *forces_aos7, double *energies_per_traj);
 /* device-resident result of the last maddy_energies call: [n_tr_local][7] doubles */
 void *maddy_energies_device(maddy_handle *h);
 

@@ -258,6 +258,24 @@ class Engine:
         self._ck(capi.lib.maddy_rebuild_and_energies(self._h, as_ptr(out, C.c_double), None))
         return out
 
+    def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False):
+        """queue the stride read-back (maddy_snapshot_begin); work queued afterwards overlaps with snapshot_end()"""
+        what = (capi.SNAP_COORDS if coords else 0) | (capi.SNAP_FORCES if forces else 0) | (capi.SNAP_ENERGIES if energies else 0) \
+            | (capi.SNAP_REBUILD if rebuild else 0)
+        self._snap = what
+        self._ck(capi.lib.maddy_snapshot_begin(self._h, what))
+
+    def snapshot_end(self):
+        """-> dict with the arrays requested in snapshot_begin (state as of the point where it was queued)"""
+        what = self._snap
+        c = np.empty((self.ntr, self.N, 7), dtype=np.float32) if what & capi.SNAP_COORDS else None
+        f = np.empty((self.ntr, self.N, 7), dtype=np.float32) if what & capi.SNAP_FORCES else None
+        e = np.empty((self.ntr, 7), dtype=np.float64) if what & capi.SNAP_ENERGIES else None
+        self._ck(capi.lib.maddy_snapshot_end(self._h, as_ptr(c, C.c_float) if c is not None else None,
+                                             as_ptr(f, C.c_float) if f is not None else None,
+                                             as_ptr(e, C.c_double) if e is not None else None))
+        return {"coords": c, "forces": f, "energies": e}
+
     @property
     def energies_device_ptr(self) -> int:
         return capi.lib.maddy_energies_device(self._h) or 0

@@ -66,10 +66,12 @@ def build_kernels(force=False, verbose_ptxas=False):
     for src in srcs:
         obj = objdir / (src.stem + ".o")
         extra = ["-fmad=false"] if src.name == "maddy_kernels.cu" else []
+        if src.name == "maddy_capi.cu":
+            extra += ["-Xcompiler", "-fopenmp"]  # host-side flag conversions / read-back transposes
         if force or _stale(obj, deps):
             _run([NVCC, "-c", *common, *extra, "-o", obj, src])
         objs.append(obj)
-    _run([NVCC, "-shared", *ARCH, "-o", LIB_KERNELS, *objs, "-ldl"])
+    _run([NVCC, "-shared", *ARCH, "-o", LIB_KERNELS, *objs, "-ldl", "-lgomp"])
     return LIB_KERNELS
 
 
@@ -78,10 +80,10 @@ def build_host(force=False):
     deps = srcs + [HOST / "mt_host.hpp", HOST / "main.cpp", ROOT / "include" / "maddy_host.h", ROOT / "include" / "maddy_b200.h"]
     build_kernels(force)
     if force or _stale(LIB_HOST, deps + [LIB_KERNELS]):
-        _run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", f"-I{ROOT / 'include'}", f"-I{HOST}", "-o", LIB_HOST, *srcs,
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-fopenmp", "-shared", "-fPIC", f"-I{ROOT / 'include'}", f"-I{HOST}", "-o", LIB_HOST, *srcs,
               f"-L{PKG}", "-lmaddy_b200", "-Wl,-rpath,$ORIGIN"])
     if force or _stale(MT_BIN, deps + [LIB_HOST]):
-        _run(["g++", "-O2", "-std=c++17", "-pthread", f"-I{ROOT / 'include'}", f"-I{HOST}", "-o", MT_BIN, HOST / "main.cpp",
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-fopenmp", f"-I{ROOT / 'include'}", f"-I{HOST}", "-o", MT_BIN, HOST / "main.cpp",
               f"-L{PKG}", "-lmaddy_host", "-lmaddy_b200", "-Wl,-rpath,$ORIGIN"])
     return LIB_HOST
 

@@ -18,6 +18,7 @@ ENERGY_TERMS = 7
 ZERO_SENTINEL = 999999
 LJ_CAPACITY = 256
 RUN_SKIP_FIRST_REBUILD = 1
+SNAP_COORDS, SNAP_FORCES, SNAP_ENERGIES, SNAP_REBUILD = 1, 2, 4, 8
 LIST_LONGITUDINAL, LIST_LATERAL, LIST_LJ = 0, 1, 2
 LOAD_QUIET, LOAD_NO_FILES = 1, 2
 
@@ -95,7 +96,7 @@ KERNEL_SYMBOLS = [
     "maddy_energies", "maddy_energies_device", "maddy_download_coords", "maddy_download_forces", "maddy_upload_coords",
     "maddy_upload_gtp", "maddy_upload_on_tubule", "maddy_upload_extra", "maddy_download_list", "maddy_upload_list",
     "maddy_download_rng", "maddy_upload_rng", "maddy_generate_seeds", "maddy_tea_beta", "maddy_ensemble_allreduce",
-    "maddy_launch_count", "maddy_schedule_gtp", "maddy_rebuild_and_energies",
+    "maddy_launch_count", "maddy_schedule_gtp", "maddy_rebuild_and_energies", "maddy_snapshot_begin", "maddy_snapshot_end",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
@@ -131,6 +132,8 @@ _sig(lib.maddy_tea_beta, _i, [C.c_double, _i, _i, C.c_float, C.c_float, _pf, _pd
 _sig(lib.maddy_ensemble_allreduce, _i, [C.POINTER(_vp), _i, C.POINTER(_pd), _i])
 _sig(lib.maddy_launch_count, _ll, [_vp])
 _sig(lib.maddy_schedule_gtp, _i, [_vp, _ll, _ll, _i, _pi])
+_sig(lib.maddy_snapshot_begin, _i, [_vp, _u])
+_sig(lib.maddy_snapshot_end, _i, [_vp, _pf, _pf, _pd])
 
 _sig(hostlib.mt_host_last_error, C.c_char_p, [])
 _sig(hostlib.mt_system_load, _i, [C.c_char_p, _i, C.POINTER(C.c_char_p), _u, C.POINTER(_vp)])

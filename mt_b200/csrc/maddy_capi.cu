@@ -7,6 +7,9 @@
  * compute entry point launches the sm_100a kernels of maddy_kernels.cu or fails.
  */
 #include <cuda_runtime.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -21,11 +24,29 @@ namespace maddy {
 cudaError_t launch_run_kernel(const KArgs &k, int mpt, int ctas_per_sm, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_phase_kernel(const KArgs &k, int mpt, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st);
+cudaError_t launch_snapshot_kernel(const float4 *pos, const float4 *ang, float *out_mapped, size_t n_monomers, cudaStream_t st);
 cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 } // namespace maddy
 
 using namespace maddy;
+
+// The flag conversions and the SoA -> AoS read-back sit on the host's critical path between two fused windows; split
+// them over a few threads when the ensemble is large (no-op when built without OpenMP or with OMP_NUM_THREADS=1).
+#define HOST_PRAGMA(x) _Pragma(#x)
+#define HOST_PARALLEL_FOR(n) HOST_PRAGMA(omp parallel for schedule(static) num_threads(host_threads()) if ((n) > 65536))
+static int host_threads()
+{
+#ifdef _OPENMP
+    static const int k = [] {
+        int m = omp_get_max_threads();
+        return m > 8 ? 8 : (m < 1 ? 1 : m);
+    }();
+    return k;
+#else
+    return 1;
+#endif
+}
 
 struct LaunchCfg {
     int mpt = 1, threads = 32, ctas = 1, nbuf = 1, near_cap = 0, rng_off = 0, topo_off = -1;
@@ -56,6 +77,22 @@ struct maddy_handle {
     uint8_t *stage[kStage] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t stage_done[kStage] = {nullptr, nullptr, nullptr, nullptr};
     int stage_next = 0;
+    // asynchronous stride snapshot (maddy_snapshot_begin/_end): pinned host mirrors of state, forces and energies
+    float4 *snap_pos = nullptr, *snap_ang = nullptr; // synchronous download path
+    float *snap_r = nullptr, *snap_f = nullptr;      // pinned AoS-7 mirrors of the snapshot
+    float *d_snap_r = nullptr, *d_snap_f = nullptr;  // device staging written by snapshot_kernel
+    double *d_snap_en = nullptr;
+    int *d_snap_status = nullptr;
+    cudaStream_t copy_stream = nullptr;              // the D2H leg runs beside the next window
+    cudaEvent_t snap_staged = nullptr;
+    double *snap_en = nullptr;
+    cudaEvent_t snap_done = nullptr;
+    unsigned snap_what = 0;
+    // MADDY_GPU_PROFILE=1: event pair around every kernel launch, summarised by maddy_destroy (development aid)
+    bool gpu_prof = getenv("MADDY_GPU_PROFILE") != nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<unsigned> prof_ops;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_copy;
 };
 
 static thread_local std::string g_create_error;
@@ -185,8 +222,19 @@ static int sync_and_check(maddy_handle *h)
 static int launch(maddy_handle *h, const KArgs &k)
 {
     CU(h, cudaSetDevice(h->p.device));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->gpu_prof) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, h->stream);
+    }
     cudaError_t e = (k.ops & OP_RUN) ? launch_run_kernel(k, h->run.mpt, h->run.ctas, h->run.threads, h->run.smem, h->stream)
                                      : launch_phase_kernel(k, h->phase.mpt, h->phase.threads, h->phase.smem, h->stream);
+    if (h->gpu_prof) {
+        cudaEventRecord(e1, h->stream);
+        h->prof_events.push_back({e0, e1});
+        h->prof_ops.push_back(k.ops);
+    }
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "trajectory kernel launch (ops=%u): %s", k.ops, cudaGetErrorString(e));
     h->launches++;
     return MADDY_OK;
@@ -234,6 +282,42 @@ extern "C" int maddy_destroy(maddy_handle *h)
     if (!h) return MADDY_EINVAL;
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->gpu_prof && !h->prof_events.empty()) {
+        double busy = 0;
+        float ms = 0, span = 0;
+        for (auto &pr : h->prof_events) {
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            busy += ms;
+        }
+        cudaEventElapsedTime(&span, h->prof_events.front().first, h->prof_events.back().second);
+        for (size_t q = 0; q < h->prof_copy.size() && q < 12; q++) {
+            cudaEventElapsedTime(&ms, h->prof_copy[q].first, h->prof_copy[q].second);
+            fprintf(stderr, "[maddy gpu profile] snapshot copy segment %zu: %.3f ms\n", q, ms);
+        }
+        double gsum[4] = {0, 0, 0, 0};
+        int gcnt[4] = {0, 0, 0, 0};
+        for (size_t q = 1; q < h->prof_events.size(); q++) {
+            cudaEventElapsedTime(&ms, h->prof_events[q - 1].second, h->prof_events[q].first);
+            const int b = ms < 0.02f ? 0 : ms < 0.1f ? 1 : ms < 0.5f ? 2 : 3;
+            if (b == 3 && gcnt[3] < 6) {
+                float k0 = 0, k1 = 0;
+                cudaEventElapsedTime(&k0, h->prof_events[q - 1].first, h->prof_events[q - 1].second);
+                cudaEventElapsedTime(&k1, h->prof_events[q].first, h->prof_events[q].second);
+                fprintf(stderr, "[maddy gpu profile] gap %.3f ms between launch %zu (ops %u, %.3f ms) and %zu (ops %u, %.3f ms)\n", ms, q - 1,
+                        h->prof_ops[q - 1], k0, q, h->prof_ops[q], k1);
+            }
+            gsum[b] += ms;
+            gcnt[b]++;
+        }
+        fprintf(stderr, "[maddy gpu profile] gaps <20us: %d (%.2f ms)  20-100us: %d (%.2f ms)  0.1-0.5ms: %d (%.2f ms)  >0.5ms: %d (%.2f ms)\n",
+                gcnt[0], gsum[0], gcnt[1], gsum[1], gcnt[2], gsum[2], gcnt[3], gsum[3]);
+        fprintf(stderr, "[maddy gpu profile] %zu launches, kernels busy %.3f ms, first-to-last span %.3f ms (idle %.3f ms)\n",
+                h->prof_events.size(), busy, (double)span, (double)span - busy);
+        for (auto &pr : h->prof_events) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+    }
     for (void *q : h->allocs) cudaFree(q);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->d_sched) cudaFree(h->d_sched);
@@ -241,6 +325,16 @@ extern "C" int maddy_destroy(maddy_handle *h)
         if (h->stage[k]) cudaFreeHost(h->stage[k]);
         if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]);
     }
+    for (void *q : {(void *)h->snap_pos, (void *)h->snap_ang, (void *)h->snap_r, (void *)h->snap_f, (void *)h->snap_en})
+        if (q) cudaFreeHost(q);
+    if (h->snap_done) cudaEventDestroy(h->snap_done);
+    if (h->snap_staged) cudaEventDestroy(h->snap_staged);
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
+    for (void *q : {(void *)h->d_snap_r, (void *)h->d_snap_f, (void *)h->d_snap_en, (void *)h->d_snap_status})
+        if (q) cudaFree(q);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MADDY_OK;
@@ -297,8 +391,8 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             CUK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
             h->own_stream = true;
         }
-        CUK(cudaMallocHost(&h->h_status, sizeof(int)));
-        *h->h_status = 0;
+        CUK(cudaMallocHost(&h->h_status, 2 * sizeof(int))); // [0] synchronous checks, [1] snapshot
+        h->h_status[0] = h->h_status[1] = 0;
 
         DevSys &a = h->a;
         memset(&a, 0, sizeof a);
@@ -559,11 +653,24 @@ static int energies_impl(maddy_handle *h, unsigned ops, double *out_per_traj, do
 extern "C" void *maddy_energies_device(maddy_handle *h) { return h ? (void *)h->a.en_traj : nullptr; }
 
 // ------------------------------------------------------------------ state transfer
+static void soa_to_aos_raw(const float4 *pos, const float4 *ang, size_t n, float *aos);
 extern "C" int maddy_download_coords(maddy_handle *h, float *aos)
 {
     if (!h || !aos) return MADDY_EINVAL;
     CU(h, cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->a.ntr * h->a.N;
+    if (!h->snap_what) { // through the pinned mirrors (a pageable destination halves the copy rate)
+        if (!h->snap_pos) {
+            CU(h, cudaMallocHost(&h->snap_pos, n * sizeof(float4)));
+            CU(h, cudaMallocHost(&h->snap_ang, n * sizeof(float4)));
+        }
+        CU(h, cudaMemcpyAsync(h->snap_pos, h->a.pos, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(h->snap_ang, h->a.ang, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+        int rc = sync_and_check(h);
+        if (rc) return rc;
+        soa_to_aos_raw(h->snap_pos, h->snap_ang, n, aos);
+        return MADDY_OK;
+    }
     std::vector<float4> pos(n), ang(n);
     CU(h, cudaMemcpyAsync(pos.data(), h->a.pos, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(ang.data(), h->a.ang, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
@@ -585,6 +692,122 @@ extern "C" int maddy_download_forces(maddy_handle *h, float *aos)
     soa_to_aos(pos, ang, aos);
     return MADDY_OK;
 }
+// ------------------------------------------------------------------ asynchronous stride snapshot
+extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
+{
+    if (!h || !(what & (MADDY_SNAP_COORDS | MADDY_SNAP_FORCES | MADDY_SNAP_ENERGIES))) return MADDY_EINVAL;
+    if (h->snap_what) return fail(h, MADDY_EINVAL, "maddy_snapshot_begin: the previous snapshot has not been collected");
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    if (!h->snap_done) CU(h, cudaEventCreateWithFlags(&h->snap_done, cudaEventDisableTiming));
+    if (what & MADDY_SNAP_ENERGIES) {
+        unsigned ops = OP_ENERGY;
+        if (what & MADDY_SNAP_REBUILD) ops |= (h->p.lj_on ? OP_REBUILD_LJ : 0u) | (h->p.is_assembly ? OP_REBUILD_BONDS : 0u);
+        int rc = launch(h, kargs(h, ops));
+        if (rc) return rc;
+        if (!h->snap_en) {
+            CU(h, cudaMallocHost(&h->snap_en, (size_t)h->a.ntr * 7 * sizeof(double)));
+            CU(h, cudaMalloc(&h->d_snap_en, (size_t)h->a.ntr * 7 * sizeof(double)));
+        }
+        CU(h, cudaMemcpyAsync(h->d_snap_en, h->a.en_traj, (size_t)h->a.ntr * 7 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    } else if (what & MADDY_SNAP_REBUILD) {
+        return fail(h, MADDY_EINVAL, "maddy_snapshot_begin: MADDY_SNAP_REBUILD needs MADDY_SNAP_ENERGIES");
+    }
+    cudaEvent_t c0 = nullptr, c1 = nullptr, c2 = nullptr;
+    if (h->gpu_prof) {
+        cudaEventCreate(&c0);
+        cudaEventCreate(&c1);
+        cudaEventCreate(&c2);
+        cudaEventRecord(c0, h->stream);
+    }
+    // state -> AoS-7 staging on the device (a few microseconds on the main stream), then the PCIe leg on a second
+    // stream so that the window queued next does not wait for it
+    const size_t aos_bytes = n * MADDY_COORD_STRIDE * sizeof(float);
+    if (!h->copy_stream) {
+        CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(h, cudaEventCreateWithFlags(&h->snap_staged, cudaEventDisableTiming));
+        CU(h, cudaMalloc(&h->d_snap_status, sizeof(int)));
+    }
+    if (what & MADDY_SNAP_COORDS) {
+        if (!h->snap_r) {
+            CU(h, cudaMallocHost(&h->snap_r, aos_bytes));
+            CU(h, cudaMalloc(&h->d_snap_r, aos_bytes));
+        }
+        cudaError_t e = launch_snapshot_kernel(h->a.pos, h->a.ang, h->d_snap_r, n, h->stream);
+        if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "snapshot kernel launch: %s", cudaGetErrorString(e));
+        h->launches++;
+    }
+    if (what & MADDY_SNAP_FORCES) {
+        if (!h->snap_f) {
+            CU(h, cudaMallocHost(&h->snap_f, aos_bytes));
+            CU(h, cudaMalloc(&h->d_snap_f, aos_bytes));
+        }
+        cudaError_t e = launch_snapshot_kernel(h->a.fpos, h->a.fang, h->d_snap_f, n, h->stream);
+        if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "snapshot kernel launch: %s", cudaGetErrorString(e));
+        h->launches++;
+    }
+    if (h->gpu_prof) cudaEventRecord(c1, h->stream);
+    CU(h, cudaMemcpyAsync(h->d_snap_status, h->a.status, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CU(h, cudaEventRecord(h->snap_staged, h->stream));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->snap_staged, 0));
+    if (what & MADDY_SNAP_COORDS) CU(h, cudaMemcpyAsync(h->snap_r, h->d_snap_r, aos_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (what & MADDY_SNAP_FORCES) CU(h, cudaMemcpyAsync(h->snap_f, h->d_snap_f, aos_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (what & MADDY_SNAP_ENERGIES)
+        CU(h, cudaMemcpyAsync(h->snap_en, h->d_snap_en, (size_t)h->a.ntr * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaMemcpyAsync(h->h_status + 1, h->d_snap_status, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaEventRecord(h->snap_done, h->copy_stream));
+    if (h->gpu_prof) {
+        cudaEventRecord(c2, h->stream);
+        h->prof_copy.push_back({c0, c1});
+        h->prof_copy.push_back({c1, c2});
+    }
+    h->snap_what = what;
+    return MADDY_OK;
+}
+
+static void host_copy(void *dst, const void *src, size_t bytes)
+{
+    const size_t chunk = 1 << 18, nchunk = (bytes + chunk - 1) / chunk;
+    HOST_PARALLEL_FOR(bytes)
+    for (size_t c = 0; c < nchunk; c++) {
+        const size_t o = c * chunk;
+        memcpy((char *)dst + o, (const char *)src + o, bytes - o < chunk ? bytes - o : chunk);
+    }
+}
+static void soa_to_aos_raw(const float4 *pos, const float4 *ang, size_t n, float *aos)
+{
+    HOST_PARALLEL_FOR(n)
+    for (size_t q = 0; q < n; q++) {
+        float *c = aos + q * MADDY_COORD_STRIDE;
+        c[0] = pos[q].x; c[1] = pos[q].y; c[2] = pos[q].z;
+        c[3] = ang[q].x; c[4] = ang[q].z; c[5] = ang[q].y;
+        c[6] = 0.f;
+    }
+}
+
+extern "C" int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *forces_aos7, double *energies_per_traj)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!h->snap_what) return fail(h, MADDY_EINVAL, "maddy_snapshot_end without maddy_snapshot_begin");
+    const unsigned what = h->snap_what;
+    h->snap_what = 0;
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaEventSynchronize(h->snap_done));
+    // the status word copied with the snapshot covers everything queued before it; later launches may already be
+    // running, so the device word is cleared by whoever synchronises the stream next (check_status)
+    if (h->h_status[1] & (ST_LJ_OVERFLOW | ST_LONG_OVERFLOW | ST_LAT_OVERFLOW)) {
+        const int st = h->h_status[1];
+        return fail(h, MADDY_EOVERFLOW, "neighbour list overflow:%s%s%s (capacities LJ %d, longitudinal %d, lateral %d)",
+                    (st & ST_LJ_OVERFLOW) ? " LJ" : "", (st & ST_LONG_OVERFLOW) ? " longitudinal" : "",
+                    (st & ST_LAT_OVERFLOW) ? " lateral" : "", MADDY_LJ_CAPACITY, h->a.capLong, h->a.capLat);
+    }
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    if ((what & MADDY_SNAP_COORDS) && coords_aos7) host_copy(coords_aos7, h->snap_r, n * MADDY_COORD_STRIDE * sizeof(float));
+    if ((what & MADDY_SNAP_FORCES) && forces_aos7) host_copy(forces_aos7, h->snap_f, n * MADDY_COORD_STRIDE * sizeof(float));
+    if ((what & MADDY_SNAP_ENERGIES) && energies_per_traj) memcpy(energies_per_traj, h->snap_en, (size_t)h->a.ntr * 7 * sizeof(double));
+    return MADDY_OK;
+}
+
 extern "C" int maddy_upload_coords(maddy_handle *h, const float *aos)
 {
     if (!h || !aos) return MADDY_EINVAL;
@@ -657,6 +880,7 @@ extern "C" int maddy_upload_gtp(maddy_handle *h, const int *gtp)
     uint8_t *v;
     int slot, rc = stage_acquire(h, &v, &slot);
     if (rc) return rc;
+    HOST_PARALLEL_FOR(n)
     for (size_t q = 0; q < n; q++) v[q] = (uint8_t)(gtp[q] == 1 ? 1 : (gtp[q] == 0 ? 0 : 2)); // kernels test == 1
     return stage_submit(h, h->a.gtp, slot);
 }
@@ -667,6 +891,7 @@ extern "C" int maddy_upload_on_tubule(maddy_handle *h, const int *on)
     uint8_t *v;
     int slot, rc = stage_acquire(h, &v, &slot);
     if (rc) return rc;
+    HOST_PARALLEL_FOR(n)
     for (size_t q = 0; q < n; q++) v[q] = on[q] != 0;
     return stage_submit(h, h->a.ontub, slot);
 }

@@ -1260,6 +1260,44 @@ cudaError_t launch_phase_kernel(const KArgs &k, int mpt, int threads, size_t sme
     }
 }
 
+// State read-back, device leg: float4 {x,y,z,-} + {fi,psi,theta,-} -> the boundary's AoS-7 record {x,y,z,fi,theta,psi,0}
+// (mt.h:63-71) in a device staging buffer; the PCIe leg is a plain copy on a second stream (maddy_snapshot_begin), so the
+// host receives the layout it hands to the DCD writer and does no transposition of its own.
+__global__ void __launch_bounds__(256) snapshot_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ ang, float *__restrict__ out,
+                                                       size_t n_monomers)
+{
+    // 256 monomers per tile: coalesced float4 loads -> AoS-7 in shared memory -> contiguous float4 stores
+    // (a tile is 256 * 28 B = 7168 B, a multiple of 16, so every tile starts 16-byte aligned)
+    __shared__ __align__(16) float tile[256 * 7];
+    const size_t ntiles = (n_monomers + 255) / 256;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t q = t * 256 + threadIdx.x;
+        if (q < n_monomers) {
+            const float4 p = __ldg(pos + q), a = __ldg(ang + q);
+            float *r = tile + threadIdx.x * 7;
+            r[0] = p.x; r[1] = p.y; r[2] = p.z;
+            r[3] = a.x; r[4] = a.z; r[5] = a.y; // fi, theta, psi
+            r[6] = 0.f;
+        }
+        __syncthreads();
+        const size_t left = n_monomers - t * 256;
+        const int nfl = (int)(left < 256 ? left : 256) * 7;
+        float *dst = out + t * 256 * 7;
+        const int n4 = nfl / 4;
+        for (int g = threadIdx.x; g < n4; g += 256) reinterpret_cast<float4 *>(dst)[g] = reinterpret_cast<const float4 *>(tile)[g];
+        if ((int)threadIdx.x < (nfl & 3)) dst[4 * n4 + threadIdx.x] = tile[4 * n4 + threadIdx.x];
+        __syncthreads();
+    }
+}
+cudaError_t launch_snapshot_kernel(const float4 *pos, const float4 *ang, float *out_mapped, size_t n_monomers, cudaStream_t st)
+{
+    int blocks = (int)((n_monomers + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    snapshot_kernel<<<blocks, 256, 0, st>>>(pos, ang, out_mapped, n_monomers);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st)
 {
     const size_t n = (size_t)k.a.ntr * k.a.N;

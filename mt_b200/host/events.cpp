@@ -14,12 +14,28 @@
 #include <cstring>
 #include <ctime>
 #include <map>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "mt_host.hpp"
 
 namespace mt {
 
 static const float R_MT = 8.12f, R_MON = 2.0f, ANG_THRES = 1.0f, R_THRES = R_MON * 8;
 static const int PF_NUMBER = 13;
+
+static int host_threads()
+{
+#ifdef _OPENMP
+    static const int k = [] {
+        int m = omp_get_max_threads();
+        return m > 8 ? 8 : (m < 1 ? 1 : m);
+    }();
+    return k;
+#else
+    return 1;
+#endif
+}
 
 // ---------------------------------------------------------------- timers (timer.cpp)
 void init_timer(System &s) { s.initial_clock = s.last_clock = (long)clock(); }
@@ -117,21 +133,37 @@ void mt_length(System &s, long long step, std::vector<int> &mt_len)
         FILE *first = fopen("mt_len.dat", "w");
         if (first) fclose(first);
     }
-    for (int t = 0; t < s.par.n_tr; t++) {
+    // Same predicate as the reference, `rad < r_mt + r_thres && rad > 1 && cosf(theta) > cosf(ang_thres)`; the libm
+    // calls are only made where their rounding could matter (cos is even and monotone on [0, pi], sqrt is monotone), so
+    // the classification is bit-identical at a fraction of the cost.  Trajectories are independent: split over threads.
+    const float cos_thr = cosf(ANG_THRES), rad_hi = R_MT + R_THRES;
+    const int Ntr = s.par.n_tr;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if ((size_t)N * Ntr > 65536)
+    for (int t = 0; t < Ntr; t++) {
         int sum = 0;
-        for (int i = t * N; i < (t + 1) * N; i++) {
-            const float *c = &s.r[(size_t)i * 7];
-            float rad = sqrt(c[0] * c[0] + c[1] * c[1]);
-            if ((rad < R_MT + R_THRES) && (rad > 1.0) && (cosf(c[4]) > cosf(ANG_THRES))) {
-                sum++;
-                s.on_tubule_cur[i] = 1;
-            } else {
-                s.on_tubule_cur[i] = 0;
+        for (size_t i = (size_t)t * N; i < (size_t)(t + 1) * N; i++) {
+            const float *c = &s.r[i * 7];
+            const float r2 = c[0] * c[0] + c[1] * c[1];
+            bool in_r;
+            if (r2 > 1.1f && r2 < 0.99f * rad_hi * rad_hi) in_r = true;
+            else {
+                float rad = sqrt(r2);
+                in_r = (rad < rad_hi) && (rad > 1.0);
             }
+            bool on = false;
+            if (in_r) {
+                const float a = fabsf(c[4]);
+                if (a < ANG_THRES - 0.01f) on = true;
+                else if (a > ANG_THRES + 0.01f && a < 6.2f - ANG_THRES) on = false;
+                else on = cosf(c[4]) > cos_thr;
+            }
+            s.on_tubule_cur[i] = on ? 1 : 0;
+            sum += on;
         }
         mt_len[t] = sum;
-        if (!s.quiet) printf("tubule[%d]: %d\n", t, sum);
     }
+    if (!s.quiet)
+        for (int t = 0; t < Ntr; t++) printf("tubule[%d]: %d\n", t, mt_len[t]);
     if (s.write_files) {
         FILE *f = fopen("mt_len.dat", "a");
         if (f) {
@@ -196,6 +228,17 @@ int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len)
     return flag;
 }
 
+static void event_message(System &s, const char *fmt, int a, int b)
+{
+    if (!s.event_log) {
+        printf(fmt, a, b);
+        return;
+    }
+    char buf[128];
+    snprintf(buf, sizeof buf, fmt, a, b);
+    *s.event_log += buf;
+}
+
 // ---------------------------------------------------------------- hydrolysis (updater.cpp:229-257)
 void hydrolyse(System &s)
 {
@@ -220,7 +263,7 @@ void hydrolyse(System &s)
                 const size_t q = 2 * d + (size_t)tr * N;
                 s.gtp[q] = 0;
                 s.gtp[q + 1] = 0;
-                if (!s.quiet) printf("*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", d, tr);
+                if (!s.quiet) event_message(s, "*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", d, tr);
             }
         }
     // GDP dimers that are off the tubule now and at the previous stride return to GTP (no draw)
@@ -239,7 +282,7 @@ void hydrolyse(System &s)
                 if (s.gtp[q] == 0 && !s.extra[q] && s.on_tubule_cur[q] == 0 && s.on_tubule_prev[q] == 0) {
                     s.gtp[q] = 1;
                     s.gtp[q + 1] = 1;
-                    printf("*** Transition to GTP occured to dimer # %d trajectory #%d ***\n", i / 2, tr);
+                    event_message(s, "*** Transition to GTP occured to dimer # %d trajectory #%d ***\n", i / 2, tr);
                 }
             }
     }
@@ -290,6 +333,11 @@ struct Prof {
 void compute(System &s, bool fused, ComputeStats *stats)
 {
     Prof prof;
+    const bool trace = getenv("MADDY_HOST_TRACE") != nullptr; // wall-clock marks of the first strides on stderr
+    const double trace_t0 = Prof::now();
+    auto mark = [&](const char *what, long long at) {
+        if (trace && at <= 3 * s.hp.stride) fprintf(stderr, "[trace] %9.3f ms  step %lld  %s\n", (Prof::now() - trace_t0) * 1e3, at, what);
+    };
     prof.begin();
     const maddy_params &par = s.par;
     const HostParams &hp = s.hp;
@@ -349,6 +397,20 @@ void compute(System &s, bool fused, ComputeStats *stats)
     //    rebuild is folded into the fused window launch;
     //  * hydrolyse() reads only host flags from the previous stride, so the draw for the NEXT event step is made
     //    while the GPU runs the current window (same rand() order: it follows every event of the current step).
+    // Overlapped stride read-back: possible whenever the host results of a stride (on-tubule flags, insertion) cannot
+    // change the forces of the following steps.
+    const bool flags_matter = par.barrier && (par.a_barr_long != 0.f || par.a_barr_lat != 0.f);
+    const bool overlap_stride = fused && !par.tea_on && !hp.is_const_conc && !hp.out_force && !flags_matter && !getenv("MADDY_NO_OVERLAP");
+    int pending_output = 0; // an overlapped stride whose update() is still to be written
+    long long pending_step = 0;
+    std::string pending_log;
+    auto flush_pending = [&] {
+        update(s, pending_step, mt_len);
+        s.gtp_for_output.reset();
+        if (!pending_log.empty()) fputs(pending_log.c_str(), stdout);
+        pending_log.clear();
+        pending_output = 0;
+    };
     long long step = 0;
     long long hydrolysed_for = -1; // event step whose hydrolysis has already been evaluated on the host
     while (step < hp.steps) {
@@ -372,6 +434,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
             if (hydrolysed_for != step) hydrolyse(s);
             for_each([&](Shard &d) { ck(maddy_upload_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_upload_gtp"); });
             st.h2d_bytes += (double)n;
+            mark("gtp uploaded", step);
         }
         prof.end("upload gtp");
         prof.begin();
@@ -379,7 +442,14 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // and insertion uploads) happens here; the output part (update(): stdout, DCD frames) is deferred until the next
         // window has been queued, so the GPU does not wait for host formatting.
         int deferred_output = 0;
-        if (stride_now) {
+        const bool overlapped = stride_now && overlap_stride;
+        if (overlapped) {
+            // Nothing the host derives from this snapshot feeds back into the forces (no insertion, barrier amplitudes
+            // zero), so the read-back is only QUEUED here; it is collected after the next window has been launched.
+            const unsigned what = MADDY_SNAP_COORDS | (hp.out_energy ? MADDY_SNAP_ENERGIES : 0u) | (fused_stride_energy ? MADDY_SNAP_REBUILD : 0u);
+            for_each([&](Shard &d) { ck(maddy_snapshot_begin(d.h, what), d.h, "maddy_snapshot_begin"); });
+            st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0);
+        } else if (stride_now) {
             if (hp.out_energy) {
                 for_each([&](Shard &d) {
                     double *out = &s.energies[(size_t)d.first * 7];
@@ -453,24 +523,75 @@ void compute(System &s, bool fused, ComputeStats *stats)
             }
         } else {
             for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, explicit_rebuild ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u), d.h, "maddy_run"); });
+            mark("window launched", step);
         }
         prof.end("launch window");
         prof.begin();
+        // Output of the PREVIOUS overlapped stride (it reads s.r / s.energies, which the collect below overwrites): by now
+        // the window after that stride and this one are both queued.
+        if (pending_output) {
+            flush_pending();
+            mark("pending output flushed", step);
+        }
+        prof.end("stride output");
+        prof.begin();
+        if (overlapped) {
+            for_each([&](Shard &d) {
+                ck(maddy_snapshot_end(d.h, &s.r[(size_t)d.first * N * 7], nullptr, hp.out_energy ? &s.energies[(size_t)d.first * 7] : nullptr),
+                   d.h, "maddy_snapshot_end");
+            });
+            prof.end("stride collect (wait + transpose)");
+            mark("snapshot collected", step);
+            prof.begin();
+            if (hp.tub_length) {
+                s.on_tubule_prev = s.on_tubule_cur;
+                if (step != 0) {
+                    mt_len_prev = mt_len;
+                    mt_length(s, step, mt_len);
+                    if (par.barrier) { // keeps the device copy current (it cannot change a force: both amplitudes are zero)
+                        for_each([&](Shard &d) {
+                            ck(maddy_upload_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N]), d.h, "maddy_upload_on_tubule");
+                        });
+                        st.h2d_bytes += (double)n;
+                    }
+                    deferred_output = 1;
+                } else {
+                    deferred_output = 2;
+                }
+            } else {
+                deferred_output = 1;
+            }
+        }
+        prof.end("stride collect");
+        prof.begin();
         if (deferred_output) {
-            update(s, step, mt_len);
-            if (deferred_output == 2) mt_length(s, step, mt_len);
+            if (overlapped && deferred_output == 1) {
+                // The next hydrolysis event only needs the flags just classified; evaluate it and queue its window
+                // BEFORE the stride's own output is formatted.  Messages are held back so stdout keeps the reference's
+                // order, and the GTP state the output refers to is kept aside.
+                pending_output = 1;
+                pending_step = step;
+                if (s.write_files && hp.hydrolysis && step % (hp.stride * 10) == 0) s.gtp_for_output = std::make_shared<std::vector<int>>(s.gtp);
+            } else {
+                update(s, step, mt_len);
+                if (deferred_output == 2) mt_length(s, step, mt_len);
+            }
         }
         prof.end("stride output");
         prof.begin();
         // overlap with the asynchronous window: evaluate the hydrolysis event AT the window end on the host now
         if (hydro && next < hp.steps && next % hp.hydrostep == 0 && next != 0) {
+            if (pending_output) s.event_log = &pending_log;
             hydrolyse(s);
+            s.event_log = nullptr;
             hydrolysed_for = next;
+            mark("next hydrolysis evaluated", step);
         }
         prof.end("hydrolyse (host)");
         step = next;
         st.steps += count;
     }
+    if (pending_output) flush_pending();
     prof.begin();
     if (s.writer) {
         s.writer->drain();

@@ -108,7 +108,7 @@ class OutputWorker {
   public:
     OutputWorker();
     ~OutputWorker();
-    void submit(std::function<void()> job); // blocks while two jobs are already pending
+    void submit(std::function<void()> job); // blocks while 16 jobs are already pending
     void drain();                           // waits for all jobs; rethrows the first failure
   private:
     void loop();
@@ -174,6 +174,9 @@ struct System {
     std::vector<int> mon_type, gtp, on_tubule_cur, on_tubule_prev;
     std::vector<double> energies; // [Ntr][7] per-trajectory sums of the last energy evaluation
     bool quiet = false;           // suppress the reference's stdout chatter (tests / bench)
+    std::string *event_log = nullptr; // when set, hydrolyse() appends its messages here instead of printing them (the
+                                      // step loop evaluates events ahead of time and prints them in the reference's order)
+    std::shared_ptr<std::vector<int>> gtp_for_output; // GTP state as of the pending stride output (see compute())
     bool write_files = true;      // DCD / mt_len.dat / hydrolysis.pdb side effects
     std::string workdir;          // relative output paths are taken relative to the cwd, like the reference
     // timers (timer.cpp)

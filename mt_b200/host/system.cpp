@@ -386,7 +386,7 @@ void OutputWorker::loop()
 void OutputWorker::submit(std::function<void()> job)
 {
     std::unique_lock<std::mutex> g(m_);
-    cv_.wait(g, [this] { return q_.size() < 2; });
+    cv_.wait(g, [this] { return q_.size() < 16; });
     q_.push_back(std::move(job));
     cv_.notify_all();
 }
@@ -512,12 +512,12 @@ void append_coord_pdb(System &s)
     const int N = s.par.n_tot, Ntr = s.par.n_tr;
     if (s.writer) {
         auto r = std::make_shared<std::vector<float>>(s.r);
-        auto g = std::make_shared<std::vector<int>>(s.gtp);
+        auto g = s.gtp_for_output ? s.gtp_for_output : std::make_shared<std::vector<int>>(s.gtp);
         const PDB *tmpl = &s.pdb;
         const bool quiet = s.quiet;
         s.writer->submit([r, g, tmpl, N, Ntr, quiet] { write_hydrolysis_pdb(*tmpl, *r, *g, N, Ntr, quiet); });
     } else {
-        write_hydrolysis_pdb(s.pdb, s.r, s.gtp, N, Ntr, s.quiet);
+        write_hydrolysis_pdb(s.pdb, s.r, s.gtp_for_output ? *s.gtp_for_output : s.gtp, N, Ntr, s.quiet);
     }
 }
 

@@ -436,3 +436,44 @@ def test_drop_in_const_conc_vs_reference_executable(rundir):
             b = mt_b200.read_dcd(d_ref / "dcd" / f"run_{t}{suffix}")
             assert a.shape == b.shape and a.shape[0] == 3
             assert np.abs(a - b).max() < tol, (t, suffix, np.abs(a - b).max())
+
+
+def test_async_snapshot_equals_synchronous_readback(rundir, load_system):
+    """maddy_snapshot_begin/_end: the state queued BEFORE the next window is what arrives, whatever runs in between."""
+    s = load_system(rundir("mt40_ensemble", runnum=6), ["hydrolysis=no"])
+    a, b = Engine(s), Engine(s)
+    a.run(0, 40)
+    b.run(0, 40)
+    ref_e = a.rebuild_and_energies()
+    ref_c = a.coords()
+    a.run(40, 60, skip_first_rebuild=True)
+    b.snapshot_begin(coords=True, energies=True, rebuild=True)
+    b.run(40, 60, skip_first_rebuild=True)  # overlaps with the read-back
+    snap = b.snapshot_end()
+    assert np.array_equal(snap["coords"], ref_c) and np.array_equal(snap["energies"], ref_e)
+    assert np.array_equal(a.coords(), b.coords())
+    from mt_b200 import MaddyError
+    with pytest.raises(MaddyError):
+        b.snapshot_end()  # nothing in flight
+
+
+def test_overlapped_stride_loop_equals_serial_loop(rundir, monkeypatch):
+    """compute(): read-back collected behind the next window (default) == the reference's serial stride block."""
+    import mt_b200
+    from mt_b200 import HostSystem, workspace
+    out = {}
+    for mode in ("overlap", "serial"):
+        d = rundir("mt40_ensemble", runnum=3, steps=700, stride=200)
+        if mode == "serial":
+            monkeypatch.setenv("MADDY_NO_OVERLAP", "1")
+        with workspace.chdir(d):
+            s = HostSystem("config.conf", [], write_files=True)
+            s.srand(s.par.rseed)
+            s.compute()
+            out[mode] = (np.array(s.coords).copy(), np.array(s.energies).copy(), np.array(s.gtp).copy(), np.array(s.on_tubule_cur).copy(),
+                         [mt_b200.read_dcd(d / "dcd" / f"run_{t}.dcd") for t in range(3)], (d / "mt_len.dat").read_text())
+            s.close()
+    monkeypatch.delenv("MADDY_NO_OVERLAP")
+    a, b = out["overlap"], out["serial"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert all(np.array_equal(x, y) and x.shape[0] == 4 for x, y in zip(a[4], b[4])) and a[5] == b[5]
