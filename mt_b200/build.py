@@ -76,7 +76,7 @@ def build_kernels(force=False, verbose_ptxas=False):
 
 
 def build_host(force=False):
-    srcs = [HOST / "io.cpp", HOST / "system.cpp", HOST / "events.cpp", HOST / "host_capi.cpp"]
+    srcs = [HOST / "io.cpp", HOST / "system.cpp", HOST / "events.cpp", HOST / "checkpoint.cpp", HOST / "host_capi.cpp"]
     deps = srcs + [HOST / "mt_host.hpp", HOST / "main.cpp", ROOT / "include" / "maddy_host.h", ROOT / "include" / "maddy_b200.h"]
     build_kernels(force)
     if force or _stale(LIB_HOST, deps + [LIB_KERNELS]):

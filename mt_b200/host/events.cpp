@@ -348,12 +348,15 @@ void compute(System &s, bool fused, ComputeStats *stats)
     // initIntegration: forces zeroed; the angle wrap happens inside maddy_create on the device copy
     // AND on the host copy (compute_cuda.cu:995-1010 modifies r in place)
     std::fill(s.f.begin(), s.f.end(), 0.f);
-    for (size_t q = 0; q < n; q++) {
-        float *c = &s.r[q * 7];
-        c[3] -= (2 * M_PI) * (int)(c[3] / (2 * M_PI));
-        c[5] -= (2 * M_PI) * (int)(c[5] / (2 * M_PI));
-        c[4] -= (2 * M_PI) * (int)(c[4] / (2 * M_PI));
-    }
+    CheckpointState resume_state;
+    if (hp.resume) checkpoint_load(s, hp.checkpoint, resume_state); // coordinates, flags, host rand(): exactly as they stood
+    else
+        for (size_t q = 0; q < n; q++) {
+            float *c = &s.r[q * 7];
+            c[3] -= (2 * M_PI) * (int)(c[3] / (2 * M_PI));
+            c[5] -= (2 * M_PI) * (int)(c[5] / (2 * M_PI));
+            c[4] -= (2 * M_PI) * (int)(c[4] / (2 * M_PI));
+        }
 
     // contiguous trajectory blocks per GPU
     int G = hp.n_gpus < 1 ? 1 : hp.n_gpus;
@@ -372,6 +375,14 @@ void compute(System &s, bool fused, ComputeStats *stats)
         int rc = maddy_create(&p, &top, &s.r[(size_t)d.first * N * 7], nullptr, &d.h);
         if (rc != MADDY_OK) die("maddy_create failed (%d): %s", rc, maddy_last_error(nullptr));
         st.h2d_bytes += (double)d.count * N * (7 * 4 + 32 + 3);
+        if (hp.resume) { // raw coordinate bits (maddy_create re-wraps angles) and the RNG streams of this shard
+            const size_t cnt = (size_t)d.count * N, off = (size_t)d.first * N;
+            std::vector<unsigned> rs(cnt * 8);
+            memcpy(rs.data(), &resume_state.rng[off * 4], cnt * 16);
+            memcpy(rs.data() + cnt * 4, &resume_state.rng[(n + off) * 4], cnt * 16);
+            ck(maddy_upload_coords(d.h, &s.r[off * 7]), d.h, "maddy_upload_coords");
+            ck(maddy_upload_rng(d.h, rs.data()), d.h, "maddy_upload_rng");
+        }
     }
     prof.end("create");
     if (!s.quiet) printf("Using %d device(s), first device %d\n", G, par.device);
@@ -413,7 +424,36 @@ void compute(System &s, bool fused, ComputeStats *stats)
     };
     long long step = 0;
     long long hydrolysed_for = -1; // event step whose hydrolysis has already been evaluated on the host
+    if (hp.resume) {
+        step = resume_state.step;
+        hydrolysed_for = resume_state.hydrolysed_for;
+        mt_len = resume_state.mt_len;
+        mt_len_prev = resume_state.mt_len_prev;
+    }
+    const long long start_step = step;
+    // checkpoint = the state at the TOP of step `at`, before any of that step's events
+    auto write_checkpoint = [&](long long at) {
+        if (pending_output) flush_pending();
+        CheckpointState out;
+        out.step = at;
+        out.hydrolysed_for = hydrolysed_for;
+        out.mt_len = mt_len;
+        out.mt_len_prev = mt_len_prev;
+        out.coords.resize(n * 7);
+        out.rng.resize(n * 8);
+        for_each([&](Shard &d) {
+            const size_t cnt = (size_t)d.count * N, off = (size_t)d.first * N;
+            std::vector<unsigned> rs(cnt * 8);
+            ck(maddy_download_coords(d.h, &out.coords[off * 7]), d.h, "maddy_download_coords");
+            ck(maddy_download_rng(d.h, rs.data()), d.h, "maddy_download_rng");
+            memcpy(&out.rng[off * 4], rs.data(), cnt * 16);
+            memcpy(&out.rng[(n + off) * 4], rs.data() + cnt * 4, cnt * 16);
+        });
+        if (s.writer) s.writer->drain(); // the frames up to here are on disk before the checkpoint says so
+        checkpoint_save(s, hp.checkpoint, out);
+    };
     while (step < hp.steps) {
+        if (!hp.checkpoint.empty() && hp.checkpoint_freq > 0 && step != start_step && step % hp.checkpoint_freq == 0) write_checkpoint(step);
         const bool rebuild_now = step % par.ljpairsupdatefreq == 0;
         const bool stride_now = step % hp.stride == 0;
         const bool may_teleport = stride_now && hp.tub_length && step != 0 && hp.is_const_conc;
@@ -592,6 +632,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         st.steps += count;
     }
     if (pending_output) flush_pending();
+    if (!hp.checkpoint.empty() && hp.steps > start_step) write_checkpoint(hp.steps);
     prof.begin();
     if (s.writer) {
         s.writer->drain();

@@ -100,6 +100,11 @@ struct HostParams { // scalars of `Parameters` that only the host uses
     std::string coord_xyz, coord_ang, ff_file, cond_file, restartkey;
     std::vector<std::string> dcd_xyz, dcd_ang, restart_xyz, restart_ang;
     int n_gpus = 1; // extension key `n_gpus` (default 1): shard trajectories over this many devices
+    // extension keys `checkpoint <file>` / `checkpoint_freq <steps>`: exact checkpoints (checkpoint.cpp); with
+    // `is_restart yes` and an existing checkpoint file the run resumes from it instead of the XYZ restart files
+    std::string checkpoint;
+    long long checkpoint_freq = 0;
+    bool resume = false;
 };
 
 // In-order background writer for trajectory output: the step loop hands over a snapshot of
@@ -149,6 +154,20 @@ class HostRand {
         if (++f_ >= 31) f_ = 0;
         if (++b_ >= 31) b_ = 0;
         return (int)(v >> 1);
+    }
+
+    // full generator state, for checkpoints: 31 words + the two cursors
+    void get_state(int32_t out[33]) const
+    {
+        for (int i = 0; i < 31; i++) out[i] = r_[i];
+        out[31] = f_;
+        out[32] = b_;
+    }
+    void set_state(const int32_t in[33])
+    {
+        for (int i = 0; i < 31; i++) r_[i] = in[i];
+        f_ = in[31] % 31;
+        b_ = in[32] % 31;
     }
 
   private:
@@ -203,6 +222,18 @@ void output_sum_force(System &s);
 void output_forces(System &s);
 void update(System &s, long long step, std::vector<int> &mt_len);
 void init_timer(System &s);
+
+// exact checkpoint / restart (checkpoint.cpp)
+struct CheckpointState {
+    long long step = 0, hydrolysed_for = -1;
+    std::vector<float> coords;  // [Ntr*Ntot][7], device state at `step`
+    std::vector<uint32_t> rng;  // [Ntr*Ntot][8]: xyz stream, angular stream per monomer
+    std::vector<int> mt_len, mt_len_prev;
+};
+bool checkpoint_peek(const std::string &name, long long *step);
+void checkpoint_save(System &s, const std::string &name, const CheckpointState &st);
+void checkpoint_load(System &s, const std::string &name, CheckpointState &st);
+void checkpoint_trim_outputs(System &s, long long step);
 
 // the step loop: compute() of compute_cuda.cu:1125-1260 over the C-ABI.
 // fused = false uses one C-ABI call per reference launch (force; integrate) — same results.

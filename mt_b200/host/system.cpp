@@ -217,7 +217,18 @@ void init_parameters(System &s, const std::string &config, const std::vector<std
     hp.n_gpus = tb.integer("n_gpus", 1); // extension of this host, absent in the reference
     hp.restartkey = tb.masked("restartkey");
     hp.is_restart = tb.yesno("is_restart", 0);
-    if (!hp.is_restart) hp.firststep = tb.long_integer("firststep", 0);
+    // extension keys, absent in the reference: exact checkpoints (checkpoint.cpp)
+    hp.checkpoint = tb.masked("checkpoint", "");
+    hp.checkpoint_freq = tb.long_integer("checkpoint_freq", 0);
+    long long resume_step = 0;
+    hp.resume = hp.is_restart && !hp.checkpoint.empty() && checkpoint_peek(hp.checkpoint, &resume_step);
+    if (!hp.checkpoint.empty()) {
+        if (hp.steps % par.ljpairsupdatefreq != 0)
+            die("checkpoint: steps (%lld) must be a multiple of LJPairsUpdateFreq (%d)", hp.steps, par.ljpairsupdatefreq);
+        if (hp.checkpoint_freq < 0 || hp.checkpoint_freq % par.ljpairsupdatefreq != 0 || hp.checkpoint_freq % hp.stride != 0)
+            die("checkpoint_freq (%lld) must be a multiple of stride and of LJPairsUpdateFreq", hp.checkpoint_freq);
+    }
+    if (!hp.is_restart || hp.resume) hp.firststep = hp.resume ? resume_step : tb.long_integer("firststep", 0);
     else {
         FILE *k = fopen(hp.restartkey.c_str(), "r");
         if (!k) die("Opening file '%s'", hp.restartkey.c_str());
@@ -241,7 +252,7 @@ void init_parameters(System &s, const std::string &config, const std::vector<std
         const std::string run = std::to_string(t);
         hp.dcd_ang[t] = tb.masked_replace("dcd_ang", run, "<run>");
         hp.dcd_xyz[t] = tb.masked_replace("dcd_xyz", run, "<run>");
-        if (s.write_files) {
+        if (s.write_files && !hp.resume) {
             for (const std::string *name : {&hp.dcd_xyz[t], &hp.dcd_ang[t]}) {
                 FILE *f = fopen(name->c_str(), "w");
                 if (!f) die("Opening file '%s'", name->c_str());
@@ -252,7 +263,8 @@ void init_parameters(System &s, const std::string &config, const std::vector<std
         hp.restart_xyz[t] = tb.masked_replace("restart_xyz", run, "<run>");
         hp.restart_ang[t] = tb.masked_replace("restart_ang", run, "<run>");
     }
-    if (hp.is_restart) read_restart(s);
+    if (hp.is_restart && !hp.resume) read_restart(s);
+    if (hp.resume && s.write_files) checkpoint_trim_outputs(s, resume_step);
 
     // ---- force field
     tb.parse(hp.ff_file, overrides);

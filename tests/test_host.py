@@ -140,3 +140,17 @@ def test_pdb_writer_matches_printf_formatting(tmp_path):
         assert xyz[i] == head + "%8.3f%8.3f%8.3f%6.2f%6.2f" % (x, y, z, 0.0, 8.12)
         assert ang[i] == head + "%8.3f%8.3f%8.3f%6.2f%6.2f" % (fi, psi, theta, 0.0, 8.12)
     s.close()
+
+
+def test_checkpoint_keys_are_validated(rundir, load_system):
+    from mt_b200 import MaddyError
+    d = rundir("mt40_single", runnum=1, steps=100, stride=50)
+    with pytest.raises(MaddyError, match="multiple of LJPairsUpdateFreq"):
+        load_system(d, ["checkpoint=ck.bin", "steps=110"])
+    with pytest.raises(MaddyError, match="checkpoint_freq"):
+        load_system(d, ["checkpoint=ck.bin", "checkpoint_freq=30"])
+    s = load_system(d, ["checkpoint=ck.bin", "checkpoint_freq=100", "is_restart=no"])
+    assert s.host.steps == 100
+    # is_restart with a checkpoint key but no checkpoint file falls back to the reference's XYZ restart (which needs its key file)
+    with pytest.raises(MaddyError, match="restart/key.txt"):
+        load_system(d, ["checkpoint=missing.bin", "is_restart=yes"])
