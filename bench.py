@@ -45,8 +45,8 @@ UNIT = "monomer-steps/s"
 B_ALG = 352.0  # algorithmic bytes per monomer-step, intact lattice (BASELINE.md 3 / SURVEY.md 8d)
 B_ALG_TERMS = "64 state r/w + 64 RNG r/w + 4*(46+1) LJ list + 4*(4+3) bond lists + 8 flags"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (a 100-step fused window at 520 x 256) from the
-# `ncu --set full` capture summarised in profiles/r1_traj_kernel_ncu_full.txt (37.5 MB read + 5.3 MB written)
-NCU_TRAFFIC_PER_LAUNCH = {("mt40_ensemble", 256, 100): 42.8e6}
+# `ncu --set full` capture summarised in profiles/r1_run_kernel_ncu_full.txt (35.6 MB read + 3.0 MB written)
+NCU_TRAFFIC_PER_LAUNCH = {("mt40_ensemble", 256, 100): 38.6e6}
 REF_NTR_LIMIT = 100
 
 
@@ -219,7 +219,7 @@ def run_own(args):
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         e2e = {"value": N * ntr_global * args.steps / float(tw.item()), "unit": UNIT,
                "h2d_bytes_per_step": st["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st["d2h_bytes"] / args.steps,
-               "call": "mt_system_compute (drop-in compute(): create + upload, fused windows, hydrolysis uploads, stride downloads, DCD output)",
+               "call": "mt_system_compute (drop-in compute(): create + upload, fused windows, hydrolysis uploads, asynchronous stride read-back, DCD output)",
                "wall_s": float(tw.item()), "wall_s_runs": [round(w, 4) for w in walls], "statistic": "median of 3 runs"}
 
         if rank == 0:
@@ -237,9 +237,9 @@ def run_own(args):
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_PER_LAUNCH.get((args.workload, ntr_local, window)),
-                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_traj_kernel_ncu_full.txt)",
+                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_run_kernel_ncu_full.txt)",
                              "algorithmic_bytes_per_launch": B_ALG * N * ntr_local * window, "peak_source": pk_src,
-                             "kernel": "maddy::traj_kernel<1,576,2> (one fused window of `window_steps` MD steps per launch)",
+                             "kernel": "maddy::run_kernel<1,2> (one fused window of `window_steps` MD steps per launch; 94.7 % of the kernel time of a step in the ncu launch list, profiles/r1_launches.csv)",
                              "algorithmic_bytes_per_monomer_step": B_ALG, "terms": B_ALG_TERMS,
                              "note": "state stays on-chip across the fused steps, so DRAM traffic is far below the algorithmic bytes; "
                                      "the binding limit is SM issue/latency (see profiles/)"},
