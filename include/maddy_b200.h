@@ -204,6 +204,11 @@ int maddy_upload_list(maddy_handle *h, int kind, const int *counts, const int *e
 int maddy_download_rng(maddy_handle *h, unsigned *state);
 int maddy_upload_rng(maddy_handle *h, const unsigned *state);
 
+/* list-maintenance statistics of the fused loop since creation / the last reset, summed over the shard's trajectories:
+ * out[0] near-list refreshes forced by the displacement guard, out[1] candidate-list re-scans, out[2] rebuilds that fell
+ * back to the all-pairs path, out[3] near-list overflows.  (The lists themselves are exact on every path.) */
+int maddy_list_stats(maddy_handle *h, unsigned long long out[4], int reset);
+
 /* ---- host-side pieces of the path that need no GPU (usable without a device) */
 /* generateSeeds (HybridTaus.cu:32-48) on a FRESH ran2 state: fills seeds[np*4]. */
 void maddy_generate_seeds(unsigned *seeds, int rseed, long long np);

@@ -258,6 +258,11 @@ class Engine:
         self._ck(capi.lib.maddy_rebuild_and_energies(self._h, as_ptr(out, C.c_double), None))
         return out
 
+    def list_stats(self, reset: bool = False) -> dict:
+        out = (C.c_ulonglong * 4)()
+        self._ck(capi.lib.maddy_list_stats(self._h, out, int(reset)))
+        return {"near_refresh": out[0], "candidate_rescan": out[1], "all_pairs_fallback": out[2], "near_overflow": out[3]}
+
     def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False):
         """queue the stride read-back (maddy_snapshot_begin); work queued afterwards overlaps with snapshot_end()"""
         what = (capi.SNAP_COORDS if coords else 0) | (capi.SNAP_FORCES if forces else 0) | (capi.SNAP_ENERGIES if energies else 0) \

@@ -271,6 +271,16 @@ extern "C" const char *maddy_last_error(const maddy_handle *h) { return h ? h->e
 extern "C" void *maddy_stream(const maddy_handle *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" long long maddy_launch_count(const maddy_handle *h) { return h ? h->launches : 0; }
 
+extern "C" int maddy_list_stats(maddy_handle *h, unsigned long long out[4], int reset)
+{
+    if (!h || !out) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaMemcpyAsync(out, h->a.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CU(h, cudaMemsetAsync(h->a.stats, 0, 4 * sizeof(unsigned long long), h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+
 extern "C" int maddy_sync(maddy_handle *h)
 {
     if (!h) return MADDY_EINVAL;
@@ -422,6 +432,10 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             const size_t fixed = (size_t)nbuf * 64 * N + tiles + N + 80 + extra;
             if (fixed + (size_t)12 * 2 * N > budget) return 0; // too little room: all-pairs path, lists from HBM only
             size_t cap = (budget - fixed) / ((size_t)2 * N);
+            if (const char *e = getenv("MADDY_NEAR_CAP")) { // test hook: a tiny cache makes crowded-monomer overflows common
+                const size_t want = (size_t)atoi(e);
+                if (want >= 1 && want < cap) cap = want;
+            }
             return (int)(cap > 32 ? 32 : cap);
         };
         // (1) phase kernel (step-granular entry points): every monomer owns a thread, one stage buffer
@@ -504,6 +518,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         pool_req(&a.en_mono, n * 7);
         pool_req(&a.en_traj, (size_t)ntr * 7);
         pool_req(&a.status, 1);
+        pool_req(&a.stats, 4);
         if (par->tea_on) {
             pool_req(&a.tea_ci, n);
             pool_req(&a.tea_eps, n);
@@ -515,6 +530,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         CK(pool_commit(h, reqs));
         CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.status, 0, sizeof(int), h->stream));
+        CUK(cudaMemsetAsync(a.stats, 0, 4 * sizeof(unsigned long long), h->stream));
         CUK(cudaMemsetAsync(a.fpos, 0, n * sizeof(float4), h->stream));
         CUK(cudaMemsetAsync(a.fang, 0, n * sizeof(float4), h->stream));
         CUK(cudaMemsetAsync(a.bcnt, 0, (size_t)ntr * 2 * a.Npad, h->stream));

@@ -216,9 +216,10 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
     if (p.lj_on) {
         const float amp = p.ljscale * p.ljsigma6;
         float fx = 0.f, fy = 0.f, fz = 0.f;
-        if (near.ok) {
+        const int ncnt = near.ok ? (int)near.cnt[i] : MD_NEAR_FULL;
+        if (ncnt != MD_NEAR_FULL) {
             // shared-memory near list: the listed pairs that can be inside the 6-nm cut-off (see MD_NEAR_R2)
-            const int n = near.cnt[i];
+            const int n = ncnt;
             const uint16_t *nl = near.list + i;
             for (int kk = 0; kk < n; kk++) {
                 const unsigned e = nl[kk * a.N];
@@ -704,7 +705,8 @@ __device__ __forceinline__ bool filter_candidates(const KArgs &k, const Stage &s
             if (nlj > MADDY_LJ_CAPACITY) status |= ST_LJ_OVERFLOW;
         }
         if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj, MADDY_LJ_CAPACITY);
-        near.cnt[i] = (uint8_t)min(nn, near.cap);
+        // a crowded monomer (more near partners than the cache holds) simply keeps walking its full lists
+        near.cnt[i] = (uint8_t)(nn > near.cap ? MD_NEAR_FULL : nn);
         ovf |= nn > near.cap;
     }
     if (status) atomicOr(a.status, status);
@@ -730,9 +732,11 @@ __device__ __forceinline__ void bonds_from_near(const KArgs &k, const Stage &s, 
             const int hraw = a.harm[a.maxH * i];
             const int hp = hraw < 0 ? -hraw : hraw;
             const float4 Ei = s.E[i], L1i = s.L1[i], L2i = s.L2[i];
-            const int n = near.cnt[i];
+            const bool full = near.cnt[i] == MD_NEAR_FULL; // near list overflowed: take the candidates (same ascending order)
+            const int n = full ? (int)a.candcnt[(size_t)traj * a.Npad + i] : (int)near.cnt[i];
+            const uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
             for (int kk = 0; kk < n; kk++) {
-                const int j = near.list[kk * N + i] & 0x7fffu;
+                const int j = full ? (int)cp[(size_t)kk * a.Npad] : (int)(near.list[kk * N + i] & 0x7fffu);
                 const float4 Pj = s.P[j];
                 const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -764,17 +768,24 @@ __device__ __forceinline__ bool refresh_near(const KArgs &k, const Stage &s, con
         if (k.p.lj_on && !(mo[t].flags & MF_EXTRA)) {
             const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
             const int n = a.ljcnt[(size_t)traj * a.Npad + i];
-            for (int kk = 0; kk < n; kk++) {
-                const int j = lj[(size_t)kk * a.Npad];
-                const float4 Pj = s.P[j];
-                const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
-                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < MD_NEAR_R2) {
-                    if (nn < near.cap) near.list[nn * N + i] = (uint16_t)(j | MD_NEAR_LJ_FLAG);
-                    nn++;
+            const size_t row = a.Npad;
+            // indices fetched MD_FILTER_BATCH at a time (one L2 round trip per batch, as in filter_candidates)
+            for (int k0 = 0; k0 < n; k0 += MD_FILTER_BATCH, lj += MD_FILTER_BATCH * row) {
+                unsigned jj[MD_FILTER_BATCH];
+#pragma unroll
+                for (int u = 0; u < MD_FILTER_BATCH; u++) jj[u] = k0 + u < n ? (unsigned)lj[u * row] : 0u;
+#pragma unroll
+                for (int u = 0; u < MD_FILTER_BATCH; u++) {
+                    const float4 Pj = s.P[jj[u]];
+                    const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
+                    if (k0 + u < n && fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < MD_NEAR_R2) {
+                        if (nn < near.cap) near.list[nn * N + i] = (uint16_t)(jj[u] | MD_NEAR_LJ_FLAG);
+                        nn++;
+                    }
                 }
             }
         }
-        near.cnt[i] = (uint8_t)min(nn, near.cap);
+        near.cnt[i] = (uint8_t)(nn > near.cap ? MD_NEAR_FULL : nn);
         ovf |= nn > near.cap;
     }
     return ovf;
@@ -806,6 +817,9 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
         fm[0].x = P.x; fm[0].y = P.y; fm[0].z = P.z;
         fm[0].flags = MF_FIXED | ((jf & 0x7f) << 1) | (jf & (MF_GTP | MF_ONTUB | MF_EXTRA));
     }
+    auto count_event = [&](int which) {
+        if (threadIdx.x == 0) atomicAdd(a.stats + which, 1ull);
+    };
     if (near.cap == 0) {
         rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
         if (with_fixed) rebuild_lists_all_pairs<1>(k, s, traj, fm, fi, ops);
@@ -825,12 +839,14 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
         }
     }
     if (__syncthreads_or(moved)) {
+        count_event(1);
         compute_tiles(s, near, N);
         __syncthreads();
         bool covf = scan_candidates<MPT>(k, s, near, traj, mo, idx);
         if (with_fixed) covf |= scan_candidates<1>(k, s, near, traj, fm, fi);
         cs.dirty = true;
         if (__syncthreads_or(covf)) { // more candidates than MD_CAND_CAPACITY: general path, candidates stay invalid
+            count_event(2);
             cs.valid = 0;
             rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
             if (with_fixed) rebuild_lists_all_pairs<1>(k, s, traj, fm, fi, ops);
@@ -843,12 +859,7 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
         if (fi[0] < N) a.cpos[base + fi[0]] = make_float4(fm[0].x, fm[0].y, fm[0].z, 0.f);
         __syncthreads(); // candidate rows of the fixed monomers are read by other threads below
     }
-    const bool ovf = filter_candidates<MPT>(k, s, near, traj, mo, idx, (ops & OP_REBUILD_LJ) != 0);
-    if (__syncthreads_or(ovf)) { // a near list overflowed: redo everything on the general path
-        rebuild_lists_all_pairs<MPT>(k, s, traj, mo, idx, ops);
-        if (with_fixed) rebuild_lists_all_pairs<1>(k, s, traj, fm, fi, ops);
-        return false;
-    }
+    if (filter_candidates<MPT>(k, s, near, traj, mo, idx, (ops & OP_REBUILD_LJ) != 0)) atomicAdd(a.stats + 3, 1ull);
     if (ops & OP_REBUILD_BONDS) bonds_from_near<MPT>(k, s, near, traj, mo, idx);
     if (with_fixed) {
         const int nwarp = blockDim.x >> 5;
@@ -1046,8 +1057,10 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                     if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
             }
         } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
-            const bool ovf = refresh_near<MPT>(k, s, near, traj, mo, idx);
-            near_state = __syncthreads_or(ovf) ? 2 : 1;
+            if (refresh_near<MPT>(k, s, near, traj, mo, idx)) atomicAdd(a.stats + 3, 1ull);
+            __syncthreads();
+            near_state = 1;
+            if (threadIdx.x == 0 && any_moved) atomicAdd(a.stats + 0, 1ull);
             formed = true;
         }
         if (formed) {

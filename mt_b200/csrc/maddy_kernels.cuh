@@ -57,6 +57,7 @@ struct DevSys {
     double *en_mono; // [n][7]
     double *en_traj; // [ntr][7]
     int *status;
+    unsigned long long *stats; // [4] list-maintenance events: near refresh on guard trip, candidate re-scan, all-pairs fallback, near overflow
     uint16_t *cand;    // [ntr][MD_CAND_CAPACITY][Npad] candidate list, k-major
     uint16_t *candcnt; // [ntr][Npad]
     float4 *cpos;      // [n] positions when the candidate list was built (.w unused)
@@ -85,6 +86,7 @@ struct DevSys {
 #define MD_CAND_SKIN 1.5f
 #define MD_CAND_GUARD2 0.5476f // 0.74^2 (< (MD_CAND_SKIN/2)^2)
 #define MD_CAND_CAPACITY 320
+#define MD_NEAR_FULL 255 // near.cnt value of a monomer whose near list overflowed: it walks its full Verlet list instead
 #define MD_FILTER_BATCH 8 // candidate indices fetched per round trip in filter_candidates
 
 // Per-run constants evaluated ONCE on the device (consts_kernel) with the same fast-math float expressions the

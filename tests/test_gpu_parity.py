@@ -380,6 +380,27 @@ def test_list_hierarchy_equals_all_pairs_path_on_diffusing_dimers(rundir, load_s
     assert moved.max() > 0.8  # the guards did trip
 
 
+def test_crowded_monomers_overflow_the_near_list_individually(rundir, load_system, monkeypatch):
+    """A near list too small for some monomers (here: forced to 6 entries) makes THOSE monomers walk their full lists;
+    forces, trajectories and lists stay bit-identical to the plain all-pairs path."""
+    s = load_system(rundir("mt40_ensemble", runnum=3), ["hydrolysis=no"])
+    monkeypatch.setenv("MADDY_NEAR_CAP", "6")
+    small = Engine(s)
+    monkeypatch.delenv("MADDY_NEAR_CAP")
+    monkeypatch.setenv("MADDY_NO_NEAR", "1")
+    plain = Engine(s)
+    monkeypatch.delenv("MADDY_NO_NEAR")
+    normal = Engine(s)
+    for e in (small, plain, normal):
+        e.run(0, 70)
+    assert small.list_stats()["near_overflow"] > 0 and normal.list_stats()["near_overflow"] == 0
+    assert small.list_stats()["all_pairs_fallback"] == 0
+    for e in (small, normal):
+        assert np.array_equal(e.coords(), plain.coords()) and np.array_equal(e.rng_state(), plain.rng_state())
+        for kind in (capi.LIST_LJ, capi.LIST_LONGITUDINAL, capi.LIST_LATERAL):
+            assert lists_equal(*e.download_list(kind), *plain.download_list(kind))
+
+
 def test_gtp_schedule_equals_explicit_uploads(rundir, load_system):
     """maddy_schedule_gtp: GTP states applied in-kernel at scheduled steps == maddy_upload_gtp between shorter windows."""
     s = load_system(rundir("mt40_ensemble", runnum=5), ["hydrolysis=no"])
