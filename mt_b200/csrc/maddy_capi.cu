@@ -10,6 +10,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <thread>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -39,7 +40,11 @@ static int host_threads()
 {
 #ifdef _OPENMP
     static const int k = [] {
+        // OMP_NUM_THREADS if it asks for several threads; launchers that pin it to 1 per rank (torchrun) still get a
+        // share of a many-core host: one sixteenth of the hardware threads, at most 8
         int m = omp_get_max_threads();
+        const int share = (int)(std::thread::hardware_concurrency() / 16);
+        if (m < share) m = share;
         return m > 8 ? 8 : (m < 1 ? 1 : m);
     }();
     return k;

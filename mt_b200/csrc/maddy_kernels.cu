@@ -27,21 +27,28 @@ namespace maddy {
 
 #define KB_BOLTZ 0.0019872041f // kcal/(mol*K), mt.h:39
 
+// Dynamic shared memory of both trajectory kernels (declared once so that every access below is a plain shared-space
+// load/store with a 32-bit address and folded immediate offsets - no generic pointers, no per-step pointer set-up).
+extern __shared__ float4 g_smem[];
+
+// One stage buffer: four float4 arrays of N entries (array-major: a warp gathering the positions of 32 different
+// neighbours then spreads over all banks; a monomer-major layout was measured 4x worse in bank conflicts).
+//   P: x, y, z, fi     E: r_mon*e3, psi     L1: R*p1, theta     L2: R*p2, flag bits (mon_type | gtp<<8 | ontub<<9 | extra<<10)
 struct Stage {
-    float4 *P;  // x, y, z, fi
-    float4 *E;  // r_mon*e3, psi
-    float4 *L1; // R*p1, theta
-    float4 *L2; // R*p2, flag bits (mon_type | gtp<<8 | ontub<<9 | extra<<10)
+    int oP, oE, oL1, oL2; // float4 indices into g_smem
+    __device__ __forceinline__ float4 &P(int j) const { return g_smem[oP + j]; }
+    __device__ __forceinline__ float4 &E(int j) const { return g_smem[oE + j]; }
+    __device__ __forceinline__ float4 &L1(int j) const { return g_smem[oL1 + j]; }
+    __device__ __forceinline__ float4 &L2(int j) const { return g_smem[oL2 + j]; }
 };
 
-__device__ __forceinline__ Stage stage_at(float4 *smem, int N, int buf)
+__device__ __forceinline__ Stage stage_at(int N, int buf)
 {
     Stage s;
-    float4 *b = smem + (size_t)buf * 4 * N;
-    s.P = b;
-    s.E = b + N;
-    s.L1 = b + 2 * N;
-    s.L2 = b + 3 * N;
+    s.oP = buf * 4 * N;
+    s.oE = s.oP + N;
+    s.oL1 = s.oE + N;
+    s.oL2 = s.oL1 + N;
     return s;
 }
 
@@ -98,11 +105,11 @@ __device__ __forceinline__ Frame publish(const Stage &s, int i, const Mono &m, c
 {
     F3 a, l1, l2;
     const Frame fr = make_frame(m.fi, m.psi, m.theta, ls, a, l1, l2);
-    s.P[i] = make_float4(m.x, m.y, m.z, m.fi);
-    s.E[i] = make_float4(a.x, a.y, a.z, m.psi);
-    s.L1[i] = make_float4(l1.x, l1.y, l1.z, m.theta);
+    s.P(i) = make_float4(m.x, m.y, m.z, m.fi);
+    s.E(i) = make_float4(a.x, a.y, a.z, m.psi);
+    s.L1(i) = make_float4(l1.x, l1.y, l1.z, m.theta);
     int jf = MF_TYPE(m.flags) | (m.flags & (MF_GTP | MF_ONTUB | MF_EXTRA));
-    s.L2[i] = make_float4(l2.x, l2.y, l2.z, __int_as_float(jf));
+    s.L2(i) = make_float4(l2.x, l2.y, l2.z, __int_as_float(jf));
     return fr;
 }
 
@@ -114,7 +121,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
     const maddy_params &p = k.p;
     const DevSys &a = k.a;
     G6 f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float4 Ei = s.E[i];
+    const float4 Ei = s.E(i);
     const float xi = m.x, yi = m.y, zi = m.z;
     const bool gtp_i = (m.flags & MF_GTP) != 0;
     const bool ontub_i = (m.flags & MF_ONTUB) != 0;
@@ -127,7 +134,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         const int raw = topo_harm(a, tw, i, kk);
         const float sg = raw < 0 ? 1.0f : -1.0f; // R_MON / r_mon
         const int j = raw < 0 ? -raw : raw;
-        const float4 Pj = s.P[j], Ej = s.E[j];
+        const float4 Pj = s.P(j), Ej = s.E(j);
         F3 d;
         d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
         d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
@@ -137,7 +144,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         if (dr < MD_ANGLE_CUTOFF) {
             const float psiji = Ej.w - m.psi;
             const float fiji = Pj.w - m.fi;
-            const float thetaji = s.L1[j].w - m.theta;
+            const float thetaji = s.L1(j).w - m.theta;
             const float th0 = gtp_i ? p.theta0_gtp : p.theta0_gdp;
             // +B sin(q_j - q_i - q0) on the R_MON > 0 side, -B sin(q_i - q_j - q0) on the other: sg (q_j - q_i) - q0, scaled by sg B
             f.psi = fmaf(sg * p.B_psi, sinf(fmaf(sg, psiji, -p.psi_0)), f.psi);
@@ -152,8 +159,8 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         const unsigned code = topo_long(a, tw, traj, i, kk);
         const int j = code >> 1;
         const float sg = (code & 1u) ? 1.0f : -1.0f;
-        const float4 Pj = s.P[j], Ej = s.E[j];
-        const float4 L2j = s.L2[j];
+        const float4 Pj = s.P(j), Ej = s.E(j);
+        const float4 L2j = s.L2(j);
         const int jf = __float_as_int(L2j.w);
         F3 d;
         d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
@@ -170,7 +177,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         if (dr < MD_ANGLE_CUTOFF) {
             const float psiji = Ej.w - m.psi;
             const float fiji = Pj.w - m.fi;
-            const float thetaji = s.L1[j].w - m.theta;
+            const float thetaji = s.L1(j).w - m.theta;
             // the dimer closer to the plus end rules theta0 (compute_cuda.cu:282-283)
             const bool gtp_last = (zi > Pj.z) ? gtp_i : ((jf & MF_GTP) != 0);
             const float th0 = gtp_last ? p.theta0_gtp : p.theta0_gdp;
@@ -184,15 +191,15 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
     // ---- lateral Morse (+ barrier), seam scaling (compute_cuda.cu:304-466)
     const int nlat = (tw.y >> 16) & 0xff;
     if (nlat > 0) {
-        const float4 L1i = s.L1[i], L2i = s.L2[i];
+        const float4 L1i = s.L1(i), L2i = s.L2(i);
         const int type_i = MF_TYPE(m.flags);
         for (int kk = 0; kk < nlat; kk++) {
             const unsigned code = topo_lat(a, tw, traj, i, kk);
             const int j = code >> 1;
             const bool neg = (code & 1u) != 0;
             // negative entry: i interacts through p1, j through p2; positive: i through p2, j through p1
-            const float4 Pj = s.P[j];
-            const float4 L1j = s.L1[j], L2j = s.L2[j];
+            const float4 Pj = s.P(j);
+            const float4 L1j = s.L1(j), L2j = s.L2(j);
             const int jf = __float_as_int(L2j.w);
             const F3 oi = neg ? mk3(L1i.x, L1i.y, L1i.z) : mk3(L2i.x, L2i.y, L2i.z);
             const F3 oj = neg ? mk3(L2j.x, L2j.y, L2j.z) : mk3(L1j.x, L1j.y, L1j.z);
@@ -219,22 +226,25 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         const int ncnt = near.ok ? (int)near.cnt[i] : MD_NEAR_FULL;
         if (ncnt != MD_NEAR_FULL) {
             // shared-memory near list: the listed pairs that can be inside the 6-nm cut-off (see MD_NEAR_R2)
+            // An entry outside the force cut-off (or not LJ-listed) gets the coefficient 0, which leaves the accumulators
+            // bit-for-bit unchanged; the rare fp64 tie-break of inside_cut is the only branch in the loop body.
             const int n = ncnt;
             const uint16_t *nl = near.list + i;
+            const float lo = k.cut_force.lo, hi = k.cut_force.hi;
             for (int kk = 0; kk < n; kk++) {
                 const unsigned e = nl[kk * a.N];
-                if (!(e & MD_NEAR_LJ_FLAG)) continue;
-                const float4 Pj = s.P[e & 0x7fffu];
+                const float4 Pj = s.P(e & 0x7fffu);
                 const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
-                    const float inv = 1.0f / sf;
-                    const float inv2 = inv * inv;
-                    const float c = amp * (6.0f * (inv2 * inv2)); // 6 / dr^8
-                    fx = fmaf(c, dx, fx);
-                    fy = fmaf(c, dy, fy);
-                    fz = fmaf(c, dz, fz);
-                }
+                bool in = sf < lo;
+                if (sf >= lo && sf <= hi) in = dist2_exact(dx, dy, dz) < k.cut_force.t;
+                in = in && (e & MD_NEAR_LJ_FLAG);
+                const float inv = 1.0f / sf;
+                const float inv2 = inv * inv;
+                const float c = in ? amp * (6.0f * (inv2 * inv2)) : 0.0f; // 6 / dr^8
+                fx = fmaf(c, dx, fx);
+                fy = fmaf(c, dy, fy);
+                fz = fmaf(c, dz, fz);
             }
         } else {
             const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
@@ -242,7 +252,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
 #pragma unroll 4
             for (int kk = 0; kk < n; kk++) {
                 const int j = lj[(size_t)kk * a.Npad];
-                const float4 Pj = s.P[j];
+                const float4 Pj = s.P(j);
                 const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
@@ -287,7 +297,7 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
     const DevSys &a = k.a;
     float U_lat = 0.f, U_long = 0.f, U_harm = 0.f, U_fi = 0.f, U_psi = 0.f, U_teta = 0.f, U_lj = 0.f;
     if (!(m.flags & MF_EXTRA)) {
-        const float4 Ei = s.E[i];
+        const float4 Ei = s.E(i);
         const float xi = m.x, yi = m.y, zi = m.z;
         const bool gtp_i = (m.flags & MF_GTP) != 0;
         const bool ontub_i = (m.flags & MF_ONTUB) != 0;
@@ -296,7 +306,7 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
             int raw = a.harm[a.maxH * i + kk];
             const float sg = raw < 0 ? 1.0f : -1.0f;
             const int j = raw < 0 ? -raw : raw;
-            const float4 Pj = s.P[j], Ej = s.E[j];
+            const float4 Pj = s.P(j), Ej = s.E(j);
             F3 d;
             d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
             d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
@@ -307,7 +317,7 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
                 // quirk kept: psi and fi use (i - j), theta uses (j - i)  (compute_cuda.cu:751-757)
                 const float psiij = -(Ej.w - m.psi);
                 const float fiij = -(Pj.w - m.fi);
-                const float thetaji = s.L1[j].w - m.theta;
+                const float thetaji = s.L1(j).w - m.theta;
                 U_psi += p.B_psi * (1 - cosf(psiij - p.psi_0));
                 U_fi += p.B_fi * (1 - cosf(fiij - p.fi_0));
                 U_teta += p.B_theta * (1 - cosf(thetaji - (gtp_i ? p.theta0_gtp : p.theta0_gdp)));
@@ -320,8 +330,8 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
             const unsigned code = bl[(size_t)kk * a.Npad];
             const int j = code >> 1;
             const float sg = (code & 1u) ? 1.0f : -1.0f;
-            const float4 Pj = s.P[j], Ej = s.E[j];
-            const int jf = __float_as_int(s.L2[j].w);
+            const float4 Pj = s.P(j), Ej = s.E(j);
+            const int jf = __float_as_int(s.L2(j).w);
             F3 d;
             d.x = fmaf(-sg, Ej.x, fmaf(-sg, Ei.x, Pj.x - xi));
             d.y = fmaf(-sg, Ej.y, fmaf(-sg, Ei.y, Pj.y - yi));
@@ -336,7 +346,7 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
             if (dr < MD_ANGLE_CUTOFF) {
                 const float psiij = -(Ej.w - m.psi);
                 const float fiij = -(Pj.w - m.fi);
-                const float thetaij = -(s.L1[j].w - m.theta);
+                const float thetaij = -(s.L1(j).w - m.theta);
                 const bool gtp_last = (zi > Pj.z) ? gtp_i : ((jf & MF_GTP) != 0);
                 const float th0 = gtp_last ? p.theta0_gtp : p.theta0_gdp;
                 U_psi += p.B_psi * (1 - cosf(psiij - p.psi_0));
@@ -346,14 +356,14 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
         }
         const int nlat = bc[a.Npad];
         if (nlat > 0) {
-            const float4 L1i = s.L1[i], L2i = s.L2[i];
+            const float4 L1i = s.L1(i), L2i = s.L2(i);
             const int type_i = MF_TYPE(m.flags);
             for (int kk = 0; kk < nlat; kk++) {
                 const unsigned code = bl[(size_t)(a.capLong + kk) * a.Npad];
                 const int j = code >> 1;
                 const bool neg = (code & 1u) != 0;
-                const float4 Pj = s.P[j];
-                const float4 L1j = s.L1[j], L2j = s.L2[j];
+                const float4 Pj = s.P(j);
+                const float4 L1j = s.L1(j), L2j = s.L2(j);
                 const int jf = __float_as_int(L2j.w);
                 const F3 oi = neg ? mk3(L1i.x, L1i.y, L1i.z) : mk3(L2i.x, L2i.y, L2i.z);
                 const F3 oj = neg ? mk3(L2j.x, L2j.y, L2j.z) : mk3(L1j.x, L1j.y, L1j.z);
@@ -372,7 +382,7 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int
             const int n = a.ljcnt[(size_t)traj * a.Npad + i];
             for (int kk = 0; kk < n; kk++) {
                 const int j = lj[(size_t)kk * a.Npad];
-                const float4 Pj = s.P[j];
+                const float4 Pj = s.P(j);
                 const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
@@ -405,7 +415,7 @@ struct BondOut {
 __device__ __forceinline__ unsigned bond_tests(const Stage &s, float xi, float yi, float zi, int type_i, int j, int hraw, const float4 &Pj,
                                                const float4 &Ei, const float4 &L1i, const float4 &L2i)
 {
-    const float4 Ej = s.E[j], L1j = s.L1[j], L2j = s.L2[j];
+    const float4 Ej = s.E(j), L1j = s.L1(j), L2j = s.L2(j);
     const int jf = __float_as_int(L2j.w);
     unsigned hit = 0;
     if (type_i != (jf & 0x7f)) {
@@ -461,7 +471,7 @@ __device__ __forceinline__ void rebuild_row_cooperative(const KArgs &k, const St
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const bool do_lj = (ops & OP_REBUILD_LJ) != 0, do_b = (ops & OP_REBUILD_BONDS) != 0;
-    const float4 Pi = s.P[i], Ei = s.E[i], L1i = s.L1[i], L2i = s.L2[i];
+    const float4 Pi = s.P(i), Ei = s.E(i), L1i = s.L1(i), L2i = s.L2(i);
     const int fl = __float_as_int(L2i.w);
     const int hraw = a.harm[a.maxH * i];
     const int hp = hraw < 0 ? -hraw : hraw;
@@ -475,7 +485,7 @@ __device__ __forceinline__ void rebuild_row_cooperative(const KArgs &k, const St
         const int kk = b0 + lane;
         const bool valid = kk < n;
         const int j = valid ? (int)cp[(size_t)kk * a.Npad] : 0;
-        const float4 Pj = s.P[j];
+        const float4 Pj = s.P(j);
         const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
         const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         if (do_lj) {
@@ -547,9 +557,9 @@ __device__ __forceinline__ void rebuild_lists_all_pairs(const KArgs &k, const St
         if (!(mo[t].flags & MF_EXTRA)) {
             const int hraw = a.harm[a.maxH * i]; // first entry, whatever harmonicCount says (compute_cuda.cu:548)
             const int hp = hraw < 0 ? -hraw : hraw;
-            const float4 Ei = s.E[i], L1i = s.L1[i], L2i = s.L2[i];
+            const float4 Ei = s.E(i), L1i = s.L1(i), L2i = s.L2(i);
             for (int j = 0; j < N; j++) {
-                const float4 Pj = s.P[j];
+                const float4 Pj = s.P(j);
                 const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 if (i == j) continue;
@@ -577,10 +587,10 @@ __device__ __forceinline__ void compute_tiles(const Stage &s, const Near &near, 
 {
     for (int t = threadIdx.x; t < near.ntiles; t += blockDim.x) {
         const int j0 = t * MD_TILE, j1 = min(N, j0 + MD_TILE);
-        float4 p = s.P[j0];
+        float4 p = s.P(j0);
         float lx = p.x, ly = p.y, lz = p.z, hx = p.x, hy = p.y, hz = p.z;
         for (int j = j0 + 1; j < j1; j++) {
-            p = s.P[j];
+            p = s.P(j);
             lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
             hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
         }
@@ -623,7 +633,7 @@ __device__ __forceinline__ bool scan_candidates(const KArgs &k, const Stage &s, 
                 if (tile >= near.ntiles) break;
                 const int j0 = tile * MD_TILE, j1 = min(N, j0 + MD_TILE);
                 for (int j = j0; j < j1; j++) {
-                    const float4 Pj = s.P[j];
+                    const float4 Pj = s.P(j);
                     const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
                     if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < rc2 && j != i) {
                         if (nc < MD_CAND_CAPACITY) {
@@ -670,7 +680,6 @@ __device__ __forceinline__ bool filter_candidates(const KArgs &k, const Stage &s
             const uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
             const uint16_t *lj_col = (const uint16_t *)__cvta_generic_to_global(a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i);
             asm volatile("" : "+l"(lj_col)); // keep the column base in registers (otherwise re-derived at every store)
-            const unsigned P_s = (unsigned)__cvta_generic_to_shared(s.P);
             unsigned near_s = (unsigned)__cvta_generic_to_shared(near.list + i);
             const unsigned near_end = near_s + (unsigned)(near.cap * N) * 2u, near_step = (unsigned)N * 2u;
             const int n = a.candcnt[(size_t)traj * a.Npad + i];
@@ -687,7 +696,7 @@ __device__ __forceinline__ bool filter_candidates(const KArgs &k, const Stage &s
                 for (int u = 0; u < MD_FILTER_BATCH; u++) jj[u] = k0 + u < n ? (unsigned)cp[u * (size_t)row] : 0u;
 #pragma unroll
                 for (int u = 0; u < MD_FILTER_BATCH; u++) {
-                    const float4 Pj = lds_f4(P_s + jj[u] * 16u);
+                    const float4 Pj = s.P((int)jj[u]);
                     const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
                     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     const float sf = k0 + u < n ? d2 : 3.0e38f; // slots past the end of the list are outside every radius
@@ -731,13 +740,13 @@ __device__ __forceinline__ void bonds_from_near(const KArgs &k, const Stage &s, 
         if (!(mo[t].flags & MF_EXTRA)) {
             const int hraw = a.harm[a.maxH * i];
             const int hp = hraw < 0 ? -hraw : hraw;
-            const float4 Ei = s.E[i], L1i = s.L1[i], L2i = s.L2[i];
+            const float4 Ei = s.E(i), L1i = s.L1(i), L2i = s.L2(i);
             const bool full = near.cnt[i] == MD_NEAR_FULL; // near list overflowed: take the candidates (same ascending order)
             const int n = full ? (int)a.candcnt[(size_t)traj * a.Npad + i] : (int)near.cnt[i];
             const uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
             for (int kk = 0; kk < n; kk++) {
                 const int j = full ? (int)cp[(size_t)kk * a.Npad] : (int)(near.list[kk * N + i] & 0x7fffu);
-                const float4 Pj = s.P[j];
+                const float4 Pj = s.P(j);
                 const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 if (sf < MD_BOND_PREFILTER2 && hp != j) bond_candidates(a, s, i, j, mo[t], hraw, Pj, Ei, L1i, L2i, bo);
@@ -776,7 +785,7 @@ __device__ __forceinline__ bool refresh_near(const KArgs &k, const Stage &s, con
                 for (int u = 0; u < MD_FILTER_BATCH; u++) jj[u] = k0 + u < n ? (unsigned)lj[u * row] : 0u;
 #pragma unroll
                 for (int u = 0; u < MD_FILTER_BATCH; u++) {
-                    const float4 Pj = s.P[jj[u]];
+                    const float4 Pj = s.P(jj[u]);
                     const float dx = mo[t].x - Pj.x, dy = mo[t].y - Pj.y, dz = mo[t].z - Pj.z;
                     if (k0 + u < n && fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < MD_NEAR_R2) {
                         if (nn < near.cap) near.list[nn * N + i] = (uint16_t)(jj[u] | MD_NEAR_LJ_FLAG);
@@ -812,8 +821,8 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
     fm[0].flags = MF_EXTRA | MF_FIXED;
     if (with_fixed && (int)threadIdx.x < a.n_fixed) {
         fi[0] = (int)a.fmap[threadIdx.x];
-        const float4 P = s.P[fi[0]];
-        const int jf = __float_as_int(s.L2[fi[0]].w);
+        const float4 P = s.P(fi[0]);
+        const int jf = __float_as_int(s.L2(fi[0]).w);
         fm[0].x = P.x; fm[0].y = P.y; fm[0].z = P.z;
         fm[0].flags = MF_FIXED | ((jf & 0x7f) << 1) | (jf & (MF_GTP | MF_ONTUB | MF_EXTRA));
     }
@@ -955,7 +964,7 @@ __device__ __forceinline__ void load_mono(const DevSys &a, size_t base, int i, M
 template <int MPT, int MINB>
 __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_constant__ KArgs k)
 {
-    extern __shared__ float4 smem[];
+    float4 *const smem = g_smem;
     const maddy_params &p = k.p;
     const DevSys &a = k.a;
     const int N = a.N;
@@ -992,8 +1001,8 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
         const int i = (int)a.fmap[threadIdx.x];
         Mono fm;
         load_mono(a, base, i, fm);
-        publish(stage_at(smem, N, 0), i, fm, ls);
-        if (k.nbuf == 2) publish(stage_at(smem, N, 1), i, fm, ls);
+        publish(stage_at(N, 0), i, fm, ls);
+        if (k.nbuf == 2) publish(stage_at(N, 1), i, fm, ls);
     }
 
     CandState cs; // candidate-list state (persists in HBM between launches)
@@ -1010,7 +1019,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     int fixed_flags_dirty = 0; // stage buffers whose copy of a fixed monomer's GTP bit is stale
     bool gtp_changed = false;
     for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
-        const Stage s = stage_at(smem, N, buf);
+        const Stage s = stage_at(N, buf);
         // scheduled hydrolysis event: the GTP flags uploaded for this step become current (maddy_schedule_gtp)
         if (k.sched_slots > 0 && step >= k.sched_first && (step - k.sched_first) % k.sched_period == 0) {
             const long long slot = (step - k.sched_first) / k.sched_period;
@@ -1028,9 +1037,9 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                 const long long slot = (step - k.sched_first) / k.sched_period; // latest slot at or before this step
                 const uint8_t *g = a.gtp_sched + (size_t)slot * a.ntr * N + base;
                 const int i = (int)a.fmap[threadIdx.x];
-                int jf = __float_as_int(s.L2[i].w);
+                int jf = __float_as_int(s.L2(i).w);
                 jf = (jf & ~MF_GTP) | (g[i] == 1 ? MF_GTP : 0);
-                s.L2[i].w = __int_as_float(jf);
+                s.L2(i).w = __int_as_float(jf);
             }
             fixed_flags_dirty--;
         }
@@ -1118,7 +1127,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
 template <int MPT>
 __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_constant__ KArgs k)
 {
-    extern __shared__ float4 smem[];
+    float4 *const smem = g_smem;
     __shared__ double red_scratch[32 * 7];
     const DevSys &a = k.a;
     const int N = a.N;
@@ -1136,7 +1145,7 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
         mo[t].flags = MF_EXTRA | MF_FIXED;
         if (i < N) load_mono(a, base, i, mo[t]);
     }
-    const Stage s = stage_at(smem, N, 0);
+    const Stage s = stage_at(N, 0);
     Frame fr[MPT];
 #pragma unroll
     for (int t = 0; t < MPT; t++)
