@@ -74,6 +74,8 @@ struct maddy_handle {
     CutTest cut_pairs, cut_force;
     std::string err;
     long long launches = 0;
+    bool lazy = false;          // fused loop keeps the Verlet list lazily (see ensure_lj)
+    bool lj_maybe_stale = false; // some trajectory's Verlet list may have to be materialised before it is read
     std::vector<void *> allocs;
     int *h_status = nullptr; // pinned
     // ring of pinned staging buffers for the flag uploads: the copies are asynchronous, so the host can queue the
@@ -198,6 +200,7 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
         const float rb = fmaxf(h->p.lj_on ? h->p.ljpairscutoff : 0.f, 7.0f) + MD_CAND_SKIN;
         k.rcand2 = rb * rb;
     }
+    k.lazy = (ops & OP_RUN) && h->lazy;
     k.cut_pairs = h->cut_pairs;
     k.cut_force = h->cut_force;
     return k;
@@ -518,6 +521,10 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         pool_req(const_cast<uint16_t **>(&a.amap), h->amap.size());
         pool_req(const_cast<uint16_t **>(&a.fmap), h->fmap.size());
         pool_req(&a.candcnt, (size_t)ntr * a.Npad);
+        pool_req(&a.ncand, (h->run.near_cap > 0 || h->phase.near_cap > 0) ? (size_t)ntr * MD_NCAND_CAPACITY * a.Npad : 1);
+        pool_req(&a.ncandcnt, (size_t)ntr * a.Npad);
+        pool_req(&a.rpos, n);
+        pool_req(&a.lj_stale, (size_t)ntr);
         pool_req(&a.cpos, n);
         pool_req(&a.cand_valid, (size_t)ntr);
         pool_req(&a.en_mono, n * 7);
@@ -534,6 +541,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         }
         CK(pool_commit(h, reqs));
         CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
+        CUK(cudaMemsetAsync(a.lj_stale, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.status, 0, sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.stats, 0, 4 * sizeof(unsigned long long), h->stream));
         CUK(cudaMemsetAsync(a.fpos, 0, n * sizeof(float4), h->stream));
@@ -547,6 +555,10 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         aos_to_soa(coords, n, pos, ang, true);
         CUK(cudaMemcpyAsync(a.pos, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
         CUK(cudaMemcpyAsync(a.ang, ang.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+        CUK(cudaMemcpyAsync(a.rpos, a.pos, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+        // Lazy Verlet list in the fused loop: every pair inside the near radius must be certain to be listed, whatever
+        // the monomers did since the candidate list was built (7.0 + 4 x 0.74 < cut-off), and both kernels need candidates.
+        h->lazy = par->lj_on && par->ljpairscutoff >= 10.0f && h->run.near_cap > 0 && h->phase.near_cap > 0 && !getenv("MADDY_NO_LAZY");
 
         // static topology
         std::vector<uint8_t> sflags(N);
@@ -609,10 +621,20 @@ bad:
 }
 
 // ------------------------------------------------------------------ step-granular entry points
+// The fused loop may leave the Verlet list of its last list-update step unwritten (KArgs::lazy); anything that reads
+// the list, or invalidates the candidates it would be derived from, calls this first.
+static int ensure_lj(maddy_handle *h)
+{
+    if (!h->lj_maybe_stale) return MADDY_OK;
+    h->lj_maybe_stale = false;
+    return launch(h, kargs(h, OP_MATERIALISE));
+}
+
 extern "C" int maddy_rebuild_lj(maddy_handle *h)
 {
     if (!h) return MADDY_EINVAL;
     if (!h->p.lj_on) return MADDY_OK;
+    h->lj_maybe_stale = false; // the kernel writes every trajectory's list and clears its flag
     return launch(h, kargs(h, OP_REBUILD_LJ));
 }
 extern "C" int maddy_rebuild_bonds(maddy_handle *h)
@@ -623,6 +645,8 @@ extern "C" int maddy_rebuild_bonds(maddy_handle *h)
 extern "C" int maddy_force(maddy_handle *h)
 {
     if (!h) return MADDY_EINVAL;
+    int rc = ensure_lj(h);
+    if (rc) return rc;
     return launch(h, kargs(h, OP_FORCE));
 }
 extern "C" int maddy_integrate(maddy_handle *h)
@@ -640,10 +664,22 @@ extern "C" int maddy_run(maddy_handle *h, long long first_step, long long n_step
     if (!h || n_steps < 0) return MADDY_EINVAL;
     if (n_steps == 0) return MADDY_OK;
     if (h->p.tea_on) return fail(h, MADDY_EINVAL, "maddy_run: fused TEA loop not available; use the step-granular TEA entry points");
+    const long long freq = h->p.ljpairsupdatefreq > 0 ? h->p.ljpairsupdatefreq : 1;
+    const bool rebuilds = h->p.lj_on || h->p.is_assembly;
+    const bool skip_first = (flags & MADDY_RUN_SKIP_FIRST_REBUILD) != 0;
+    if (!(rebuilds && first_step % freq == 0 && !skip_first)) { // the window starts from the lists as they stand
+        int rc = ensure_lj(h);
+        if (rc) return rc;
+    }
     KArgs k = kargs(h, OP_RUN);
     k.first_step = first_step;
     k.n_steps = n_steps;
     k.run_flags = flags;
+    if (k.lazy && rebuilds) { // does the window contain a list-update step?
+        long long m = (first_step + freq - 1) / freq * freq;
+        if (m == first_step && skip_first) m += freq;
+        if (m < first_step + n_steps) h->lj_maybe_stale = true;
+    }
     return launch(h, k);
 }
 
@@ -661,7 +697,10 @@ extern "C" int maddy_rebuild_and_energies(maddy_handle *h, double *out_per_traj,
 }
 static int energies_impl(maddy_handle *h, unsigned ops, double *out_per_traj, double *out_per_monomer)
 {
-    int rc = launch(h, kargs(h, ops));
+    int rc = (ops & OP_REBUILD_LJ) ? MADDY_OK : ensure_lj(h);
+    if (rc) return rc;
+    if (ops & OP_REBUILD_LJ) h->lj_maybe_stale = false;
+    rc = launch(h, kargs(h, ops));
     if (rc) return rc;
     const size_t n = (size_t)h->a.ntr * h->a.N;
     if (out_per_traj)
@@ -724,7 +763,10 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
     if (what & MADDY_SNAP_ENERGIES) {
         unsigned ops = OP_ENERGY;
         if (what & MADDY_SNAP_REBUILD) ops |= (h->p.lj_on ? OP_REBUILD_LJ : 0u) | (h->p.is_assembly ? OP_REBUILD_BONDS : 0u);
-        int rc = launch(h, kargs(h, ops));
+        int rc = (ops & OP_REBUILD_LJ) ? MADDY_OK : ensure_lj(h);
+        if (rc) return rc;
+        if (ops & OP_REBUILD_LJ) h->lj_maybe_stale = false;
+        rc = launch(h, kargs(h, ops));
         if (rc) return rc;
         if (!h->snap_en) {
             CU(h, cudaMallocHost(&h->snap_en, (size_t)h->a.ntr * 7 * sizeof(double)));
@@ -836,9 +878,12 @@ extern "C" int maddy_upload_coords(maddy_handle *h, const float *aos)
     const size_t n = (size_t)h->a.ntr * h->a.N;
     std::vector<float4> pos, ang;
     aos_to_soa(aos, n, pos, ang, false);
+    int rc = ensure_lj(h); // the Verlet list keeps referring to the old positions until the next list-update step
+    if (rc) return rc;
     CU(h, cudaMemsetAsync(h->a.cand_valid, 0, (size_t)h->a.ntr * sizeof(int), h->stream)); // candidate lists refer to the old positions
     CU(h, cudaMemcpyAsync(h->a.pos, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->a.ang, ang.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->a.rpos, h->a.pos, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return MADDY_OK;
 }
@@ -924,6 +969,8 @@ extern "C" int maddy_upload_extra(maddy_handle *h, const unsigned char *extra)
     int slot, rc = stage_acquire(h, &v, &slot);
     if (rc) return rc;
     for (size_t q = 0; q < n; q++) v[q] = extra[q] != 0;
+    rc = ensure_lj(h);
+    if (rc) return rc;
     if (h->a.cand_valid) CU(h, cudaMemsetAsync(h->a.cand_valid, 0, (size_t)h->a.ntr * sizeof(int), h->stream)); // rows of former extras are empty
     return stage_submit(h, h->a.extra, slot);
 }
@@ -952,6 +999,8 @@ extern "C" int maddy_download_list(maddy_handle *h, int kind, int *counts, int *
     const int N = a.N, Npad = a.Npad, ntr = a.ntr;
     if (kind == MADDY_LIST_LJ) {
         if (!h->p.lj_on) return fail(h, MADDY_EINVAL, "LJ list requested but LJ_on is off");
+        int rce = ensure_lj(h);
+        if (rce) return rce;
         std::vector<uint16_t> lj((size_t)ntr * MADDY_LJ_CAPACITY * Npad), cnt((size_t)ntr * Npad);
         CU(h, cudaMemcpyAsync(lj.data(), a.lj, lj.size() * 2, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaMemcpyAsync(cnt.data(), a.ljcnt, cnt.size() * 2, cudaMemcpyDeviceToHost, h->stream));
@@ -1002,6 +1051,8 @@ extern "C" int maddy_upload_list(maddy_handle *h, int kind, const int *counts, c
     const int N = a.N, Npad = a.Npad, ntr = a.ntr;
     if (kind == MADDY_LIST_LJ) {
         if (!h->p.lj_on) return fail(h, MADDY_EINVAL, "LJ list upload but LJ_on is off");
+        h->lj_maybe_stale = false; // the uploaded list is the list
+        CU(h, cudaMemsetAsync(h->a.lj_stale, 0, (size_t)ntr * sizeof(int), h->stream));
         std::vector<uint16_t> lj((size_t)ntr * MADDY_LJ_CAPACITY * Npad, 0), cnt((size_t)ntr * Npad, 0);
         for (int t = 0; t < ntr; t++)
             for (int i = 0; i < N; i++) {

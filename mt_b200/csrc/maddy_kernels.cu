@@ -58,6 +58,9 @@ struct Near { // shared-memory near list of the fused loop (see MD_NEAR_R2 in ma
     float4 *tlo, *thi; // bounding boxes of tiles of MD_TILE consecutive monomers
     int cap, ntiles;
     bool ok;        // CTA-uniform: the near list is valid for this step
+    bool stale_lj;  // CTA-uniform: the Verlet list in HBM predates the last list-update step (lazy fused loop): a monomer
+                    // whose near list overflowed walks its near-candidates instead (same pairs inside the force cut-off,
+                    // same order: every such pair is certainly listed, see KArgs::lazy)
     uint4 *topo;    // [N] packed topology words (see load_topo), or nullptr: read the lists from HBM
 };
 
@@ -248,7 +251,13 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
             }
         } else {
             const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
-            const int n = a.ljcnt[(size_t)traj * a.Npad + i];
+            int n = a.ljcnt[(size_t)traj * a.Npad + i];
+            if (near.stale_lj) {
+                const int nnc = a.ncandcnt[(size_t)traj * a.Npad + i];
+                const bool all = nnc == MD_NEAR_FULL;
+                lj = all ? a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i : a.ncand + (size_t)traj * MD_NCAND_CAPACITY * a.Npad + i;
+                n = all ? (int)a.candcnt[(size_t)traj * a.Npad + i] : nnc;
+            }
 #pragma unroll 4
             for (int kk = 0; kk < n; kk++) {
                 const int j = lj[(size_t)kk * a.Npad];
@@ -616,9 +625,10 @@ __device__ __forceinline__ bool scan_candidates(const KArgs &k, const Stage &s, 
     for (int t = 0; t < MPT; t++) {
         const int i = idx[t];
         if (i >= N) continue;
-        int nc = 0;
+        int nc = 0, nnc = 0;
         if (!(mo[t].flags & MF_EXTRA)) {
             uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
+            uint16_t *np = a.ncand + (size_t)traj * MD_NCAND_CAPACITY * a.Npad + i;
             const float x = mo[t].x, y = mo[t].y, z = mo[t].z;
             int tile = 0;
             for (;;) {
@@ -635,18 +645,27 @@ __device__ __forceinline__ bool scan_candidates(const KArgs &k, const Stage &s, 
                 for (int j = j0; j < j1; j++) {
                     const float4 Pj = s.P(j);
                     const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
-                    if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < rc2 && j != i) {
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (d2 < rc2 && j != i) {
                         if (nc < MD_CAND_CAPACITY) {
                             *cp = (uint16_t)j;
                             cp += a.Npad;
                         }
                         nc++;
+                        if (d2 < MD_NCAND_R2) {
+                            if (nnc < MD_NCAND_CAPACITY) {
+                                *np = (uint16_t)j;
+                                np += a.Npad;
+                            }
+                            nnc++;
+                        }
                     }
                 }
                 tile++;
             }
         }
         a.candcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nc, MD_CAND_CAPACITY);
+        a.ncandcnt[(size_t)traj * a.Npad + i] = (uint8_t)(nnc > MD_NCAND_CAPACITY ? MD_NEAR_FULL : nnc);
         ovf |= nc > MD_CAND_CAPACITY;
     }
     return ovf;
@@ -719,6 +738,81 @@ __device__ __forceinline__ bool filter_candidates(const KArgs &k, const Stage &s
         ovf |= nn > near.cap;
     }
     if (status) atomicOr(a.status, status);
+    return ovf;
+}
+
+// The exact Verlet row of monomer i as of the last list-update step of the fused loop: candidates (valid for that step)
+// re-tested with the reference's cut-off test on the positions recorded then (a.rpos, gathered from HBM/L2).  Same
+// order and same arithmetic as filter_candidates.  Runs on demand only (maddy_download_list, energies, a window that
+// starts between two list-update steps, a tripped displacement guard).
+__device__ __forceinline__ void materialise_row(const KArgs &k, int traj, int i)
+{
+    const DevSys &a = k.a;
+    const size_t base = (size_t)traj * a.N;
+    int nlj = 0, status = 0;
+    if (!a.extra[base + i]) {
+        const float4 Pi = a.rpos[base + i];
+        const uint16_t *cp = a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i;
+        uint16_t *lp = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+        const int n = a.candcnt[(size_t)traj * a.Npad + i];
+        for (int kk = 0; kk < n; kk++) {
+            const int j = cp[(size_t)kk * a.Npad];
+            const float4 Pj = a.rpos[base + j];
+            const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+            const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (inside_cut(k.cut_pairs, dx, dy, dz, sf)) {
+                if (nlj < MADDY_LJ_CAPACITY) lp[(size_t)nlj * a.Npad] = (uint16_t)j;
+                else status |= ST_LJ_OVERFLOW;
+                nlj++;
+            }
+        }
+    }
+    a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj, MADDY_LJ_CAPACITY);
+    if (status) atomicOr(a.status, status);
+}
+
+// Lazy variant of phase 1b (fused loop): only the near list is refreshed, from the near-candidates.  Valid when the
+// pairs cut-off exceeds MD_NEAR_R + MD_CAND_SKIN, so that every pair inside the near radius is certainly listed.
+template <int MPT>
+__device__ __forceinline__ bool near_from_candidates(const KArgs &k, const Stage &s, const Near &near, int traj, const Mono (&mo)[MPT],
+                                                     const int (&idx)[MPT])
+{
+    const DevSys &a = k.a;
+    const int N = a.N;
+    bool ovf = false;
+#pragma unroll
+    for (int t = 0; t < MPT; t++) {
+        const int i = idx[t];
+        if (i >= N) continue;
+        int nn = 0;
+        if (!(mo[t].flags & MF_EXTRA)) {
+            const int nnc = a.ncandcnt[(size_t)traj * a.Npad + i];
+            const bool full = nnc == MD_NEAR_FULL;
+            const int n = full ? (int)a.candcnt[(size_t)traj * a.Npad + i] : nnc;
+            const uint16_t *cp = full ? a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i : a.ncand + (size_t)traj * MD_NCAND_CAPACITY * a.Npad + i;
+            const float x = mo[t].x, y = mo[t].y, z = mo[t].z;
+            const size_t row = a.Npad;
+            unsigned near_s = (unsigned)__cvta_generic_to_shared(near.list + i);
+            const unsigned near_end = near_s + (unsigned)(near.cap * N) * 2u, near_step = (unsigned)N * 2u;
+            for (int k0 = 0; k0 < n; k0 += MD_FILTER_BATCH, cp += MD_FILTER_BATCH * row) {
+                unsigned jj[MD_FILTER_BATCH];
+#pragma unroll
+                for (int u = 0; u < MD_FILTER_BATCH; u++) jj[u] = k0 + u < n ? (unsigned)cp[u * row] : 0u;
+#pragma unroll
+                for (int u = 0; u < MD_FILTER_BATCH; u++) {
+                    const float4 Pj = s.P((int)jj[u]);
+                    const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const bool innear = k0 + u < n && d2 < MD_NEAR_R2;
+                    if (innear && near_s < near_end) sts_u16(near_s, (unsigned short)(jj[u] | MD_NEAR_LJ_FLAG));
+                    near_s += innear ? near_step : 0u;
+                    nn += innear;
+                }
+            }
+        }
+        near.cnt[i] = (uint8_t)(nn > near.cap ? MD_NEAR_FULL : nn);
+        ovf |= nn > near.cap;
+    }
     return ovf;
 }
 
@@ -812,8 +906,10 @@ struct CandState {
 // handles fixed monomer f with the per-thread functions.
 template <int MPT>
 __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Near &near, CandState &cs, int traj,
-                                              const Mono (&mo)[MPT], const int (&idx)[MPT], unsigned ops, bool with_fixed)
+                                              const Mono (&mo)[MPT], const int (&idx)[MPT], unsigned ops, bool with_fixed,
+                                              bool lazy, bool &lj_exact)
 {
+    lj_exact = true; // set to false only on the lazy path below
     const DevSys &a = k.a;
     const int N = a.N;
     Mono fm[1];
@@ -868,11 +964,16 @@ __device__ __forceinline__ bool rebuild_lists(const KArgs &k, const Stage &s, Ne
         if (fi[0] < N) a.cpos[base + fi[0]] = make_float4(fm[0].x, fm[0].y, fm[0].z, 0.f);
         __syncthreads(); // candidate rows of the fixed monomers are read by other threads below
     }
-    if (filter_candidates<MPT>(k, s, near, traj, mo, idx, (ops & OP_REBUILD_LJ) != 0)) atomicAdd(a.stats + 3, 1ull);
+    lj_exact = !lazy;
+    if (lazy ? near_from_candidates<MPT>(k, s, near, traj, mo, idx)
+             : filter_candidates<MPT>(k, s, near, traj, mo, idx, (ops & OP_REBUILD_LJ) != 0))
+        atomicAdd(a.stats + 3, 1ull);
     if (ops & OP_REBUILD_BONDS) bonds_from_near<MPT>(k, s, near, traj, mo, idx);
     if (with_fixed) {
         const int nwarp = blockDim.x >> 5;
-        for (int f = threadIdx.x >> 5; f < a.n_fixed; f += nwarp) rebuild_row_cooperative(k, s, traj, (int)a.fmap[f], ops);
+        const unsigned fops = lazy ? (ops & ~(unsigned)OP_REBUILD_LJ) : ops;
+        if (fops)
+            for (int f = threadIdx.x >> 5; f < a.n_fixed; f += nwarp) rebuild_row_cooperative(k, s, traj, (int)a.fmap[f], fops);
     }
     return (ops & OP_REBUILD_LJ) != 0 || !k.p.lj_on;
 }
@@ -939,6 +1040,7 @@ __device__ __forceinline__ Near carve_near(float4 *smem, const KArgs &k, int N)
     near.list = reinterpret_cast<uint16_t *>(near.thi + near.ntiles);
     near.cnt = reinterpret_cast<uint8_t *>(near.list + (size_t)near.cap * N);
     near.ok = false;
+    near.stale_lj = false;
     near.topo = nullptr;
     return near;
 }
@@ -1016,6 +1118,8 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     for (int t = 0; t < MPT; t++) gx[t] = gy[t] = gz[t] = 0.f;
     const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
 
+    bool lazy = k.lazy != 0;              // list-update steps refresh only the near / bond lists (see KArgs::lazy)
+    bool stale = a.lj_stale[traj] != 0;   // the Verlet list in HBM predates the last list-update step
     int fixed_flags_dirty = 0; // stage buffers whose copy of a fixed monomer's GTP bit is stale
     bool gtp_changed = false;
     for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
@@ -1058,7 +1162,14 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                                 !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
         bool formed = false;
         if (do_rebuild) {
-            near_state = rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, rops, true) ? 1 : 2;
+            bool lj_exact;
+            near_state = rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, rops, true, lazy, lj_exact) ? 1 : 2;
+            stale = !lj_exact;
+            if (stale) { // the Verlet list of this step is (cand, these positions): written out only if someone asks
+#pragma unroll
+                for (int t = 0; t < MPT; t++)
+                    if (idx[t] < N) a.rpos[base + idx[t]] = make_float4(mo[t].x, mo[t].y, mo[t].z, 0.f);
+            }
             formed = true;
             if (near.topo) { // own rows were just rewritten by this thread
 #pragma unroll
@@ -1066,6 +1177,15 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                     if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
             }
         } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
+            if (stale) { // the refresh below reads the Verlet list: write it out now and stay exact for the rest of the launch
+                __syncthreads(); // rpos of the whole trajectory is in place
+#pragma unroll
+                for (int t = 0; t < MPT; t++)
+                    if (idx[t] < N) materialise_row(k, traj, idx[t]);
+                if ((int)threadIdx.x < a.n_fixed) materialise_row(k, traj, (int)a.fmap[threadIdx.x]);
+                stale = false;
+                lazy = false;
+            }
             if (refresh_near<MPT>(k, s, near, traj, mo, idx)) atomicAdd(a.stats + 3, 1ull);
             __syncthreads();
             near_state = 1;
@@ -1081,6 +1201,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
             }
         }
         near.ok = near.cap > 0 && near_state == 1;
+        near.stale_lj = stale;
 #pragma unroll
         for (int t = 0; t < MPT; t++) {
             if (idx[t] < N && !(mo[t].flags & (MF_EXTRA | MF_FIXED))) {
@@ -1118,6 +1239,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
         a.gtp[base + i] = a.gtp_sched[(size_t)slot * a.ntr * N + base + i] == 1 ? 1 : 0;
     }
     store_cand_state(a, cs, traj);
+    if (threadIdx.x == 0) a.lj_stale[traj] = stale ? 1 : 0;
 }
 
 /*
@@ -1152,12 +1274,21 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
         if (idx[t] < N) fr[t] = publish(s, idx[t], mo[t], ls);
     __syncthreads();
 
+    if ((k.ops & OP_MATERIALISE) && a.lj_stale[traj]) { // CTA-uniform
+#pragma unroll
+        for (int t = 0; t < MPT; t++)
+            if (idx[t] < N) materialise_row(k, traj, idx[t]);
+        __syncthreads(); // every thread has read the flag
+        if (threadIdx.x == 0) a.lj_stale[traj] = 0;
+    }
     if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) {
         CandState cs;
         cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
         cs.dirty = false;
-        rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, k.ops, false);
+        bool lj_exact;
+        rebuild_lists<MPT>(k, s, near, cs, traj, mo, idx, k.ops, false, false, lj_exact);
         store_cand_state(a, cs, traj);
+        if ((k.ops & OP_REBUILD_LJ) && threadIdx.x == 0) a.lj_stale[traj] = 0; // the list written above is current
     }
     near.ok = false;
 

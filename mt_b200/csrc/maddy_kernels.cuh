@@ -21,7 +21,8 @@ enum : unsigned {
     OP_FORCE = 4u,   // evaluate forces and store them (step-granular maddy_force)
     OP_ENERGY = 8u,  // per-monomer energies + per-trajectory reduction
     OP_RUN = 16u,    // fused multi-step loop
-    OP_TEA_EPS = 32u // TEA epsilon / C_i statistics (integrateTea_epsilon_unlisted)
+    OP_TEA_EPS = 32u, // TEA epsilon / C_i statistics (integrateTea_epsilon_unlisted)
+    OP_MATERIALISE = 64u // write the exact Verlet list of the last (lazy) list-update step of the fused loop
 };
 
 // status bits written by kernels
@@ -60,6 +61,10 @@ struct DevSys {
     unsigned long long *stats; // [4] list-maintenance events: near refresh on guard trip, candidate re-scan, all-pairs fallback, near overflow
     uint16_t *cand;    // [ntr][MD_CAND_CAPACITY][Npad] candidate list, k-major
     uint16_t *candcnt; // [ntr][Npad]
+    uint16_t *ncand;   // [ntr][MD_NCAND_CAPACITY][Npad] the candidates within MD_NEAR_R + MD_CAND_SKIN (subset of cand, same order)
+    uint8_t *ncandcnt; // [ntr][Npad]; MD_NEAR_FULL = more than the capacity: use cand
+    float4 *rpos;      // [n] positions at the last list-update step of the fused loop (what the Verlet list refers to)
+    int *lj_stale;     // [ntr] 1: lj/ljcnt predate that step; the exact rows follow from rpos + cand (materialise_row)
     float4 *cpos;      // [n] positions when the candidate list was built (.w unused)
     int *cand_valid;   // [ntr] 1 = cand/candcnt/cpos describe the current extra flags
     // TEA (bdhitea): per-bead sum of squared tensor rows (d_ci), per-bead epsilon sums, per-traj beta
@@ -86,6 +91,8 @@ struct DevSys {
 #define MD_CAND_SKIN 1.5f
 #define MD_CAND_GUARD2 0.5476f // 0.74^2 (< (MD_CAND_SKIN/2)^2)
 #define MD_CAND_CAPACITY 320
+#define MD_NCAND_CAPACITY 64
+#define MD_NCAND_R2 72.25f // (MD_NEAR_R + MD_CAND_SKIN)^2 = 8.5^2
 #define MD_NEAR_FULL 255 // near.cnt value of a monomer whose near list overflowed: it walks its full Verlet list instead
 #define MD_FILTER_BATCH 8 // candidate indices fetched per round trip in filter_candidates
 
@@ -114,6 +121,7 @@ struct KArgs {
     int near_cap;      // rows of the shared-memory near list (0: fast path disabled)
     int rng_smem_offset; // byte offset of the shared-memory RNG area (two-CTA shape only)
     int topo_smem_offset; // byte offset of the packed per-monomer topology words, or -1
+    int lazy;          // fused loop: list-update steps only refresh the near/bond lists; the exact Verlet list is materialised on demand
     float rcand2;      // squared candidate radius: (max(LJ pairs cut-off, near radius) + MD_CAND_SKIN)^2
     CutTest cut_pairs; // LJ list cut-off (ljpairscutoff)
     CutTest cut_force; // LJ force cut-off (6.0)

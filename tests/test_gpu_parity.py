@@ -401,6 +401,45 @@ def test_crowded_monomers_overflow_the_near_list_individually(rundir, load_syste
             assert lists_equal(*e.download_list(kind), *plain.download_list(kind))
 
 
+def test_lazy_verlet_list_equals_eager(rundir, load_system, monkeypatch):
+    """The fused loop only keeps the near / bond lists current and writes the 15-nm Verlet list of its last list-update
+    step when somebody reads it (download, energies, a window starting between two list-update steps, coordinate upload).
+    Everything observable must equal the eager build (MADDY_NO_LAZY)."""
+    s = load_system(rundir("mt40_ensemble", runnum=4), ["hydrolysis=no"])
+    lazy = Engine(s)
+    monkeypatch.setenv("MADDY_NO_LAZY", "1")
+    eager = Engine(s)
+    monkeypatch.delenv("MADDY_NO_LAZY")
+
+    def same(what):
+        assert np.array_equal(lazy.coords(), eager.coords()), what
+        assert lists_equal(*lazy.download_list(capi.LIST_LJ), *eager.download_list(capi.LIST_LJ)), what
+        assert lists_equal(*lazy.download_list(capi.LIST_LATERAL), *eager.download_list(capi.LIST_LATERAL)), what
+
+    for e in (lazy, eager):
+        e.run(0, 50)  # list-update steps 0, 20, 40: the list of step 40 is the one to be produced
+    same("after a window")
+    for e in (lazy, eager):
+        e.run(50, 95)  # starts between two list-update steps
+        e.run(145, 10)  # no list-update step inside
+    assert np.array_equal(lazy.energies(), eager.energies())
+    same("after windows that start off the list-update grid")
+    for e in (lazy, eager):
+        e.run(155, 30)
+        e.force()  # step-granular call on the lists of step 180
+    assert np.array_equal(lazy.forces(), eager.forces())
+    c = lazy.coords()
+    c[:, 100:110, :3] += 0.3
+    for e in (lazy, eager):
+        e.run(185, 20)  # list-update step 200 inside
+        e.upload_coords(c)  # the Verlet list keeps referring to the positions of step 200
+    same("after a coordinate upload")
+    for e in (lazy, eager):
+        e.run(205, 40)
+    same("end")
+    assert np.array_equal(lazy.rng_state(), eager.rng_state())
+
+
 def test_gtp_schedule_equals_explicit_uploads(rundir, load_system):
     """maddy_schedule_gtp: GTP states applied in-kernel at scheduled steps == maddy_upload_gtp between shorter windows."""
     s = load_system(rundir("mt40_ensemble", runnum=5), ["hydrolysis=no"])
