@@ -230,24 +230,41 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
         if (ncnt != MD_NEAR_FULL) {
             // shared-memory near list: the listed pairs that can be inside the 6-nm cut-off (see MD_NEAR_R2)
             // An entry outside the force cut-off (or not LJ-listed) gets the coefficient 0, which leaves the accumulators
-            // bit-for-bit unchanged; the rare fp64 tie-break of inside_cut is the only branch in the loop body.
+            // bit-for-bit unchanged, so the loop body has no branch.  A pair inside the +-1e-6 band around the exact
+            // threshold (practically never) is only noted; the sum is then redone with the fp64 tie-break.
             const int n = ncnt;
-            const uint16_t *nl = near.list + i;
+            const int16_t *nl = reinterpret_cast<const int16_t *>(near.list) + i; // bit 15 (LJ-listed) read as the sign
             const float lo = k.cut_force.lo, hi = k.cut_force.hi;
+            bool band = false;
             for (int kk = 0; kk < n; kk++) {
-                const unsigned e = nl[kk * a.N];
-                const float4 Pj = s.P(e & 0x7fffu);
+                const int e = nl[kk * a.N];
+                const float4 Pj = s.P(e & 0x7fff);
                 const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                bool in = sf < lo;
-                if (sf >= lo && sf <= hi) in = dist2_exact(dx, dy, dz) < k.cut_force.t;
-                in = in && (e & MD_NEAR_LJ_FLAG);
+                const bool in = sf < lo && e < 0;
+                band |= !(sf < lo) && sf <= hi;
                 const float inv = 1.0f / sf;
                 const float inv2 = inv * inv;
                 const float c = in ? amp * (6.0f * (inv2 * inv2)) : 0.0f; // 6 / dr^8
                 fx = fmaf(c, dx, fx);
                 fy = fmaf(c, dy, fy);
                 fz = fmaf(c, dz, fz);
+            }
+            if (band) {
+                fx = fy = fz = 0.f;
+                for (int kk = 0; kk < n; kk++) {
+                    const int e = nl[kk * a.N];
+                    const float4 Pj = s.P(e & 0x7fff);
+                    const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
+                    const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const bool in = e < 0 && inside_cut(k.cut_force, dx, dy, dz, sf);
+                    const float inv = 1.0f / sf;
+                    const float inv2 = inv * inv;
+                    const float c = in ? amp * (6.0f * (inv2 * inv2)) : 0.0f;
+                    fx = fmaf(c, dx, fx);
+                    fy = fmaf(c, dy, fy);
+                    fz = fmaf(c, dz, fz);
+                }
             }
         } else {
             const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
