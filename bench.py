@@ -45,8 +45,8 @@ UNIT = "monomer-steps/s"
 B_ALG = 352.0  # algorithmic bytes per monomer-step, intact lattice (BASELINE.md 3 / SURVEY.md 8d)
 B_ALG_TERMS = "64 state r/w + 64 RNG r/w + 4*(46+1) LJ list + 4*(4+3) bond lists + 8 flags"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (a 100-step fused window at 520 x 256) from the
-# `ncu --set full` capture summarised in profiles/r1_run_kernel_ncu_full.txt (35.6 MB read + 3.0 MB written)
-NCU_TRAFFIC_PER_LAUNCH = {("mt40_ensemble", 256, 100): 38.6e6}
+# `ncu --set full` capture summarised in profiles/r1_run_kernel_ncu_full.txt (32.8 MB read + 0.13 MB written)
+NCU_TRAFFIC_PER_LAUNCH = {("mt40_ensemble", 256, 100): 32.9e6}
 REF_NTR_LIMIT = 100
 
 
@@ -239,7 +239,7 @@ def run_own(args):
                              "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_PER_LAUNCH.get((args.workload, ntr_local, window)),
                              "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_run_kernel_ncu_full.txt)",
                              "algorithmic_bytes_per_launch": B_ALG * N * ntr_local * window, "peak_source": pk_src,
-                             "kernel": "maddy::run_kernel<1,2> (one fused window of `window_steps` MD steps per launch; 94.7 % of the kernel time of a step in the ncu launch list, profiles/r1_launches.csv)",
+                             "kernel": "maddy::run_kernel<1,2> (one fused window of `window_steps` MD steps per launch; 95 % of the kernel time of a step in the ncu launch list, profiles/r1_launches.csv)",
                              "algorithmic_bytes_per_monomer_step": B_ALG, "terms": B_ALG_TERMS,
                              "note": "state stays on-chip across the fused steps, so DRAM traffic is far below the algorithmic bytes; "
                                      "the binding limit is SM issue/latency (see profiles/)"},
