@@ -39,7 +39,8 @@ extern "C" {
 #define MADDY_ENERGY_TERMS 7      /* harm,long,lat,psi,fi,teta,lj (updater.cpp:35-36) */
 #define MADDY_ZERO_SENTINEL 999999 /* src/mt.h:35 (ZERO)                              */
 #define MADDY_LJ_CAPACITY 256     /* src/compute_cuda.cu:1076                         */
-#define MADDY_MAX_NTOT 3200       /* one-CTA-per-trajectory path: SMEM staging limit  */
+#define MADDY_MAX_NTOT 32767      /* bond codes are (index << 1 | sign) in 16 bits    */
+#define MADDY_MAX_NTOT_CTA 3200   /* above this a trajectory no longer fits one CTA's shared memory: wide path */
 
 /* status codes */
 #define MADDY_OK 0

@@ -28,6 +28,9 @@ cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st);
 cudaError_t launch_snapshot_kernel(const float4 *pos, const float4 *ang, float *out_mapped, size_t n_monomers, cudaStream_t st);
 cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
+cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
+cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
+cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
 } // namespace maddy
 
 using namespace maddy;
@@ -74,6 +77,7 @@ struct maddy_handle {
     CutTest cut_pairs, cut_force;
     std::string err;
     long long launches = 0;
+    bool wide = false;          // trajectories spread over many CTAs, stage in HBM (maddy_wide.cuh): N > MADDY_MAX_NTOT_CTA
     bool lazy = false;          // fused loop keeps the Verlet list lazily (see ensure_lj)
     bool lj_maybe_stale = false; // some trajectory's Verlet list may have to be materialised before it is read
     std::vector<void *> allocs;
@@ -227,6 +231,53 @@ static int sync_and_check(maddy_handle *h)
     return check_status(h);
 }
 
+// Wide path: the same operations as launch sequences over the whole GPU (maddy_wide.cuh).  A step-granular phase is
+// [publish -> phase]; a fused window is [publish, then per step: (rebuild at list-update steps) -> step], one launch per
+// step, the step kernel publishing the next step's stage itself.
+static cudaError_t wide_dispatch(maddy_handle *h, const KArgs &k)
+{
+    cudaStream_t st = h->stream;
+    cudaError_t e;
+    if (!(k.ops & OP_RUN)) {
+        KArgs kk = k;
+        kk.ops &= OP_REBUILD_LJ | OP_REBUILD_BONDS | OP_FORCE | OP_ENERGY; // nothing is ever lazy here: OP_MATERIALISE is a no-op
+        if (!kk.ops) return cudaSuccess;
+        if ((e = launch_wide_publish(kk, 0, st)) != cudaSuccess) return e;
+        h->launches += 1 + ((kk.ops & OP_ENERGY) ? 1 : 0);
+        return launch_wide_phase(kk, 0, st);
+    }
+    const maddy_params &p = h->p;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
+    KArgs ks = k, kr = k;
+    ks.ops = OP_FORCE;
+    kr.ops = rops;
+    int buf = 0;
+    if ((e = launch_wide_publish(ks, buf, st)) != cudaSuccess) return e;
+    for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
+        // scheduled hydrolysis event (maddy_schedule_gtp): the flags of this slot become current, the stage is re-published
+        if (k.sched_slots > 0 && step >= k.sched_first && (step - k.sched_first) % k.sched_period == 0) {
+            const long long slot = (step - k.sched_first) / k.sched_period;
+            if (slot < k.sched_slots) {
+                e = cudaMemcpyAsync(h->a.gtp, h->d_sched + (size_t)slot * n, n, cudaMemcpyDeviceToDevice, st);
+                if (e != cudaSuccess) return e;
+                if ((e = launch_wide_publish(ks, buf, st)) != cudaSuccess) return e;
+                h->launches++;
+            }
+        }
+        const bool do_rebuild = rops != 0 && step % p.ljpairsupdatefreq == 0 &&
+                                !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
+        if (do_rebuild) {
+            if ((e = launch_wide_phase(kr, buf, st)) != cudaSuccess) return e;
+            h->launches++;
+        }
+        if ((e = launch_wide_step(ks, buf, st)) != cudaSuccess) return e;
+        h->launches++;
+        buf ^= 1;
+    }
+    return cudaSuccess;
+}
+
 static int launch(maddy_handle *h, const KArgs &k)
 {
     CU(h, cudaSetDevice(h->p.device));
@@ -236,8 +287,9 @@ static int launch(maddy_handle *h, const KArgs &k)
         cudaEventCreate(&e1);
         cudaEventRecord(e0, h->stream);
     }
-    cudaError_t e = (k.ops & OP_RUN) ? launch_run_kernel(k, h->run.mpt, h->run.ctas, h->run.threads, h->run.smem, h->stream)
-                                     : launch_phase_kernel(k, h->phase.mpt, h->phase.threads, h->phase.smem, h->stream);
+    cudaError_t e = h->wide ? wide_dispatch(h, k)
+                    : (k.ops & OP_RUN) ? launch_run_kernel(k, h->run.mpt, h->run.ctas, h->run.threads, h->run.smem, h->stream)
+                                       : launch_phase_kernel(k, h->phase.mpt, h->phase.threads, h->phase.smem, h->stream);
     if (h->gpu_prof) {
         cudaEventRecord(e1, h->stream);
         h->prof_events.push_back({e0, e1});
@@ -368,7 +420,10 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         return fail(nullptr, MADDY_EINVAL, "maddy_create: abi_version %d, library has %d", par->abi_version, MADDY_ABI_VERSION);
     const int N = par->n_tot, ntr = par->n_tr_local;
     if (N <= 0 || N > MADDY_MAX_NTOT)
-        return fail(nullptr, MADDY_EINVAL, "maddy_create: n_tot=%d outside [1,%d] (one-CTA-per-trajectory path)", N, MADDY_MAX_NTOT);
+        return fail(nullptr, MADDY_EINVAL, "maddy_create: n_tot=%d outside [1,%d]", N, MADDY_MAX_NTOT);
+    const bool wide = N > MADDY_MAX_NTOT_CTA || getenv("MADDY_FORCE_WIDE") != nullptr;
+    if (wide && par->n_tr_local > 65535)
+        return fail(nullptr, MADDY_EINVAL, "maddy_create: the wide path takes at most 65535 trajectories per handle (%d asked)", par->n_tr_local);
     if (ntr <= 0 || par->traj_first < 0 || par->traj_first + ntr > par->n_tr)
         return fail(nullptr, MADDY_EINVAL, "maddy_create: bad shard [%d,%d) of %d trajectories", par->traj_first,
                     par->traj_first + ntr, par->n_tr);
@@ -446,6 +501,16 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             }
             return (int)(cap > 32 ? 32 : cap);
         };
+        h->wide = wide;
+        if (wide) {
+            // wide path (maddy_wide.cuh): one thread per monomer over many CTAs, stage in HBM, lists walked from HBM
+            h->phase = LaunchCfg();
+            h->run = LaunchCfg();
+            h->amap.resize(N);
+            for (int i = 0; i < N; i++) h->amap[i] = (uint16_t)i;
+            a.n_active = N;
+            a.n_fixed = 0;
+        } else {
         // (1) phase kernel (step-granular entry points): every monomer owns a thread, one stage buffer
         h->phase.mpt = (N + MD_MAX_THREADS - 1) / MD_MAX_THREADS;
         if (h->phase.mpt > MD_MAX_MPT) {
@@ -496,6 +561,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
                 layout(h->run, nbuf, best_cap(nbuf, topo ? (size_t)16 * N : 0, 200 * 1024), false, topo);
             }
         }
+        } // !wide
         h->cut_pairs = make_cut(par->ljpairscutoff);
         h->cut_force = make_cut(MD_LJ_FORCE_CUTOFF);
 
@@ -539,6 +605,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             pool_req(&a.tea_mf, n);
             pool_req(&a.tea_rf, n);
         }
+        if (wide) pool_req(&a.gstage, 8 * n);
         CK(pool_commit(h, reqs));
         CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.lj_stale, 0, (size_t)ntr * sizeof(int), h->stream));

@@ -118,7 +118,8 @@ __device__ __forceinline__ Frame publish(const Stage &s, int i, const Mono &m, c
 
 // ------------------------------------------------------------------ forces
 // Generalized force on monomer i (non-extra) from the staged trajectory.
-__device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, const Near &near, int traj, int i, const Mono &m,
+template <class S>
+__device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Near &near, int traj, int i, const Mono &m,
                                             const Frame &fr)
 {
     const maddy_params &p = k.p;
@@ -317,7 +318,8 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const Stage &s, cons
 // ------------------------------------------------------------------ energies (compute_cuda.cu:676-911)
 struct E7 { double harm, lng, lat, psi, fi, teta, lj; };
 
-__device__ __forceinline__ E7 monomer_energy(const KArgs &k, const Stage &s, int traj, int i, const Mono &m)
+template <class S>
+__device__ __forceinline__ E7 monomer_energy(const KArgs &k, const S &s, int traj, int i, const Mono &m)
 {
     const maddy_params &p = k.p;
     const DevSys &a = k.a;
@@ -438,7 +440,8 @@ struct BondOut {
     int nlong, nlat, status;
 };
 // bit0: longitudinal hit, bit1: lateral (i:p1, j:p2) hit, bit2: lateral (i:p2, j:p1) hit
-__device__ __forceinline__ unsigned bond_tests(const Stage &s, float xi, float yi, float zi, int type_i, int j, int hraw, const float4 &Pj,
+template <class S>
+__device__ __forceinline__ unsigned bond_tests(const S &s, float xi, float yi, float zi, int type_i, int j, int hraw, const float4 &Pj,
                                                const float4 &Ei, const float4 &L1i, const float4 &L2i)
 {
     const float4 Ej = s.E(j), L1j = s.L1(j), L2j = s.L2(j);
@@ -467,7 +470,8 @@ __device__ __forceinline__ unsigned bond_tests(const Stage &s, float xi, float y
 // longitudinal entries are stored as +j when harmonic < 0, -j otherwise; -0 == 0 loses its sign (compute_cuda.cu:588-592)
 __device__ __forceinline__ uint16_t long_code(int j, int hraw) { return (uint16_t)((j << 1) | ((hraw < 0 || j == 0) ? 0u : 1u)); }
 
-__device__ __forceinline__ void bond_candidates(const DevSys &a, const Stage &s, int i, int j, const Mono &m, int hraw, const float4 &Pj,
+template <class S>
+__device__ __forceinline__ void bond_candidates(const DevSys &a, const S &s, int i, int j, const Mono &m, int hraw, const float4 &Pj,
                                                 const float4 &Ei, const float4 &L1i, const float4 &L2i, BondOut &o)
 {
     const unsigned hit = bond_tests(s, m.x, m.y, m.z, MF_TYPE(m.flags), j, hraw, Pj, Ei, L1i, L2i);
@@ -562,8 +566,8 @@ __device__ __forceinline__ void rebuild_row_cooperative(const KArgs &k, const St
 // General path: one pass over ALL j for the MPT monomers of this thread (LJ Verlet list,
 // compute_cuda.cu:913-940, and bond lists).  Used by the step-granular entry points when the near
 // list is disabled and as the fallback when a near list overflows.
-template <int MPT>
-__device__ __forceinline__ void rebuild_lists_all_pairs(const KArgs &k, const Stage &s, int traj, const Mono (&mo)[MPT],
+template <int MPT, class S>
+__device__ __forceinline__ void rebuild_lists_all_pairs(const KArgs &k, const S &s, int traj, const Mono (&mo)[MPT],
                                                         const int (&idx)[MPT], unsigned ops)
 {
     const DevSys &a = k.a;
@@ -1429,6 +1433,10 @@ cudaError_t launch_phase_kernel(const KArgs &k, int mpt, int threads, size_t sme
     default: return cudaErrorInvalidValue;
     }
 }
+
+} // namespace maddy
+#include "maddy_wide.cuh"
+namespace maddy {
 
 // State read-back, device leg: float4 {x,y,z,-} + {fi,psi,theta,-} -> the boundary's AoS-7 record {x,y,z,fi,theta,psi,0}
 // (mt.h:63-71) in a device staging buffer; the PCIe leg is a plain copy on a second stream (maddy_snapshot_begin), so the

@@ -575,3 +575,118 @@ def test_checkpoint_restart_is_bit_exact(case, stride, over, rundir):
             b = mt_b200.read_dcd(d_part / "dcd" / f"run_{t}{suffix}")
             assert a.shape[0] == 400 // stride and np.array_equal(a, b)
     assert (d_full / "mt_len.dat").read_text() == (d_part / "mt_len.dat").read_text()
+
+
+# ------------------------------------------------------------------ wide path (N > MADDY_MAX_NTOT_CTA, maddy_wide.cuh)
+@pytest.mark.parametrize("case,ntr,over,structure", [
+    ("mt40_ensemble", 3, ["hydrolysis=no"], None),
+    ("mt120_disassembly", 2, ["hydrolysis=no"], None),
+    ("mt120_constconc", 2, ["hydrolysis=no"], None),
+    ("cylinder_tea", 3, ["hydrolysis=no", "tea_on=no"], ("free", 120, 14.0, 60.0, 5)),
+])
+def test_wide_path_equals_cta_path_bitwise(case, ntr, over, structure, rundir, load_system, monkeypatch):
+    """The many-CTAs-per-trajectory path (stage in HBM, one launch per step) runs the device functions of the
+    one-CTA path: on a system both can take, everything observable is bit-identical."""
+    d = rundir(case, structure=structure, runnum=ntr) if structure else rundir(case, runnum=ntr)
+    s = load_system(d, over)
+    monkeypatch.setenv("MADDY_FORCE_WIDE", "1")
+    wide = Engine(s)
+    monkeypatch.delenv("MADDY_FORCE_WIDE")
+    cta = Engine(s)
+    kinds = (capi.LIST_LJ, capi.LIST_LONGITUDINAL, capi.LIST_LATERAL)
+
+    def same(what):
+        assert np.array_equal(wide.coords(), cta.coords()), what
+        assert np.array_equal(wide.rng_state(), cta.rng_state()), what
+        for kind in kinds:
+            assert lists_equal(*wide.download_list(kind), *cta.download_list(kind)), (what, kind)
+
+    for e in (wide, cta):
+        rebuild(e, s)
+        e.force()
+    assert np.array_equal(wide.forces(), cta.forces())
+    same("step-granular rebuild")
+    (wt, wm), (ct, cm) = wide.energies(per_monomer=True), cta.energies(per_monomer=True)
+    assert np.array_equal(wm, cm)
+    assert np.allclose(wt, ct, rtol=1e-13, atol=1e-9)  # the per-trajectory sums are reduced in a different order
+    for e in (wide, cta):
+        e.integrate()
+        e.run(1, 44)   # list-update steps 20 and 40 inside
+    same("window")
+    for e in (wide, cta):
+        e.run(45, 35, skip_first_rebuild=True)
+        e.force()
+    assert np.array_equal(wide.forces(), cta.forces())
+    same("second window")
+    wt, ct = wide.rebuild_and_energies(), cta.rebuild_and_energies()
+    assert np.allclose(wt, ct, rtol=1e-13, atol=1e-9)
+    same("rebuild + energies")
+    rng = np.random.default_rng(3)
+    g = [(rng.random((ntr, s.Ntot // 2)) > p).astype(np.int32).repeat(2, axis=1) for p in (0.2, 0.6)]
+    for e in (wide, cta):
+        e.schedule_gtp(90, 15, np.stack(g))
+        e.run(80, 40)
+    same("scheduled GTP flags")
+    assert np.allclose(wide.energies(), cta.energies(), rtol=1e-13, atol=1e-9)
+    assert wide.launches > cta.launches
+
+
+def test_wide_large_lattice_against_oracle(rundir, load_system):
+    """BASELINE config 5's 'large-N single system' (synthetic: the make_mt.py lattice, 13 x 400 = 5200 monomers):
+    beyond one CTA's shared memory, so it runs on the wide path.  Lists bit-exact, forces / energies / a 25-step window
+    against the CPU oracle."""
+    d = rundir("mt40_single", structure=("lattice", 400, 3), runnum=1)
+    s = load_system(d, ["hydrolysis=no"])
+    assert s.Ntot == 5200
+    rng = np.random.default_rng(5)
+    c0 = s.coords.copy()
+    c0[..., :3] += rng.normal(0, 0.05, c0[..., :3].shape).astype(np.float32)
+    c0[..., 3:6] += rng.normal(0, 0.02, c0[..., 3:6].shape).astype(np.float32)
+    e = Engine(s, coords=c0)
+    o = oracle_for(s)
+    o.coords[:] = e.coords()
+    rebuild(e, s)
+    o.rebuild_lj()
+    o.rebuild_bonds()
+    assert lists_equal(*e.download_list(capi.LIST_LJ), o.lj_count, o.lj)
+    assert lists_equal(*e.download_list(capi.LIST_LONGITUDINAL), o.long_count, o.long)
+    assert lists_equal(*e.download_list(capi.LIST_LATERAL), o.lat_count, o.lat)
+    e.force()
+    F, OF = e.forces(), o.force()
+    assert np.allclose(F[..., :6], OF[..., :6], rtol=1e-4, atol=2e-2), np.abs(F - OF).max()
+    et, em = e.energies(per_monomer=True)
+    oe = o.energies()
+    assert np.allclose(em[..., [0, 1, 2, 6]], oe[..., [0, 1, 2, 6]], rtol=1e-5, atol=2e-4)
+    assert np.allclose(em[..., 3:6], oe[..., 3:6], rtol=1e-4, atol=1e-2)
+    assert np.allclose(et, em.sum(axis=1), rtol=1e-12)
+    e.run(0, 25, skip_first_rebuild=True)
+    o.run(0, 25, skip_first_rebuild=True)
+    assert np.array_equal(e.rng_state(), o.rng)
+    c = e.coords()
+    assert np.abs(c[..., :3] - o.coords[..., :3]).max() < 2e-3 and np.abs(c[..., 3:6] - o.coords[..., 3:6]).max() < 2e-3
+    assert lists_equal(*e.download_list(capi.LIST_LJ), o.lj_count, o.lj)
+
+
+def test_wide_large_tea_system_against_oracle(rundir, load_system):
+    """TEA hydrodynamics on a single large system (synthetic free dimers, 26 seed + 2 x 1650 = 3326 beads > one CTA): force from
+    the wide path, the warp-per-bead TEA kernels, against the oracle's sequential restatement."""
+    d = rundir("cylinder_tea", structure=("free", 1650, 60.0, 320.0, 7), runnum=1, steps=100, stride=100000)
+    s = load_system(d, ["hydrolysis=no"])
+    assert s.Ntot == 3326 and s.par.tea_on
+    e = Engine(s)
+    o = oracle_for(s)
+    for step in range(0, 6):
+        if step % s.par.ljpairsupdatefreq == 0:
+            rebuild(e, s)
+            o.rebuild_lj()
+            o.rebuild_bonds()
+        e.force()
+        o.force()
+        e.tea_update(step)
+        if step % s.par.tea_epsilon_freq == 0:
+            o.tea_update()
+        e.tea_integrate()
+        o.tea_integrate()
+    assert np.array_equal(e.rng_state(), o.rng)
+    c = e.coords()
+    assert np.abs(c[..., :3] - o.coords[..., :3]).max() < 1e-3 and np.abs(c[..., 3:6] - o.coords[..., 3:6]).max() < 1e-3
