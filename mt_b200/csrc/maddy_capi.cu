@@ -606,6 +606,8 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             pool_req(&a.tea_rf, n);
         }
         if (wide) pool_req(&a.gstage, 8 * n);
+        if (wide && !getenv("MADDY_WIDE_ALL_PAIRS")) // WGrid header + count/start/cursor[32768] + members[Npad] per trajectory (maddy_wide.cuh)
+            pool_req(reinterpret_cast<char **>(&a.wgrid), (size_t)ntr * (64 + (size_t)3 * 32768 * 4 + (size_t)a.Npad * 2));
         CK(pool_commit(h, reqs));
         CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.lj_stale, 0, (size_t)ntr * sizeof(int), h->stream));
@@ -726,14 +728,31 @@ extern "C" int maddy_integrate(maddy_handle *h)
     return MADDY_OK;
 }
 
+extern "C" int maddy_tea_update(maddy_handle *h, long long step);
+extern "C" int maddy_tea_integrate(maddy_handle *h);
 extern "C" int maddy_run(maddy_handle *h, long long first_step, long long n_steps, unsigned flags)
 {
     if (!h || n_steps < 0) return MADDY_EINVAL;
     if (n_steps == 0) return MADDY_OK;
-    if (h->p.tea_on) return fail(h, MADDY_EINVAL, "maddy_run: fused TEA loop not available; use the step-granular TEA entry points");
     const long long freq = h->p.ljpairsupdatefreq > 0 ? h->p.ljpairsupdatefreq : 1;
     const bool rebuilds = h->p.lj_on || h->p.is_assembly;
     const bool skip_first = (flags & MADDY_RUN_SKIP_FIRST_REBUILD) != 0;
+    if (h->p.tea_on) {
+        // TEA window: the step is a chain of GPU-wide launches (force -> [epsilon/beta] -> prepare -> pair kernel), queued
+        // here back to back; the only host round trip is the capricious check every tea_epsilon_freq steps.
+        for (long long step = first_step; step < first_step + n_steps; step++) {
+            int rc = MADDY_OK;
+            if (rebuilds && step % freq == 0 && !(step == first_step && skip_first)) {
+                h->lj_maybe_stale = false;
+                rc = launch(h, kargs(h, (h->p.lj_on ? OP_REBUILD_LJ : 0u) | (h->p.is_assembly ? OP_REBUILD_BONDS : 0u)));
+            }
+            if (!rc) rc = maddy_force(h);
+            if (!rc) rc = maddy_tea_update(h, step);
+            if (!rc) rc = maddy_tea_integrate(h);
+            if (rc) return rc;
+        }
+        return MADDY_OK;
+    }
     if (!(rebuilds && first_step % freq == 0 && !skip_first)) { // the window starts from the lists as they stand
         int rc = ensure_lj(h);
         if (rc) return rc;

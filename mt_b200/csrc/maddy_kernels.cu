@@ -35,6 +35,7 @@ extern __shared__ float4 g_smem[];
 // neighbours then spreads over all banks; a monomer-major layout was measured 4x worse in bank conflicts).
 //   P: x, y, z, fi     E: r_mon*e3, psi     L1: R*p1, theta     L2: R*p2, flag bits (mon_type | gtp<<8 | ontub<<9 | extra<<10)
 struct Stage {
+    static constexpr bool kGlobal = false;
     int oP, oE, oL1, oL2; // float4 indices into g_smem
     __device__ __forceinline__ float4 &P(int j) const { return g_smem[oP + j]; }
     __device__ __forceinline__ float4 &E(int j) const { return g_smem[oE + j]; }
@@ -276,6 +277,31 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
                 lj = all ? a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i : a.ncand + (size_t)traj * MD_NCAND_CAPACITY * a.Npad + i;
                 n = all ? (int)a.candcnt[(size_t)traj * a.Npad + i] : nnc;
             }
+            if (S::kGlobal) {
+                // stage in HBM/L2 (wide path): every load is an L2 round trip, so fetch 16 indices, then their 16 positions,
+                // then accumulate in list order (same arithmetic, same order: only the number of dependent trips changes)
+                for (int k0 = 0; k0 < n; k0 += 16) {
+                    int jv[16];
+                    float4 Pv[16];
+#pragma unroll
+                    for (int q = 0; q < 16; q++) jv[q] = k0 + q < n ? (int)lj[(size_t)(k0 + q) * a.Npad] : -1;
+#pragma unroll
+                    for (int q = 0; q < 16; q++) Pv[q] = s.P(jv[q] < 0 ? i : jv[q]);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float dx = xi - Pv[q].x, dy = yi - Pv[q].y, dz = zi - Pv[q].z;
+                        const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (jv[q] >= 0 && inside_cut(k.cut_force, dx, dy, dz, sf)) {
+                            const float inv = 1.0f / sf;
+                            const float inv2 = inv * inv;
+                            const float c = amp * (6.0f * (inv2 * inv2)); // 6 / dr^8
+                            fx = fmaf(c, dx, fx);
+                            fy = fmaf(c, dy, fy);
+                            fz = fmaf(c, dz, fz);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 4
             for (int kk = 0; kk < n; kk++) {
                 const int j = lj[(size_t)kk * a.Npad];
@@ -290,6 +316,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
                     fy = fmaf(c, dy, fy);
                     fz = fmaf(c, dz, fz);
                 }
+            }
             }
         }
         f.x += fx;

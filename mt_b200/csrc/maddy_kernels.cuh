@@ -73,6 +73,7 @@ struct DevSys {
     float *tea_beta;
     float4 *tea_co, *tea_mf, *tea_rf; // per-step snapshots: coordinates (+extra in .w), molecular force, random force
     float4 *gstage; // wide path only (maddy_wide.cuh): [2][4][ntr*N] stage in HBM, or nullptr
+    void *wgrid;    // wide path only: per-trajectory cell grid of the list rebuild (see wcells_at), or nullptr
 };
 
 // Near list (shared memory, fused loop only): all j != i with centre distance < MD_NEAR_R at the last

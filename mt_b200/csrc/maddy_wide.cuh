@@ -9,7 +9,8 @@
  *
  *   stage in HBM: [2 buffers][P,E,L1,L2][ntr*N] float4 (64 B per monomer and buffer; 5200 monomers = 333 KB, L2-resident)
  *   wide_publish_kernel   state -> stage[buf]                                (before a step-granular phase, once per window)
- *   wide_phase_kernel     rebuild / force / energy from stage[buf]           (compute_cuda.cu:913-940, :527-674, :32-525, :676-911)
+ *   wide_grid/count/scan/fill/rebuild_kernel   cell grid + sorted gather: the list rebuild in O(N)       (compute_cuda.cu:913-940, :527-674)
+ *   wide_phase_kernel     force / energy from stage[buf]                     (compute_cuda.cu:32-525, :676-911)
  *   wide_step_kernel      force from stage[buf] -> integrate -> state + stage[buf^1]: ONE launch per step
  *                         (replaces compute_kernel + integrate_kernel + 2 cudaDeviceSynchronize, compute_cuda.cu:1228-1238)
  *   wide_reduce_kernel    per-trajectory energy sums (OutputAllEnergies, updater.cpp:3-43)
@@ -21,6 +22,7 @@ namespace maddy {
 #define WIDE_THREADS 128
 
 struct GStage { // read side: the buffer is read-only for the lifetime of the kernel that reads it (ld.global.nc)
+    static constexpr bool kGlobal = true;
     const float4 *p, *e, *l1, *l2;
     __device__ __forceinline__ float4 P(int j) const { return __ldg(p + j); }
     __device__ __forceinline__ float4 E(int j) const { return __ldg(e + j); }
@@ -70,6 +72,236 @@ __device__ __forceinline__ Near no_near()
     return near;
 }
 
+// ---- cell grid for the list rebuild (per trajectory, rebuilt with the lists).  Cells are at least WIDE_CELL_MARGIN x
+// the search radius wide, so every partner of a monomer sits in the 27 cells around its own; the members of those cells
+// inside the radius are gathered, SORTED (the reference's lists are in ascending j, compute_cuda.cu:913-940) and then put
+// through the very statements of rebuild_lists_all_pairs.  O(N) per rebuild instead of O(N^2), whatever the index order
+// of the structure (a lattice is index-coherent, free dimers in a cylinder are not).
+#define WIDE_MAX_CELLS 32768
+#define WIDE_AXIS_CELLS 128
+#define WIDE_CELL_MARGIN 1.001f
+#define WIDE_GATHER_CAP 320 // partners inside the radius: the Verlet list holds at most 256 of them (more is MADDY_EOVERFLOW anyway)
+struct WGrid {
+    float ox, oy, oz, ihx, ihy, ihz;
+    int nx, ny, nz, ncells;
+};
+// per trajectory: WGrid header (64 B), then unsigned count[WIDE_MAX_CELLS], start[WIDE_MAX_CELLS], cursor[WIDE_MAX_CELLS], then uint16 members[Npad]
+__device__ __forceinline__ size_t wgrid_stride(const DevSys &a) { return 64 + (size_t)3 * WIDE_MAX_CELLS * 4 + (size_t)a.Npad * 2; }
+struct WCells {
+    WGrid *g;
+    unsigned *count, *start, *cursor;
+    uint16_t *members;
+};
+__device__ __forceinline__ WCells wcells_at(const DevSys &a, int traj)
+{
+    char *b = reinterpret_cast<char *>(a.wgrid) + (size_t)traj * wgrid_stride(a);
+    WCells c;
+    c.g = reinterpret_cast<WGrid *>(b);
+    c.count = reinterpret_cast<unsigned *>(b + 64);
+    c.start = c.count + WIDE_MAX_CELLS;
+    c.cursor = c.start + WIDE_MAX_CELLS;
+    c.members = reinterpret_cast<uint16_t *>(c.cursor + WIDE_MAX_CELLS);
+    return c;
+}
+__device__ __forceinline__ float search_radius2(const KArgs &k, unsigned ops)
+{
+    return fmaxf((ops & OP_REBUILD_LJ) ? k.cut_pairs.hi : 0.f, (ops & OP_REBUILD_BONDS) ? MD_BOND_PREFILTER2 : 0.f) * 1.00001f;
+}
+__device__ __forceinline__ int cell_coord(float x, float o, float ih, int n)
+{
+    return min(n - 1, max(0, (int)((x - o) * ih)));
+}
+
+// (1) bounding box of the trajectory -> grid geometry; clears the counts.  One CTA per trajectory.
+__global__ void __launch_bounds__(256) wide_grid_kernel(const __grid_constant__ KArgs k, int buf)
+{
+    __shared__ float red[6][8];
+    __shared__ WGrid sg;
+    const DevSys &a = k.a;
+    const int traj = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 *P = gstage_array(a, buf, 0) + (size_t)traj * a.N;
+    const float inf = __int_as_float(0x7f800000);
+    float v[6] = {inf, inf, inf, inf, inf, inf}; // min x,y,z and min of the negated coordinates
+    for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
+        const float4 p = P[j];
+        v[0] = fminf(v[0], p.x); v[1] = fminf(v[1], p.y); v[2] = fminf(v[2], p.z);
+        v[3] = fminf(v[3], -p.x); v[4] = fminf(v[4], -p.y); v[5] = fminf(v[5], -p.z);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] = fminf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+        if (lane == 0) red[q][warp] = v[q];
+    }
+    __syncthreads();
+    const WCells c = wcells_at(a, traj);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 6; q++)
+            for (int w = 1; w < 8; w++) red[q][0] = fminf(red[q][0], red[q][w]);
+        const float h = sqrtf(search_radius2(k, k.ops)) * WIDE_CELL_MARGIN;
+        const float ext[3] = {-red[3][0] - red[0][0], -red[4][0] - red[1][0], -red[5][0] - red[2][0]};
+        int n[3];
+        for (int q = 0; q < 3; q++) n[q] = min(WIDE_AXIS_CELLS, (int)(ext[q] / h) + 1);
+        while ((long long)n[0] * n[1] * n[2] > WIDE_MAX_CELLS) { // coarsen the axis with the most cells
+            const int q = n[0] >= n[1] && n[0] >= n[2] ? 0 : (n[1] >= n[2] ? 1 : 2);
+            n[q] = (n[q] + 1) / 2;
+        }
+        WGrid g;
+        g.ox = red[0][0]; g.oy = red[1][0]; g.oz = red[2][0];
+        // cell width = max(h, extent / n): never below the margin-widened radius
+        g.ihx = 1.0f / fmaxf(h, ext[0] / (float)n[0] * WIDE_CELL_MARGIN);
+        g.ihy = 1.0f / fmaxf(h, ext[1] / (float)n[1] * WIDE_CELL_MARGIN);
+        g.ihz = 1.0f / fmaxf(h, ext[2] / (float)n[2] * WIDE_CELL_MARGIN);
+        g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+        g.ncells = n[0] * n[1] * n[2];
+        sg = g;
+        *c.g = g;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < sg.ncells; q += blockDim.x) c.count[q] = 0;
+}
+__device__ __forceinline__ int cell_of(const WGrid &g, const float4 &p)
+{
+    return (cell_coord(p.z, g.oz, g.ihz, g.nz) * g.ny + cell_coord(p.y, g.oy, g.ihy, g.ny)) * g.nx + cell_coord(p.x, g.ox, g.ihx, g.nx);
+}
+// (2) members per cell
+__global__ void __launch_bounds__(256) wide_count_kernel(const __grid_constant__ KArgs k, int buf)
+{
+    const DevSys &a = k.a;
+    const int traj = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.N) return;
+    const WCells c = wcells_at(a, traj);
+    atomicAdd(c.count + cell_of(*c.g, gstage_array(a, buf, 0)[(size_t)traj * a.N + j]), 1u);
+}
+// (3) exclusive scan of the counts.  One CTA of 1024 threads per trajectory, 32 cells per thread at most.
+__global__ void __launch_bounds__(1024) wide_scan_kernel(const __grid_constant__ KArgs k)
+{
+    __shared__ unsigned wsum[32];
+    const DevSys &a = k.a;
+    const WCells c = wcells_at(a, blockIdx.x);
+    const int ncells = c.g->ncells;
+    const int per = (ncells + 1023) / 1024;
+    const int q0 = threadIdx.x * per, q1 = min(ncells, q0 + per);
+    unsigned s = 0;
+    for (int q = q0; q < q1; q++) s += c.count[q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = wsum[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        wsum[lane] = winc - w;
+    }
+    __syncthreads();
+    unsigned run = wsum[warp] + inc - s;
+    for (int q = q0; q < q1; q++) {
+        c.start[q] = run;
+        c.cursor[q] = run;
+        run += c.count[q];
+    }
+}
+// (4) member lists (order inside a cell is whatever the atomics give: the gather sorts)
+__global__ void __launch_bounds__(256) wide_fill_kernel(const __grid_constant__ KArgs k, int buf)
+{
+    const DevSys &a = k.a;
+    const int traj = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.N) return;
+    const WCells c = wcells_at(a, traj);
+    const unsigned slot = atomicAdd(c.cursor + cell_of(*c.g, gstage_array(a, buf, 0)[(size_t)traj * a.N + j]), 1u);
+    c.members[slot] = (uint16_t)j;
+}
+
+// (5) the rebuild proper: gather from the 27 cells, sort ascending, then the statements of rebuild_lists_all_pairs
+// (LJ_kernel compute_cuda.cu:913-940, pairs_kernel :527-674) on the survivors only.
+__global__ void __launch_bounds__(WIDE_THREADS) wide_rebuild_kernel(const __grid_constant__ KArgs k, int buf)
+{
+    const DevSys &a = k.a;
+    const int N = a.N;
+    const int traj = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t base = (size_t)traj * N;
+    const GStage s = gstage_at(a, buf, traj);
+    const unsigned ops = k.ops;
+    const bool do_lj = (ops & OP_REBUILD_LJ) != 0;
+    const bool do_b = (ops & OP_REBUILD_BONDS) != 0;
+    Mono m;
+    load_mono(a, base, i, m);
+    uint16_t *ljb = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad;
+    int status = 0, nlj = 0;
+    BondOut bo;
+    bo.col = a.bl + (size_t)traj * (a.capLong + a.capLat) * a.Npad + i;
+    bo.nlong = bo.nlat = bo.status = 0;
+    if (!(m.flags & MF_EXTRA)) {
+        const WCells c = wcells_at(a, traj);
+        const WGrid g = *c.g;
+        const float rc2 = search_radius2(k, ops);
+        const float x = m.x, y = m.y, z = m.z;
+        uint16_t found[WIDE_GATHER_CAP];
+        int nf = 0;
+        const int cx = cell_coord(x, g.ox, g.ihx, g.nx), cy = cell_coord(y, g.oy, g.ihy, g.ny), cz = cell_coord(z, g.oz, g.ihz, g.nz);
+        for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.nz - 1); zz++)
+            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); yy++) {
+                // the cells x-1..x+1 of a row are contiguous in memory, and so are their member ranges
+                const int q0 = (zz * g.ny + yy) * g.nx + max(cx - 1, 0), q1 = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
+                const unsigned m0 = c.start[q0], m1 = c.start[q1] + c.count[q1];
+                for (unsigned q = m0; q < m1; q++) {
+                    const int j = c.members[q];
+                    const float4 Pj = s.P(j);
+                    const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
+                    const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (sf <= rc2 && j != i) {
+                        if (nf < WIDE_GATHER_CAP) found[nf] = (uint16_t)j;
+                        else status |= do_lj ? ST_LJ_OVERFLOW : ST_LAT_OVERFLOW;
+                        nf = min(nf + 1, WIDE_GATHER_CAP);
+                    }
+                }
+            }
+        for (int q = 1; q < nf; q++) { // insertion sort (a few dozen entries, thread-local)
+            const uint16_t v = found[q];
+            int r = q - 1;
+            while (r >= 0 && found[r] > v) {
+                found[r + 1] = found[r];
+                r--;
+            }
+            found[r + 1] = v;
+        }
+        const int hraw = a.harm[a.maxH * i]; // first entry, whatever harmonicCount says (compute_cuda.cu:548)
+        const int hp = hraw < 0 ? -hraw : hraw;
+        const float4 Ei = s.E(i), L1i = s.L1(i), L2i = s.L2(i);
+        for (int q = 0; q < nf; q++) {
+            const int j = found[q];
+            const float4 Pj = s.P(j);
+            const float dx = x - Pj.x, dy = y - Pj.y, dz = z - Pj.z;
+            const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (do_lj && inside_cut(k.cut_pairs, dx, dy, dz, sf)) {
+                if (nlj < MADDY_LJ_CAPACITY) ljb[(size_t)nlj * a.Npad + i] = (uint16_t)j;
+                else status |= ST_LJ_OVERFLOW;
+                nlj++;
+            }
+            if (do_b && sf < MD_BOND_PREFILTER2 && hp != j) bond_candidates(a, s, i, j, m, hraw, Pj, Ei, L1i, L2i, bo);
+        }
+    }
+    if (do_lj) a.ljcnt[(size_t)traj * a.Npad + i] = (uint16_t)min(nlj, MADDY_LJ_CAPACITY);
+    if (do_b) {
+        uint8_t *bc = a.bcnt + (size_t)traj * 2 * a.Npad + i;
+        bc[0] = (uint8_t)min(bo.nlong, a.capLong);
+        bc[a.Npad] = (uint8_t)min(bo.nlat, a.capLat);
+    }
+    status |= bo.status;
+    if (status) atomicOr(a.status, status);
+}
+
 __global__ void __launch_bounds__(256) wide_publish_kernel(const __grid_constant__ KArgs k, int buf)
 {
     const DevSys &a = k.a;
@@ -101,8 +333,9 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_phase_kernel(const __grid_c
     mo[0].flags = MF_EXTRA | MF_FIXED;
     if (i < N) load_mono(a, base, i, mo[0]);
 
-    if (k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) rebuild_lists_all_pairs<1>(k, s, traj, mo, idx, k.ops);
     if (i >= N) return;
+    if ((k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) && !a.wgrid)
+        rebuild_lists_all_pairs<1>(k, s, traj, mo, idx, k.ops); // MADDY_WIDE_ALL_PAIRS=1 (test hook): O(N^2) scan
 
     if ((k.ops & OP_FORCE) && !(mo[0].flags & MF_EXTRA)) {
         F3 e, l1, l2;
@@ -178,6 +411,15 @@ cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st)
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st)
 {
     const dim3 grid((k.a.N + WIDE_THREADS - 1) / WIDE_THREADS, k.a.ntr);
+    if ((k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) && k.a.wgrid) {
+        const dim3 mgrid((k.a.N + 255) / 256, k.a.ntr);
+        wide_grid_kernel<<<k.a.ntr, 256, 0, st>>>(k, buf);
+        wide_count_kernel<<<mgrid, 256, 0, st>>>(k, buf);
+        wide_scan_kernel<<<k.a.ntr, 1024, 0, st>>>(k);
+        wide_fill_kernel<<<mgrid, 256, 0, st>>>(k, buf);
+        wide_rebuild_kernel<<<grid, WIDE_THREADS, 0, st>>>(k, buf);
+        if (!(k.ops & (OP_FORCE | OP_ENERGY))) return cudaGetLastError();
+    }
     wide_phase_kernel<<<grid, WIDE_THREADS, 0, st>>>(k, buf);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

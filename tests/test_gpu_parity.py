@@ -687,6 +687,26 @@ def test_wide_large_tea_system_against_oracle(rundir, load_system):
             o.tea_update()
         e.tea_integrate()
         o.tea_integrate()
+    assert lists_equal(*e.download_list(capi.LIST_LJ), o.lj_count, o.lj)  # free dimers: the cell-grid rebuild, unordered input
+    assert lists_equal(*e.download_list(capi.LIST_LATERAL), o.lat_count, o.lat)
     assert np.array_equal(e.rng_state(), o.rng)
     c = e.coords()
     assert np.abs(c[..., :3] - o.coords[..., :3]).max() < 1e-3 and np.abs(c[..., 3:6] - o.coords[..., 3:6]).max() < 1e-3
+
+
+def test_tea_window_equals_step_granular_calls(rundir, load_system):
+    """maddy_run with tea_on queues the step-granular TEA launches itself: same results as the explicit call sequence."""
+    d = rundir("cylinder_tea", runnum=3, steps=100, stride=100000)
+    s = load_system(d, ["hydrolysis=no", "tea_epsilon_freq=15"])
+    a, b = Engine(s), Engine(s)
+    freq = s.par.ljpairsupdatefreq
+    for step in range(0, 47):
+        if step % freq == 0:
+            rebuild(a, s)
+        a.force()
+        a.tea_update(step)
+        a.tea_integrate()
+    b.run(0, 30)
+    b.run(30, 17)
+    assert np.array_equal(a.coords(), b.coords()) and np.array_equal(a.rng_state(), b.rng_state())
+    assert lists_equal(*a.download_list(capi.LIST_LJ), *b.download_list(capi.LIST_LJ))

@@ -23,13 +23,13 @@ def main():
         side = (size / 247.0) ** (1.0 / 3.0)
         workspace.make_rundir(d, ("free", size, 30.0 * side, 160.0 * side, 1), dict(spec["config"], runnum=ntr), None, spec["conditions"])
     with workspace.chdir(d):
-        s = HostSystem("config.conf", ["hydrolysis=no"] + sys.argv[5:])
+        s = HostSystem("config.conf", ["hydrolysis=no"] + [x for x in sys.argv[5:] if not x.startswith("--")])
     e = Engine(s)
     print(f"N={s.Ntot} Ntr={s.Ntr} tea={bool(s.par.tea_on)}")
     freq = s.par.ljpairsupdatefreq
 
     def window(first, n):
-        if not s.par.tea_on:
+        if not s.par.tea_on or "--window" in sys.argv:
             e.run(first, n)
             return
         for step in range(first, first + n):
