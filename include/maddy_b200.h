@@ -210,6 +210,27 @@ int maddy_upload_rng(maddy_handle *h, const unsigned *state);
  * back to the all-pairs path, out[3] near-list overflows.  (The lists themselves are exact on every path.) */
 int maddy_list_stats(maddy_handle *h, unsigned long long out[4], int reset);
 
+/* ---- in-situ analysis: the reference's offline DCD post-processing tools as reductions over the state
+ * already on the device, so a run needs no DCD round trip for them.  All of them read the CURRENT state of the handle.
+ *
+ * maddy_analysis_setup: per-monomer PDB labels of the structure (shared by all trajectories): chain index
+ *   (chain - 'A', or -1 for atoms outside the protofilaments, e.g. the reserve chain 'X'), residue number and the
+ *   second character of the atom name ('A' / 'B' of CA / CB); n_pf protofilaments (pf_number, disc.cpp:12).
+ * maddy_analysis_reference: the state becomes the "previous frame" of the displacement statistics.
+ * maddy_analysis_temperature: scripts/temp_calc/main.cpp:70-92 between the previous frame and the current state, then
+ *   the current state becomes the previous frame.  sums[traj][8] = raw sums over the monomers
+ *   {dx2+dy2+dz2, dfi2+dpsi2+dtheta2 - 2 dfi dtheta cos2(psi), dx2, dy2, dz2, dfi2, dpsi2, dtheta2} (the tool then scales
+ *   them with constants of its own, main.cpp:94-106).
+ * maddy_analysis_project: scripts/disas_speed/3d22d.cpp:42-51: out[traj][i] = {sqrtf(x*x + y*y), z, theta}.
+ * maddy_analysis_protofilaments: scripts/disas_speed/disc.cpp:62-117 on that projection: out[traj][pf] =
+ *   {pf_end_number, curled_start, mt_end_number}: the dimer where the protofilament breaks off (radial-axial gap
+ *   > 5 nm between consecutive dimers), where its curl starts (theta > 0.2) and the dimer number of its straight tip. */
+int maddy_analysis_setup(maddy_handle *h, const int *chain, const int *resid, const char *name1, int n_pf);
+int maddy_analysis_reference(maddy_handle *h);
+int maddy_analysis_temperature(maddy_handle *h, double *sums);
+int maddy_analysis_project(maddy_handle *h, float *out);
+int maddy_analysis_protofilaments(maddy_handle *h, int *out);
+
 /* ---- host-side pieces of the path that need no GPU (usable without a device) */
 /* generateSeeds (HybridTaus.cu:32-48) on a FRESH ran2 state: fills seeds[np*4]. */
 void maddy_generate_seeds(unsigned *seeds, int rseed, long long np);

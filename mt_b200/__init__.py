@@ -14,7 +14,7 @@ import importlib
 
 _LAZY = {
     "MaddyError": "capi", "generate_seeds": "capi", "read_dcd": "capi",
-    "Engine": "api", "HostSystem": "api",
+    "Engine": "api", "HostSystem": "api", "pdb_labels": "api",
 }
 
 

@@ -281,6 +281,37 @@ class Engine:
                                              as_ptr(e, C.c_double) if e is not None else None))
         return {"coords": c, "forces": f, "energies": e}
 
+    # ---- in-situ analysis (scripts/temp_calc, scripts/disas_speed of the reference)
+    def analysis_setup(self, chain, resid, name1, n_pf: int = 13):
+        """PDB labels per monomer: chain index (chain - 'A', -1 outside the protofilaments), residue number, second
+        character of the atom name (see pdb_labels)."""
+        chain = np.ascontiguousarray(chain, dtype=np.int32)
+        resid = np.ascontiguousarray(resid, dtype=np.int32)
+        name1 = bytes(name1)
+        assert chain.size == self.N and resid.size == self.N and len(name1) == self.N
+        self._npf = int(n_pf)
+        self._ck(capi.lib.maddy_analysis_setup(self._h, as_ptr(chain, C.c_int), as_ptr(resid, C.c_int), name1, self._npf))
+
+    def analysis_reference(self):
+        self._ck(capi.lib.maddy_analysis_reference(self._h))
+
+    def analysis_temperature(self) -> np.ndarray:
+        """raw displacement sums [ntr, 8] against the previous frame, which then becomes the current state"""
+        out = np.empty((self.ntr, 8), dtype=np.float64)
+        self._ck(capi.lib.maddy_analysis_temperature(self._h, as_ptr(out, C.c_double)))
+        return out
+
+    def analysis_project(self) -> np.ndarray:
+        out = np.empty((self.ntr, self.N, 3), dtype=np.float32)
+        self._ck(capi.lib.maddy_analysis_project(self._h, as_ptr(out, C.c_float)))
+        return out
+
+    def analysis_protofilaments(self) -> np.ndarray:
+        """[ntr, n_pf, 3] = pf_end_number, curled_start, mt_end_number per protofilament"""
+        out = np.empty((self.ntr, self._npf, 3), dtype=np.int32)
+        self._ck(capi.lib.maddy_analysis_protofilaments(self._h, as_ptr(out, C.c_int)))
+        return out
+
     @property
     def energies_device_ptr(self) -> int:
         return capi.lib.maddy_energies_device(self._h) or 0
@@ -341,3 +372,19 @@ class Engine:
     def upload_rng(self, st):
         st = np.ascontiguousarray(st, dtype=np.uint32)
         self._ck(capi.lib.maddy_upload_rng(self._h, as_ptr(st, C.c_uint)))
+
+
+def pdb_labels(path, n_pf: int = 13):
+    """(chain index, residue number, second character of the atom name) per ATOM record of a PDB file, in the form
+    maddy_analysis_setup takes them (fixed PDB columns: name 13-16, chain 22, resSeq 23-26)."""
+    chain, resid, name1 = [], [], bytearray()
+    with open(path) as f:
+        for line in f:
+            if not line.startswith(("ATOM", "HETATM")):
+                continue
+            c = ord(line[21]) - ord("A")
+            chain.append(c if 0 <= c < n_pf else -1)
+            resid.append(int(line[22:26]))
+            name = line[12:16].strip()
+            name1.append(ord(name[1]) if len(name) > 1 else 32)
+    return np.asarray(chain, dtype=np.int32), np.asarray(resid, dtype=np.int32), bytes(name1)

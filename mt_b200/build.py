@@ -6,6 +6,7 @@
   oracle/_build/libmaddy_oracle.so   CPU restatement used by tests / smoke / cpu_baseline (gcc)
   oracle/_ref/{mt,ref_probe} the reference's own CUDA build, compiled IN PLACE from
                              /root/reference/src when that tree is present (nvcc)
+  oracle/_ref/{disc,p3d22d,temp_calc}  the reference's analysis tools (scripts/), same rule (g++)
 
 Run:  python -m mt_b200.build [--force] [--no-ref]
 """
@@ -49,7 +50,7 @@ def _run(cmd, **kw):
 
 
 def build_kernels(force=False, verbose_ptxas=False):
-    srcs = [CSRC / "maddy_kernels.cu", CSRC / "maddy_tea.cu", CSRC / "maddy_capi.cu", CSRC / "maddy_seeds.cpp"]
+    srcs = [CSRC / "maddy_kernels.cu", CSRC / "maddy_tea.cu", CSRC / "maddy_analysis.cu", CSRC / "maddy_capi.cu", CSRC / "maddy_seeds.cpp"]
     deps = srcs + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "maddy_b200.h"]
     if not force and not _stale(LIB_KERNELS, deps):
         return LIB_KERNELS
@@ -117,6 +118,11 @@ def build_reference(force=False):
     flags = ["-O2", "-arch=sm_100", "-rdc=true", "-use_fast_math", "-DCUDA", "-DMORSE", "-w", f"-I{src}"]
     if force or not REF_MT.exists():
         _run([NVCC, *flags, "-o", REF_MT, *[src / f for f in common], src / "main.cpp"])
+    # the reference's offline analysis tools (plain g++, their Makefile's recipe): checkers for the in-situ analysis
+    for out, main, d in (("disc", "disc.cpp", "disas_speed"), ("p3d22d", "3d22d.cpp", "disas_speed"), ("temp_calc", "main.cpp", "temp_calc")):
+        sdir = REFERENCE / "scripts" / d
+        if sdir.is_dir() and (force or not (REF_MT.parent / out).exists()):
+            _run(["g++", "-O3", "-w", "-o", REF_MT.parent / out, sdir / main, sdir / "dcdio.cpp", sdir / "pdbio.cpp"])
     probe_src = ORACLE / "ref_probe.cu"
     if probe_src.exists() and (force or _stale(REF_PROBE, [probe_src])):
         _run([NVCC, *flags, "-o", REF_PROBE, *[src / f for f in common], probe_src])

@@ -97,7 +97,8 @@ KERNEL_SYMBOLS = [
     "maddy_upload_gtp", "maddy_upload_on_tubule", "maddy_upload_extra", "maddy_download_list", "maddy_upload_list",
     "maddy_download_rng", "maddy_upload_rng", "maddy_generate_seeds", "maddy_tea_beta", "maddy_ensemble_allreduce",
     "maddy_launch_count", "maddy_schedule_gtp", "maddy_rebuild_and_energies", "maddy_snapshot_begin", "maddy_snapshot_end",
-    "maddy_list_stats",
+    "maddy_list_stats", "maddy_analysis_setup", "maddy_analysis_reference", "maddy_analysis_temperature", "maddy_analysis_project",
+    "maddy_analysis_protofilaments",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
@@ -134,6 +135,11 @@ _sig(lib.maddy_ensemble_allreduce, _i, [C.POINTER(_vp), _i, C.POINTER(_pd), _i])
 _sig(lib.maddy_launch_count, _ll, [_vp])
 _sig(lib.maddy_schedule_gtp, _i, [_vp, _ll, _ll, _i, _pi])
 _sig(lib.maddy_list_stats, _i, [_vp, C.POINTER(C.c_ulonglong), _i])
+_sig(lib.maddy_analysis_setup, _i, [_vp, _pi, _pi, C.c_char_p, _i])
+_sig(lib.maddy_analysis_reference, _i, [_vp])
+_sig(lib.maddy_analysis_temperature, _i, [_vp, _pd])
+_sig(lib.maddy_analysis_project, _i, [_vp, _pf])
+_sig(lib.maddy_analysis_protofilaments, _i, [_vp, _pi])
 _sig(lib.maddy_snapshot_begin, _i, [_vp, _u])
 _sig(lib.maddy_snapshot_end, _i, [_vp, _pf, _pf, _pd])
 

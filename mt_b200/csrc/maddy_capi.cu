@@ -31,6 +31,7 @@ cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaSt
 cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
+cudaError_t launch_analysis(int which, const AnalysisArgs &a, cudaStream_t st);
 } // namespace maddy
 
 using namespace maddy;
@@ -77,6 +78,8 @@ struct maddy_handle {
     CutTest cut_pairs, cut_force;
     std::string err;
     long long launches = 0;
+    AnalysisArgs an{};          // in-situ analysis buffers (maddy_analysis_setup), an.temp == nullptr until then
+    bool an_has_reference = false;
     bool wide = false;          // trajectories spread over many CTAs, stage in HBM (maddy_wide.cuh): N > MADDY_MAX_NTOT_CTA
     bool lazy = false;          // fused loop keeps the Verlet list lazily (see ensure_lj)
     bool lj_maybe_stale = false; // some trajectory's Verlet list may have to be materialised before it is read
@@ -1240,6 +1243,107 @@ extern "C" int maddy_tea_integrate(maddy_handle *h)
     cudaError_t e = launch_tea_kernels(kargs(h, 0), 1, 0, h->stream);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "TEA integrate kernel: %s", cudaGetErrorString(e));
     h->launches += 2;
+    return MADDY_OK;
+}
+
+// ------------------------------------------------------------------ in-situ analysis
+extern "C" int maddy_analysis_setup(maddy_handle *h, const int *chain, const int *resid, const char *name1, int n_pf)
+{
+    if (!h || !chain || !resid || !name1) return MADDY_EINVAL;
+    if (n_pf < 1 || n_pf > 32) return fail(h, MADDY_EINVAL, "maddy_analysis_setup: n_pf=%d outside [1,32]", n_pf);
+    if (h->an.temp) return fail(h, MADDY_EINVAL, "maddy_analysis_setup: already set up");
+    CU(h, cudaSetDevice(h->p.device));
+    const int N = h->a.N, ntr = h->a.ntr;
+    const size_t n = (size_t)ntr * N;
+    std::vector<short> c(N), r(N);
+    for (int i = 0; i < N; i++) {
+        if (resid[i] < -32768 || resid[i] > 32767) return fail(h, MADDY_EINVAL, "maddy_analysis_setup: residue number %d of atom %d", resid[i], i);
+        c[i] = (short)((chain[i] >= 0 && chain[i] < n_pf) ? chain[i] : -1);
+        r[i] = (short)resid[i];
+    }
+    AnalysisArgs &a = h->an;
+    std::vector<PoolReq> reqs;
+    g_pool_reqs = &reqs;
+    pool_req(&a.ppos, n);
+    pool_req(&a.pang, n);
+    pool_req(const_cast<short **>(&a.chain), (size_t)N);
+    pool_req(const_cast<short **>(&a.resid), (size_t)N);
+    pool_req(const_cast<char **>(&a.name1), (size_t)N);
+    pool_req(&a.temp, (size_t)ntr * 8);
+    pool_req(&a.proj, n * 3);
+    pool_req(&a.pf, (size_t)ntr * n_pf * 3);
+    int rc = pool_commit(h, reqs);
+    if (rc) {
+        a = AnalysisArgs{};
+        return rc;
+    }
+    a.pos = h->a.pos;
+    a.ang = h->a.ang;
+    a.N = N;
+    a.ntr = ntr;
+    a.n_pf = n_pf;
+    CU(h, cudaMemcpyAsync((void *)a.chain, c.data(), (size_t)N * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync((void *)a.resid, r.data(), (size_t)N * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync((void *)a.name1, name1, (size_t)N, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+static int analysis_ready(maddy_handle *h, const char *who)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!h->an.temp) return fail(h, MADDY_EINVAL, "%s: call maddy_analysis_setup first", who);
+    CU(h, cudaSetDevice(h->p.device));
+    return MADDY_OK;
+}
+extern "C" int maddy_analysis_reference(maddy_handle *h)
+{
+    int rc = analysis_ready(h, "maddy_analysis_reference");
+    if (rc) return rc;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    CU(h, cudaMemcpyAsync(h->an.ppos, h->a.pos, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->an.pang, h->a.ang, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    h->an_has_reference = true;
+    return MADDY_OK;
+}
+static int analysis_launch(maddy_handle *h, int which, const char *who)
+{
+    cudaError_t e = launch_analysis(which, h->an, h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "%s: %s", who, cudaGetErrorString(e));
+    h->launches++;
+    return MADDY_OK;
+}
+extern "C" int maddy_analysis_temperature(maddy_handle *h, double *sums)
+{
+    int rc = analysis_ready(h, "maddy_analysis_temperature");
+    if (rc) return rc;
+    if (!sums) return MADDY_EINVAL;
+    if (!h->an_has_reference) return fail(h, MADDY_EINVAL, "maddy_analysis_temperature: no previous frame (maddy_analysis_reference)");
+    rc = analysis_launch(h, 0, "analysis_temperature_kernel");
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(sums, h->an.temp, (size_t)h->a.ntr * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+extern "C" int maddy_analysis_project(maddy_handle *h, float *out)
+{
+    int rc = analysis_ready(h, "maddy_analysis_project");
+    if (rc) return rc;
+    if (!out) return MADDY_EINVAL;
+    rc = analysis_launch(h, 1, "analysis_project_kernel");
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(out, h->an.proj, (size_t)h->a.ntr * h->a.N * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+extern "C" int maddy_analysis_protofilaments(maddy_handle *h, int *out)
+{
+    int rc = analysis_ready(h, "maddy_analysis_protofilaments");
+    if (rc) return rc;
+    if (!out) return MADDY_EINVAL;
+    rc = analysis_launch(h, 2, "analysis_protofilament_kernel");
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(out, h->an.pf, (size_t)h->a.ntr * h->an.n_pf * 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     return MADDY_OK;
 }
 

@@ -129,4 +129,16 @@ struct KArgs {
     CutTest cut_force; // LJ force cut-off (6.0)
 };
 
+// in-situ analysis (maddy_analysis.cu)
+struct AnalysisArgs {
+    const float4 *pos, *ang;   // current state
+    float4 *ppos, *pang;       // previous frame of the displacement statistics
+    const short *chain, *resid; // [N] PDB labels (chain - 'A' or -1, residue number)
+    const char *name1;         // [N] second character of the atom name
+    int N, ntr, n_pf;
+    double *temp; // [ntr][8]
+    float *proj;  // [ntr*N][3]
+    int *pf;      // [ntr][n_pf][3]
+};
+
 } // namespace maddy

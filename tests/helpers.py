@@ -48,3 +48,64 @@ def system_from_golden(g, rundir, load_system, ntr=None, extra_overrides=()):
     over = [o for o in str(g["overrides"]).split() if not o.startswith("probe_")] + list(extra_overrides)
     d = rundir(str(g["case"]), runnum=int(g["ntr"]) if ntr is None else ntr, steps=int(g["window"]), stride=100000)
     return load_system(d, over)
+
+
+# ---------------------------------------------------------------- analysis tools of the reference
+def write_dcd(path, frames, stride=1000):
+    """float32 [F, N, 3] -> a DCD file in the layout of the reference's dcdio.cpp:98-203 (what its tools read)"""
+    import struct
+    frames = np.asarray(frames, dtype=np.float32)
+    f_count, n = frames.shape[0], frames.shape[1]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i4s9if10i", 84, b"CORD", f_count, stride, stride, 0, 0, 0, 0, 0, 0, 1.0, *([0] * 9), 24))
+        f.write(struct.pack("<ii", 84, 164))
+        f.write(struct.pack("<i", 2) + b"REMARKS CREATED BY dcdio.c".ljust(80, b"\0") + b"REMARKS DATE: test".ljust(80, b"\0"))
+        f.write(struct.pack("<iiii", 164, 4, n, 4))
+        for fr in frames:
+            for k in range(3):
+                f.write(struct.pack("<i", 4 * n) + np.ascontiguousarray(fr[:, k]).tobytes() + struct.pack("<i", 4 * n))
+
+
+def run_reference_analysis(ref_dir, workdir, pdb, xyz_frames, ang_frames, stride):
+    """Runs the reference's own tools (oracle/_ref/{temp_calc,p3d22d,disc}) over DCD files written from the frames.
+    -> dict(temp=[F-1, 8] printed columns, proj=[F, N, 3], timeline=[F] values, summary=(mean, frames, mean_curled))"""
+    import subprocess
+    from pathlib import Path
+    from mt_b200 import read_dcd
+    ref_dir, workdir = Path(ref_dir), Path(workdir)
+    workdir.mkdir(parents=True, exist_ok=True)
+    fx, fa, fp = workdir / "xyz.dcd", workdir / "ang.dcd", workdir / "proj.dcd"
+    write_dcd(fx, xyz_frames, stride)
+    write_dcd(fa, ang_frames, stride)
+    n_frames = len(xyz_frames)
+    out = subprocess.run([str(ref_dir / "temp_calc"), str(pdb), str(fx), str(fa), str(stride)], capture_output=True, text=True, check=True).stdout
+    rows = [l.split() for l in out.splitlines() if l and l[0].isdigit()]
+    temp = np.array([[float(v) for v in r[1:9]] for r in rows if 2 <= int(r[0]) <= n_frames])
+    subprocess.run([str(ref_dir / "p3d22d"), str(pdb), str(fx), str(fa), str(fp)], capture_output=True, text=True, check=True)
+    proj = read_dcd(fp)[:n_frames]
+    subprocess.run([str(ref_dir / "disc"), str(pdb), str(fp), "timeline"], capture_output=True, text=True, check=True)
+    timeline = np.array([float(l.split()[1]) for l in open(str(fp) + ".dat").read().splitlines()][:n_frames])
+    summ = subprocess.run([str(ref_dir / "disc"), str(pdb), str(fp)], capture_output=True, text=True, check=True).stdout.split("\n")[-1].split()
+    return {"temp": temp, "proj": proj, "timeline": timeline, "summary": (float(summ[0]), int(summ[1]), float(summ[2]))}
+
+
+def synthetic_disassembly_frames(xyz0, ang0, chain, resid, n_frames=5, seed=3):
+    """A lattice whose protofilaments progressively peel outwards: per frame, the top dimers of some protofilaments get a
+    larger radius (breaks > 5 nm), theta curls, and everything jitters.  float32 [F, N, 3] x 2 (ang = fi, psi, theta)."""
+    rng = np.random.default_rng(seed)
+    xyz, ang = [np.asarray(xyz0, np.float32).copy()], [np.asarray(ang0, np.float32).copy()]
+    top = resid.max()
+    for f in range(1, n_frames):
+        x, a = xyz[-1].copy(), ang[-1].copy()
+        x += rng.normal(0, 0.03, x.shape).astype(np.float32)
+        a += rng.normal(0, 0.01, a.shape).astype(np.float32)
+        for c in rng.choice(13, size=5, replace=False):
+            cut = top - rng.integers(1, 3 * f + 1)
+            sel = (chain == c) & (resid > cut)
+            scale = (1.0 + 0.25 * f * (resid[sel] - cut) / 3.0).astype(np.float32)
+            x[sel, 0] *= scale
+            x[sel, 1] *= scale
+            a[sel, 2] += np.float32(0.15 * f)
+        xyz.append(x)
+        ang.append(a)
+    return np.stack(xyz), np.stack(ang)
