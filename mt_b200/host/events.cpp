@@ -457,6 +457,73 @@ void compute(System &s, bool fused, ComputeStats *stats)
         if (s.writer) s.writer->drain(); // the frames up to here are on disk before the checkpoint says so
         checkpoint_save(s, hp.checkpoint, out);
     };
+    // ---- in-situ analysis (extension key insitu_analysis): per stride frame and trajectory, the line
+    // scripts/temp_calc prints (main.cpp:94-107, with this run's gammaR / gammaTheta / dt / Ntot / k_B instead of the
+    // tool's hard-coded ones) and the timeline line of scripts/disas_speed/disc (disc.cpp:160-166)
+    const int n_pf = 13; // pf_number, disc.cpp:12
+    long insitu_frames = 0;
+    std::vector<FILE *> insitu_temp, insitu_disc;
+    struct InsituClose {
+        std::vector<FILE *> &a, &b;
+        ~InsituClose()
+        {
+            for (FILE *f : a) if (f) fclose(f);
+            for (FILE *f : b) if (f) fclose(f);
+        }
+    } insitu_close{insitu_temp, insitu_disc};
+    if (hp.insitu) {
+        std::vector<int> chain(N), resid(N);
+        std::vector<char> name1(N);
+        for (int i = 0; i < N; i++) {
+            const PDBAtom &at = s.pdb.atoms[i];
+            const int c = at.chain - 'A';
+            chain[i] = (c >= 0 && c < n_pf) ? c : -1;
+            resid[i] = at.resid;
+            name1[i] = at.name[0] ? at.name[1] : ' ';
+        }
+        for_each([&](Shard &d) {
+            ck(maddy_analysis_setup(d.h, chain.data(), resid.data(), name1.data(), n_pf), d.h, "maddy_analysis_setup");
+            ck(maddy_analysis_reference(d.h), d.h, "maddy_analysis_reference");
+        });
+        if (s.write_files)
+            for (int t = 0; t < Ntr; t++) {
+                insitu_temp.push_back(fopen((hp.dcd_xyz[t] + ".temp.dat").c_str(), hp.resume ? "a" : "w"));
+                insitu_disc.push_back(fopen((hp.dcd_xyz[t] + ".disc.dat").c_str(), hp.resume ? "a" : "w"));
+            }
+    }
+    auto insitu_frame = [&](long long at) {
+        insitu_frames++;
+        std::vector<double> sums((size_t)Ntr * 8);
+        std::vector<int> pf((size_t)Ntr * n_pf * 3);
+        for_each([&](Shard &d) {
+            if (insitu_frames > 1) ck(maddy_analysis_temperature(d.h, &sums[(size_t)d.first * 8]), d.h, "maddy_analysis_temperature");
+            else ck(maddy_analysis_reference(d.h), d.h, "maddy_analysis_reference");
+            ck(maddy_analysis_protofilaments(d.h, &pf[(size_t)d.first * n_pf * 3]), d.h, "maddy_analysis_protofilaments");
+        });
+        st.d2h_bytes += (double)Ntr * (8 * 8 + n_pf * 12);
+        if (insitu_temp.empty()) return;
+        const double kB = 0.0019872041; // kcal/(mol K), mt.h:39
+        const double six = 6.0 * (double)hp.stride * par.dt * N * kB, two = six / 3.0;
+        for (int t = 0; t < Ntr; t++) {
+            if (insitu_frames > 1 && insitu_temp[t]) {
+                const double *q = &sums[(size_t)t * 8];
+                fprintf(insitu_temp[t], "%ld %f %f %15f %f %f %15f %f %f\n", insitu_frames, q[0] * par.gammaR / six, q[1] * par.gammaTheta / six,
+                        q[2] * par.gammaR / two, q[3] * par.gammaR / two, q[4] * par.gammaR / two, q[5] * par.gammaTheta / two,
+                        q[6] * par.gammaTheta / two, q[7] * par.gammaTheta / two);
+            }
+            if (insitu_disc[t]) {
+                float lt = 0;
+                for (int c = 0; c < n_pf; c++) lt += (float)pf[((size_t)t * n_pf + c) * 3 + 2] / 13.0;
+                fprintf(insitu_disc[t], "%ld %f", insitu_frames, 2 * lt);
+                for (int c = 0; c < n_pf; c++) {
+                    const int *o = &pf[((size_t)t * n_pf + c) * 3];
+                    fprintf(insitu_disc[t], " %d:%d:%d", o[0], o[1], o[2]); // pf_end_number : curled_start : mt_end_number
+                }
+                fputc('\n', insitu_disc[t]);
+            }
+        }
+        (void)at;
+    };
     while (step < hp.steps) {
         if (!hp.checkpoint.empty() && hp.checkpoint_freq > 0 && step != start_step && step % hp.checkpoint_freq == 0) write_checkpoint(step);
         const bool rebuild_now = step % par.ljpairsupdatefreq == 0;
@@ -486,6 +553,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // ---- stride block (compute_cuda.cu:1163-1226).  Everything the device needs (energies, downloads, on-tubule
         // and insertion uploads) happens here; the output part (update(): stdout, DCD frames) is deferred until the next
         // window has been queued, so the GPU does not wait for host formatting.
+        if (hp.insitu && stride_now) insitu_frame(step);
         int deferred_output = 0;
         const bool overlapped = stride_now && overlap_stride;
         if (overlapped) {

@@ -105,6 +105,9 @@ struct HostParams { // scalars of `Parameters` that only the host uses
     std::string checkpoint;
     long long checkpoint_freq = 0;
     bool resume = false;
+    // extension key `insitu_analysis yes`: the reference's offline DCD tools (scripts/temp_calc, scripts/disas_speed)
+    // evaluated on the device at every stride, one line per frame into <dcd_xyz>.temp.dat / <dcd_xyz>.disc.dat
+    bool insitu = false;
 };
 
 // In-order background writer for trajectory output: the step loop hands over a snapshot of

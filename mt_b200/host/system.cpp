@@ -220,6 +220,7 @@ void init_parameters(System &s, const std::string &config, const std::vector<std
     // extension keys, absent in the reference: exact checkpoints (checkpoint.cpp)
     hp.checkpoint = tb.masked("checkpoint", "");
     hp.checkpoint_freq = tb.long_integer("checkpoint_freq", 0);
+    hp.insitu = tb.yesno("insitu_analysis", 0);
     long long resume_step = 0;
     hp.resume = hp.is_restart && !hp.checkpoint.empty() && checkpoint_peek(hp.checkpoint, &resume_step);
     if (!hp.checkpoint.empty()) {

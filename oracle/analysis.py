@@ -87,5 +87,5 @@ def timeline_value(pf):
     """disc.cpp:163-166: 2 * sum(float(mt_end_number) / 13.0) accumulated in float"""
     lt = np.float32(0)
     for v in pf[:, 2]:
-        lt = np.float32(lt + np.float32(np.float64(np.float32(v)) / 13.0))
+        lt = np.float32(np.float64(lt) + np.float64(np.float32(v)) / 13.0)  # float += double quotient
     return float(np.float32(2) * lt)

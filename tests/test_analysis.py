@@ -134,3 +134,33 @@ def test_device_analysis_on_broken_protofilaments(rundir, load_system):
     assert broke > 0
     with pytest.raises(Exception):
         Engine(s).analysis_temperature()  # no setup: fails loudly
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not HAVE_TOOLS, reason="reference analysis tools not built (oracle/_ref)")
+def test_drop_in_insitu_analysis_vs_tools_on_the_dcd_output(rundir):
+    """`mt config.conf` with the extension key insitu_analysis: the per-stride lines it writes beside the DCD files
+    against the reference's tools run afterwards over those DCD files (what a user of the reference does today)."""
+    import subprocess
+    from mt_b200 import HostSystem, read_dcd, workspace
+    d = rundir("mt120_disassembly", structure=("lattice", 40, 3), runnum=2, steps=500, stride=100, insitu_analysis="yes")
+    r = subprocess.run([str(ROOT / "mt_b200" / "mt"), "config.conf"], cwd=str(d), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    with workspace.chdir(d):
+        s = HostSystem("config.conf")
+    par = s.par
+    for t in range(2):
+        fx, fa = read_dcd(d / "dcd" / f"run_{t}.dcd"), read_dcd(d / "dcd" / f"run_{t}.dcd_ang")
+        assert fx.shape == (5, 520, 3)  # frames at steps 0 .. 400
+        out = run_reference_analysis(REF, d / f"tools_{t}", d / "dcd" / "xyz.pdb", fx, fa, 100)
+        mine = np.loadtxt(d / "dcd" / f"run_{t}.dcd.temp.dat")
+        assert mine.shape == (4, 9) and list(mine[:, 0]) == [2, 3, 4, 5]
+        # both print scaled sums with six decimals; undo the two scalings (the tool's constants are hard-coded, main.cpp:94-97)
+        six = 6.0 * 100 * par.dt * 520 * 0.0019872041
+        own_scale = np.array([par.gammaR / six, par.gammaTheta / six] + [par.gammaR / (six / 3)] * 3 + [par.gammaTheta / (six / 3)] * 3)
+        tool_scale = oa.temperature_scale(np.ones(8), 100)
+        assert np.allclose(mine[:, 1:] / own_scale, out["temp"] / tool_scale, rtol=2e-5, atol=1e-7)
+        disc = [l.split() for l in (d / "dcd" / f"run_{t}.dcd.disc.dat").read_text().splitlines()]
+        assert len(disc) == 5
+        assert np.allclose([float(l[1]) for l in disc], out["timeline"], rtol=0, atol=2e-6)
+    s.close()
