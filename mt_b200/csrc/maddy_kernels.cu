@@ -119,7 +119,9 @@ __device__ __forceinline__ Frame publish(const Stage &s, int i, const Mono &m, c
 
 // ------------------------------------------------------------------ forces
 // Generalized force on monomer i (non-extra) from the staged trajectory.
-template <class S>
+// kBatchWalk: walk the full Verlet list in batches of 16 (index loads first, then positions): for callers whose list
+// walk is a chain of L2 round trips (step-granular phase kernel, wide path).  Same arithmetic in the same order.
+template <bool kBatchWalk = false, class S>
 __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Near &near, int traj, int i, const Mono &m,
                                             const Frame &fr)
 {
@@ -277,9 +279,9 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
                 lj = all ? a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i : a.ncand + (size_t)traj * MD_NCAND_CAPACITY * a.Npad + i;
                 n = all ? (int)a.candcnt[(size_t)traj * a.Npad + i] : nnc;
             }
-            if (S::kGlobal) {
-                // stage in HBM/L2 (wide path): every load is an L2 round trip, so fetch 16 indices, then their 16 positions,
-                // then accumulate in list order (same arithmetic, same order: only the number of dependent trips changes)
+            if (kBatchWalk) {
+                // every index load is an L2 round trip: fetch 16 indices, then their 16 positions, then accumulate in list
+                // order (same arithmetic, same order: only the number of dependent trips changes)
                 for (int k0 = 0; k0 < n; k0 += 16) {
                     int jv[16];
                     float4 Pv[16];
@@ -1346,7 +1348,7 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
             const int i = idx[t];
             if (i < N && !(mo[t].flags & MF_EXTRA)) {
                 // extras keep the zero written by the integrator (compute_cuda.cu:55, :966-972)
-                const G6 f = monomer_force(k, s, near, traj, i, mo[t], fr[t]);
+                const G6 f = monomer_force<true>(k, s, near, traj, i, mo[t], fr[t]);
                 a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
                 a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
             }

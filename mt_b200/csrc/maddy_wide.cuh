@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_phase_kernel(const __grid_c
     if ((k.ops & OP_FORCE) && !(mo[0].flags & MF_EXTRA)) {
         F3 e, l1, l2;
         const Frame fr = make_frame(mo[0].fi, mo[0].psi, mo[0].theta, ls, e, l1, l2);
-        const G6 f = monomer_force(k, s, near, traj, i, mo[0], fr);
+        const G6 f = monomer_force<true>(k, s, near, traj, i, mo[0], fr);
         a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
         a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
     }
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_step_kernel(const __grid_co
     if (!(m.flags & (MF_EXTRA | MF_FIXED))) {
         F3 e, l1, l2;
         const Frame fr = make_frame(m.fi, m.psi, m.theta, ls, e, l1, l2);
-        const G6 f = monomer_force(k, s, near, traj, i, m, fr);
+        const G6 f = monomer_force<true>(k, s, near, traj, i, m, fr);
         m.rx = a.rng_xyz[base + i];
         m.ra = a.rng_ang[base + i];
         integrate_monomer(k, m, f);

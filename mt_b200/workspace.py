@@ -92,6 +92,13 @@ BASELINE_CONFIGS = {
     "cylinder_tea": dict(structure=("free", 247, 30.0, 160.0, 1), config={"runnum": 64, "steps": 10000, "tea_on": "yes", "tea_a": 1.5,
                                                                     "tea_epsilon_freq": 100, "tea_capricious": "yes"},
                          conditions={"hydrolysis": "no"}),
+    # 5b: the "large-N single system" of config 5 (SYNTHETIC: 2600 free dimers + the seed ring = 5226 beads, cylinder scaled
+    #     to the same density): longer than one CTA's shared memory, runs on the wide path (maddy_wide.cuh)
+    "cylinder_tea_large": dict(structure=("free", 2600, 65.7, 350.5, 1), config={"runnum": 1, "steps": 10000, "tea_on": "yes", "tea_a": 1.5,
+                                                                               "tea_epsilon_freq": 100, "tea_capricious": "yes"},
+                               conditions={"hydrolysis": "no"}),
+    # large-N lattice (SYNTHETIC: make_mt.py recipe, 13 x 400 = 5200 monomers), wide path without TEA
+    "mt400_single": dict(structure=("lattice", 400, 3), config={"runnum": 1, "steps": 100000}),
 }
 
 
