@@ -239,7 +239,7 @@ def run_own(args):
                              "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_PER_LAUNCH.get((args.workload, ntr_local, window)),
                              "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_run_kernel_ncu_full.txt)",
                              "algorithmic_bytes_per_launch": B_ALG * N * ntr_local * window, "peak_source": pk_src,
-                             "kernel": "maddy::run_kernel<1,2> (one fused window of `window_steps` MD steps per launch; 95 % of the kernel time of a step in the ncu launch list, profiles/r1_launches.csv)",
+                             "kernel": "maddy::run_kernel<1,2> (one fused window of `window_steps` MD steps per launch; 92 % of the kernel time in the ncu launch list profiles/r1_launches.csv; the rest is the stride-step rebuild+energies launch and the L2 flush fill)",
                              "algorithmic_bytes_per_monomer_step": B_ALG, "terms": B_ALG_TERMS,
                              "note": "state stays on-chip across the fused steps, so DRAM traffic is far below the algorithmic bytes; "
                                      "the binding limit is SM issue/latency (see profiles/)"},
