@@ -164,3 +164,25 @@ def test_drop_in_insitu_analysis_vs_tools_on_the_dcd_output(rundir):
         assert len(disc) == 5
         assert np.allclose([float(l[1]) for l in disc], out["timeline"], rtol=0, atol=2e-6)
     s.close()
+
+
+@pytest.mark.gpu
+def test_device_analysis_skips_atoms_outside_the_protofilaments(rundir, load_system):
+    """Reserve dimers (chain 'X', parked above the lattice) belong to no protofilament: disc.cpp would index out of its
+    13-entry arrays; here they are skipped, and the numbers equal those of the lattice alone."""
+    from mt_b200 import Engine, pdb_labels
+    d = rundir("mt120_constconc", structure=("reserve", 40, 10), runnum=2)
+    s = load_system(d, ["hydrolysis=no"])
+    chain, resid, name1 = pdb_labels(d / "dcd" / "xyz.pdb")
+    assert (chain == -1).sum() > 0
+    e = Engine(s)
+    e.analysis_setup(chain, resid, name1)
+    e.analysis_reference()
+    e.run(0, 60)
+    pf, proj, c = e.analysis_protofilaments(), e.analysis_project(), e.coords()
+    for t in range(2):
+        p = oa.project(c[t, :, :3], c[t][:, [3, 5, 4]])
+        assert np.array_equal(proj[t], p)
+        assert np.array_equal(pf[t], oa.protofilaments(p, chain, resid, name1))
+        keep = chain >= 0
+        assert np.array_equal(pf[t], oa.protofilaments(p[keep], chain[keep], resid[keep], bytes(np.frombuffer(name1, dtype=np.uint8)[keep])))

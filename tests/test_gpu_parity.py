@@ -687,6 +687,9 @@ def test_wide_large_tea_system_against_oracle(rundir, load_system):
             o.tea_update()
         e.tea_integrate()
         o.tea_integrate()
+    w = Engine(s)
+    w.run(0, 6)  # the same six steps as one TEA window of maddy_run
+    assert np.array_equal(w.coords(), e.coords()) and np.array_equal(w.rng_state(), e.rng_state())
     assert lists_equal(*e.download_list(capi.LIST_LJ), o.lj_count, o.lj)  # free dimers: the cell-grid rebuild, unordered input
     assert lists_equal(*e.download_list(capi.LIST_LATERAL), o.lat_count, o.lat)
     assert np.array_equal(e.rng_state(), o.rng)
@@ -710,3 +713,17 @@ def test_tea_window_equals_step_granular_calls(rundir, load_system):
     b.run(30, 17)
     assert np.array_equal(a.coords(), b.coords()) and np.array_equal(a.rng_state(), b.rng_state())
     assert lists_equal(*a.download_list(capi.LIST_LJ), *b.download_list(capi.LIST_LJ))
+
+
+def test_wide_path_reports_list_overflow(rundir, load_system, monkeypatch):
+    """More partners inside the pair cut-off than the reference's list capacity (256) is undefined behaviour there and
+    MADDY_EOVERFLOW here, on the wide path as on the one-CTA path."""
+    from mt_b200 import MaddyError
+    d = rundir("cylinder_tea", structure=("free", 250, 20.0, 80.0, 4), runnum=1, tea_on="no")
+    s = load_system(d, ["hydrolysis=no", "LJPairsCutoff=100"])
+    monkeypatch.setenv("MADDY_FORCE_WIDE", "1")
+    e = Engine(s)
+    monkeypatch.delenv("MADDY_FORCE_WIDE")
+    e.rebuild_lj()
+    with pytest.raises(MaddyError, match="overflow"):
+        e.sync()
