@@ -619,6 +619,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         CUK(cudaMemsetAsync(a.fpos, 0, n * sizeof(float4), h->stream));
         CUK(cudaMemsetAsync(a.fang, 0, n * sizeof(float4), h->stream));
         CUK(cudaMemsetAsync(a.bcnt, 0, (size_t)ntr * 2 * a.Npad, h->stream));
+        CUK(cudaMemsetAsync(a.bl, 0, (size_t)ntr * (a.capLong + a.capLat) * a.Npad * sizeof(uint16_t), h->stream)); // rows beyond the counts are never read; zeroed so that the read-modify-write of maddy_upload_list moves defined bytes
         CUK(cudaMemsetAsync(a.ljcnt, 0, (size_t)ntr * a.Npad * sizeof(uint16_t), h->stream));
         CUK(cudaMemsetAsync(a.en_mono, 0, n * 7 * sizeof(double), h->stream));
 
