@@ -246,7 +246,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
                 const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 const bool in = sf < lo && e < 0;
-                band |= !(sf < lo) && sf <= hi;
+                band |= sf <= hi && !in; // also trips for an unlisted pair inside the cut-off (rare): the exact redo below gives the same sum
                 const float inv = 1.0f / sf;
                 const float inv2 = inv * inv;
                 const float c = in ? amp * (6.0f * (inv2 * inv2)) : 0.0f; // 6 / dr^8
