@@ -91,6 +91,22 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
 
 
+def scratch_dir(prefix: str) -> Path:
+    """Run directories of BOTH arms (config files in, DCD / PDB trajectories out).  At 8 GPUs the ensemble writes
+    ~5 GB/s of trajectory frames; on a box whose /tmp sits on a virtual disk that rate is throttled by dirty-page
+    write-back (measured: 5 ms per stride instead of 0.5 ms), which times the disk and not the path.  So the output
+    goes to tmpfs when there is one with room; MADDY_BENCH_SCRATCH overrides."""
+    root = os.environ.get("MADDY_BENCH_SCRATCH")
+    if not root:
+        shm = Path("/dev/shm")
+        try:
+            if shm.is_dir() and os.access(shm, os.W_OK) and shutil.disk_usage(shm).free > (8 << 30):
+                root = str(shm)
+        except OSError:
+            root = None
+    return Path(tempfile.mkdtemp(prefix=prefix, dir=root))
+
+
 def make_system(workload: str, ntr_global: int, tmp: Path, overrides=(), write_files=False, **config):
     from mt_b200 import HostSystem, workspace
     workspace.make_baseline_rundir(tmp, workload, runnum=ntr_global, **config)
@@ -140,7 +156,7 @@ def run_own(args):
     pk, pk_src = peaks()
     ntr_local = args.ntr
     ntr_global = ntr_local * world
-    tmp = Path(tempfile.mkdtemp(prefix=f"bench_r{rank}_"))
+    tmp = scratch_dir(f"bench_r{rank}_")
     try:
         system = make_system(args.workload, ntr_global, tmp)
         N = system.Ntot
@@ -220,7 +236,8 @@ def run_own(args):
         e2e = {"value": N * ntr_global * args.steps / float(tw.item()), "unit": UNIT,
                "h2d_bytes_per_step": st["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st["d2h_bytes"] / args.steps,
                "call": "mt_system_compute (drop-in compute(): create + upload, fused windows, hydrolysis uploads, asynchronous stride read-back, DCD output)",
-               "wall_s": float(tw.item()), "wall_s_runs": [round(w, 4) for w in walls], "statistic": "median of 3 runs"}
+               "wall_s": float(tw.item()), "wall_s_runs": [round(w, 4) for w in walls], "statistic": "median of 3 runs",
+               "scratch": str(tmp.parent)}
 
         if rank == 0:
             achieved = value / world * B_ALG / 1e9  # per-GPU algorithmic GB/s of the dominant (only) kernel
@@ -267,7 +284,7 @@ def run_reference(args):
     from mt_b200 import workspace
     ntr = min(args.ntr, REF_NTR_LIMIT)
     warm = max(args.warmup, 3)
-    tmp = Path(tempfile.mkdtemp(prefix="bench_ref_"))
+    tmp = scratch_dir("bench_ref_")
 
     def timed(steps: int) -> float:
         procs, t0 = [], time.perf_counter()
@@ -292,7 +309,7 @@ def run_reference(args):
             N = len(structures.lattice(40, 0)[0])
         value = N * ntr * world * args.steps / dt
         cores_note = f"reference's own CUDA build (oracle/_ref/mt, unmodified sources, -arch=sm_100 -use_fast_math), {world} x B200, " \
-                     f"runnum {ntr} per process (zs[100] limit of the reference), wall clock of {warm + args.steps} minus {warm} steps"
+                     f"runnum {ntr} per process (zs[100] limit of the reference), wall clock of {warm + args.steps} minus {warm} steps, run directories under {tmp.parent}"
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
