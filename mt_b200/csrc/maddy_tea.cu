@@ -255,6 +255,62 @@ __device__ __forceinline__ void tea_round(TeaBeads &B, const float4 *sco, const 
     }
 }
 
+// Two rounds of 32 partners at once, common case only (no self pair, no padding): the four bead-pair streams are
+// independent until the accumulators, which doubles the instruction-level parallelism a warp offers (the top stall of
+// the one-round version was `wait`: dependent packed operations).  Accumulation order = round A, then round B, as when
+// the rounds are taken one by one, so the result is bit-identical.
+__device__ __forceinline__ void tea_round2(TeaBeads &B, const float4 *sco, const float4 *smf, const float4 *srf, int jjA, int jjB, float ta, float inv_a,
+                                           float near2)
+{
+    const float4 c[2] = {sco[jjA], sco[jjB]}, m[2] = {smf[jjA], smf[jjB]}, r[2] = {srf[jjA], srf[jjB]};
+    float2 ux[4], uy[4], uz[4], crr[4], cii[4], w2[4], iw[4];
+    bool near = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { // q = 2 * round + pair
+        const int rd = q >> 1, pk = q & 1;
+        const float2 dx = __fadd2_rn(f2(c[rd].x, c[rd].x), B.npx[pk]);
+        const float2 dy = __fadd2_rn(f2(c[rd].y, c[rd].y), B.npy[pk]);
+        const float2 dz = __fadd2_rn(f2(c[rd].z, c[rd].z), B.npz[pk]);
+        w2[q] = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+        iw[q] = f2(rsqrtf(w2[q].x), rsqrtf(w2[q].y));
+        ux[q] = __fmul2_rn(dx, iw[q]);
+        uy[q] = __fmul2_rn(dy, iw[q]);
+        uz[q] = __fmul2_rn(dz, iw[q]);
+        const float2 ira = __fmul2_rn(f2(ta, ta), iw[q]);
+        const float2 ira2 = __fmul2_rn(ira, ira);
+        const float2 far = __fmul2_rn(f2(0.75f, 0.75f), ira);
+        crr[q] = __fmul2_rn(far, __ffma2_rn(f2(-2.f, -2.f), ira2, f2(1.f, 1.f)));
+        cii[q] = __fmul2_rn(far, __ffma2_rn(f2(2.f / 3.f, 2.f / 3.f), ira2, f2(1.f, 1.f)));
+        near |= fminf(w2[q].x, w2[q].y) <= near2;
+    }
+    if (__any_sync(0xffffffffu, near)) { // overlapping beads (ra <= 2): rare, scalar
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (w2[q].x <= near2) {
+                const float ra = (w2[q].x * iw[q].x) * inv_a;
+                crr[q].x = (3.f / 32.f) * ra;
+                cii[q].x = 1.f - (9.f / 32.f) * ra;
+            }
+            if (w2[q].y <= near2) {
+                const float ra = (w2[q].y * iw[q].y) * inv_a;
+                crr[q].y = (3.f / 32.f) * ra;
+                cii[q].y = 1.f - (9.f / 32.f) * ra;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int rd = q >> 1, pk = q & 1;
+        const float2 gx = __ffma2_rn(f2(r[rd].x, r[rd].x), B.cx[pk], f2(m[rd].x, m[rd].x));
+        const float2 gy = __ffma2_rn(f2(r[rd].y, r[rd].y), B.cy[pk], f2(m[rd].y, m[rd].y));
+        const float2 gz = __ffma2_rn(f2(r[rd].z, r[rd].z), B.cz[pk], f2(m[rd].z, m[rd].z));
+        const float2 pr = __fmul2_rn(crr[q], __ffma2_rn(uz[q], gz, __ffma2_rn(uy[q], gy, __fmul2_rn(ux[q], gx))));
+        B.ax[pk] = __ffma2_rn(cii[q], gx, __ffma2_rn(pr, ux[q], B.ax[pk]));
+        B.ay[pk] = __ffma2_rn(cii[q], gy, __ffma2_rn(pr, uy[q], B.ay[pk]));
+        B.az[pk] = __ffma2_rn(cii[q], gz, __ffma2_rn(pr, uz[q], B.az[pk]));
+    }
+}
+
 // 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 fills zeros
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
 {
@@ -268,7 +324,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // short ones (their ensembles have warps to spare, and a part would only see a handful of rounds).  The choice depends
 // on N alone, so a trajectory's result does not depend on how many trajectories share the launch.
 template <int TEA_S, int TEA_G>
-__global__ void __launch_bounds__(TEA_THREADS, 3) tea_pair_kernel(const __grid_constant__ KArgs k)
+__global__ void __launch_bounds__(TEA_THREADS, 2) tea_pair_kernel(const __grid_constant__ KArgs k)
 {
     constexpr int TEA_ROUNDS = TEA_TILE / 32 / TEA_S;
     const maddy_params &p = k.p;
@@ -324,13 +380,21 @@ __global__ void __launch_bounds__(TEA_THREADS, 3) tea_pair_kernel(const __grid_c
         __syncthreads();                 // everybody's has; and everybody is done with the stage refilled below
         fetch(t + TEA_STAGES - 1);
         const float4(*T)[TEA_TILE] = tile[t % TEA_STAGES];
-#pragma unroll 1
-        for (int r = 0; r < TEA_ROUNDS; r++) {
-            const int jj0 = (part + TEA_S * r) * 32, j0 = t * TEA_TILE + jj0;
-            if (j0 >= N) break;
-            if ((j0 <= i0 + TEA_IB - 1 && i0 <= j0 + 31) || j0 + 31 >= N)
-                tea_round<true>(B, T[0], T[1], T[2], jj0 + lane, j0 + lane, i0, N, ta, inv_a, near2);
+        auto special = [&](int j0) { return (j0 <= i0 + TEA_IB - 1 && i0 <= j0 + 31) || j0 + 31 >= N; }; // self pair or padding inside
+        auto one = [&](int jj0, int j0) {
+            if (special(j0)) tea_round<true>(B, T[0], T[1], T[2], jj0 + lane, j0 + lane, i0, N, ta, inv_a, near2);
             else tea_round<false>(B, T[0], T[1], T[2], jj0 + lane, j0 + lane, i0, N, ta, inv_a, near2);
+        };
+#pragma unroll 1
+        for (int r = 0; r < TEA_ROUNDS; r += 2) {
+            const int jjA = (part + TEA_S * r) * 32, jA = t * TEA_TILE + jjA;
+            const int jjB = jjA + TEA_S * 32, jB = jA + TEA_S * 32;
+            if (jA >= N) break;
+            if (jB < N && !special(jA) && !special(jB)) tea_round2(B, T[0], T[1], T[2], jjA + lane, jjB + lane, ta, inv_a, near2);
+            else {
+                one(jjA, jA);
+                if (jB < N) one(jjB, jB);
+            }
         }
     }
     cp_async_wait<0>();
