@@ -13,8 +13,8 @@ stream = torch.cuda.Stream()
 e = Engine(s, stream=stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 e.run(0, 200); e.sync()
-for W, do_flush in ((1000, False), (100, False), (100, True), (20, False), (500, False)):
-    K = 4000
+for W, do_flush in ((1000, False), (100, False), (100, True), (20, False), (500, False), (5, False), (1, False)):
+    K = 4000 if W >= 20 else 400
     evs = []
     step = 200
     with torch.cuda.stream(stream):
