@@ -330,8 +330,8 @@ def test_drop_in_mt_executable_vs_reference_executable(rundir):
     if not refprobe.REF_MT.exists():
         pytest.skip("oracle/_ref/mt did not travel with the tree")
     mine_bin = ROOT / "mt_b200" / "mt"
-    # stride 350 with hydrolysis every 100 steps: events at 400, 500, 600 fall INSIDE a stride and are applied
-    # in-kernel from the GTP schedule; 350 and 700 are not multiples of the hydrolysis period
+    # stride 350 with hydrolysis every 100 steps: events at 400, 500, 600 fall INSIDE a stride (one fused window per
+    # event period); 350 and 700 are not multiples of the hydrolysis period
     d_ref = rundir("mt40_single", runnum=2, steps=800, stride=350)
     d_own = d_ref.parent / (d_ref.name + "_own")
     shutil.copytree(d_ref, d_own)

@@ -1,6 +1,6 @@
 import sys, tempfile
 from pathlib import Path
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from mt_b200 import Engine, HostSystem, workspace
 d = Path(tempfile.mkdtemp()); workspace.make_baseline_rundir(d, "mt40_ensemble", runnum=256)
 with workspace.chdir(d): s = HostSystem("config.conf")
