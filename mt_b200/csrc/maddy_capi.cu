@@ -243,8 +243,8 @@ static cudaError_t wide_dispatch(maddy_handle *h, const KArgs &k)
     cudaError_t e;
     if (!(k.ops & OP_RUN)) {
         KArgs kk = k;
-        kk.ops &= OP_REBUILD_LJ | OP_REBUILD_BONDS | OP_FORCE | OP_ENERGY; // nothing is ever lazy here: OP_MATERIALISE is a no-op
-        if (!kk.ops) return cudaSuccess;
+        kk.ops &= OP_REBUILD_LJ | OP_REBUILD_BONDS | OP_FORCE | OP_ENERGY | OP_TEA_PREP; // nothing is ever lazy here: OP_MATERIALISE is a no-op
+        if (!(kk.ops & ~(unsigned)OP_TEA_PREP)) return cudaSuccess;
         if ((e = launch_wide_publish(kk, 0, st)) != cudaSuccess) return e;
         h->launches += 1 + ((kk.ops & OP_ENERGY) ? 1 : 0);
         return launch_wide_phase(kk, 0, st);
@@ -750,9 +750,14 @@ extern "C" int maddy_run(maddy_handle *h, long long first_step, long long n_step
                 h->lj_maybe_stale = false;
                 rc = launch(h, kargs(h, (h->p.lj_on ? OP_REBUILD_LJ : 0u) | (h->p.is_assembly ? OP_REBUILD_BONDS : 0u)));
             }
-            if (!rc) rc = maddy_force(h);
+            if (!rc) rc = ensure_lj(h);
+            if (!rc) rc = launch(h, kargs(h, OP_FORCE | OP_TEA_PREP)); // force + integrateTea_prepare in one launch
             if (!rc) rc = maddy_tea_update(h, step);
-            if (!rc) rc = maddy_tea_integrate(h);
+            if (!rc) {
+                cudaError_t e = launch_tea_kernels(kargs(h, 0), 2, 0, h->stream);
+                if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "TEA pair kernel: %s", cudaGetErrorString(e));
+                h->launches++;
+            }
             if (rc) return rc;
         }
         return MADDY_OK;

@@ -1292,6 +1292,27 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     if (threadIdx.x == 0) a.lj_stale[traj] = stale ? 1 : 0;
 }
 
+// integrateTea_prepare (bdhitea_kernel.cu:16-36) for one bead, fused behind its force evaluation: the same statements as
+// tea_prepare_kernel (maddy_tea.cu) on the same values (products only: no contraction either way), so the TEA window of
+// maddy_run and the step-granular calls stay bit-identical.
+__device__ __forceinline__ void tea_prepare_bead(const KArgs &k, size_t q, const Mono &m, const G6 &f, bool extra)
+{
+    const maddy_params &p = k.p;
+    const DevSys &a = k.a;
+    const float var = sqrtf(2.0f * KB_BOLTZ * p.Temp * p.gammaR / p.dt);
+    uint4 st = a.rng_xyz[q];
+    float4 df = rforce(st); // every bead draws, fixed and reserve ones included (:22)
+    a.rng_xyz[q] = st;
+    df.x *= var;
+    df.y *= var;
+    df.z *= var;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.tea_rf[q] = extra ? zero : df;
+    a.tea_mf[q] = extra ? zero : make_float4(f.x, f.y, f.z, 0.f);
+    a.tea_co[q] = make_float4(m.x, m.y, m.z, extra ? 1.f : 0.f);
+    a.fpos[q] = zero; // only xyz is zeroed (:31-33)
+}
+
 /*
  * phase_kernel<MPT> — one phase of the step for EVERY monomer (the step-granular entry points: one call per
  * reference launch).  Same device functions as the fused loop, lists read from HBM, so results are bit-identical.
@@ -1346,12 +1367,16 @@ __global__ void __launch_bounds__(MD_MAX_THREADS, 1) phase_kernel(const __grid_c
 #pragma unroll
         for (int t = 0; t < MPT; t++) {
             const int i = idx[t];
-            if (i < N && !(mo[t].flags & MF_EXTRA)) {
+            if (i >= N) continue;
+            const bool extra = (mo[t].flags & MF_EXTRA) != 0;
+            G6 f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (!extra) {
                 // extras keep the zero written by the integrator (compute_cuda.cu:55, :966-972)
-                const G6 f = monomer_force<true>(k, s, near, traj, i, mo[t], fr[t]);
-                a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
+                f = monomer_force<true>(k, s, near, traj, i, mo[t], fr[t]);
+                if (!(k.ops & OP_TEA_PREP)) a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
                 a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
             }
+            if (k.ops & OP_TEA_PREP) tea_prepare_bead(k, base + i, mo[t], f, extra);
         }
     }
 

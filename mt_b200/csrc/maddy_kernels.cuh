@@ -22,7 +22,8 @@ enum : unsigned {
     OP_ENERGY = 8u,  // per-monomer energies + per-trajectory reduction
     OP_RUN = 16u,    // fused multi-step loop
     OP_TEA_EPS = 32u, // TEA epsilon / C_i statistics (integrateTea_epsilon_unlisted)
-    OP_MATERIALISE = 64u // write the exact Verlet list of the last (lazy) list-update step of the fused loop
+    OP_MATERIALISE = 64u, // write the exact Verlet list of the last (lazy) list-update step of the fused loop
+    OP_TEA_PREP = 128u    // with OP_FORCE: also do integrateTea_prepare for the bead (TEA windows of maddy_run: one launch fewer per step)
 };
 
 // status bits written by kernels

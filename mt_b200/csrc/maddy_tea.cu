@@ -455,7 +455,8 @@ __global__ void __launch_bounds__(TEA_THREADS, 2) tea_pair_kernel(const __grid_c
     }
 }
 
-// which = 0: epsilon update (snapshot, per-bead statistics, per-trajectory beta); which = 1: prepare + pair step
+// which = 0: epsilon update (snapshot, per-bead statistics, per-trajectory beta); which = 1: prepare + pair step;
+// which = 2: pair step only (the force launch did the prepare part, OP_TEA_PREP)
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long /*step*/, cudaStream_t st)
 {
     const int N = k.a.N;
@@ -468,7 +469,7 @@ cudaError_t launch_tea_kernels(const KArgs &k, int which, long long /*step*/, cu
         tea_epsilon_kernel<<<grid, TEA_WARPS * 32, 0, st>>>(k);
         tea_beta_kernel<<<k.a.ntr, 256, 0, st>>>(k);
     } else {
-        tea_prepare_kernel<<<eblocks, 256, 0, st>>>(k);
+        if (which == 1) tea_prepare_kernel<<<eblocks, 256, 0, st>>>(k);
         if (N >= TEA_SPLIT_NTOT) tea_pair_kernel<4, 2><<<dim3((N + 2 * TEA_IB - 1) / (2 * TEA_IB), k.a.ntr), TEA_THREADS, 0, st>>>(k);
         else tea_pair_kernel<1, 8><<<dim3((N + 8 * TEA_IB - 1) / (8 * TEA_IB), k.a.ntr), TEA_THREADS, 0, st>>>(k);
     }

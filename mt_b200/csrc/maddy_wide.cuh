@@ -337,12 +337,17 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_phase_kernel(const __grid_c
     if ((k.ops & (OP_REBUILD_LJ | OP_REBUILD_BONDS)) && !a.wgrid)
         rebuild_lists_all_pairs<1>(k, s, traj, mo, idx, k.ops); // MADDY_WIDE_ALL_PAIRS=1 (test hook): O(N^2) scan
 
-    if ((k.ops & OP_FORCE) && !(mo[0].flags & MF_EXTRA)) {
-        F3 e, l1, l2;
-        const Frame fr = make_frame(mo[0].fi, mo[0].psi, mo[0].theta, ls, e, l1, l2);
-        const G6 f = monomer_force<true>(k, s, near, traj, i, mo[0], fr);
-        a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
-        a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
+    if (k.ops & OP_FORCE) {
+        const bool extra = (mo[0].flags & MF_EXTRA) != 0;
+        G6 f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (!extra) {
+            F3 e, l1, l2;
+            const Frame fr = make_frame(mo[0].fi, mo[0].psi, mo[0].theta, ls, e, l1, l2);
+            f = monomer_force<true>(k, s, near, traj, i, mo[0], fr);
+            if (!(k.ops & OP_TEA_PREP)) a.fpos[base + i] = make_float4(f.x, f.y, f.z, 0.f);
+            a.fang[base + i] = make_float4(f.fi, f.psi, f.theta, 0.f);
+        }
+        if (k.ops & OP_TEA_PREP) tea_prepare_bead(k, base + i, mo[0], f, extra);
     }
     if (k.ops & OP_ENERGY) {
         const E7 en = monomer_energy(k, s, traj, i, mo[0]);

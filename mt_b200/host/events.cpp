@@ -611,7 +611,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // ---- steps up to the next host event
         long long next = hp.steps;
         next = std::min(next, (step / hp.stride + 1) * hp.stride);
-        const bool stepwise = par.tea_on || !fused;
+        const bool stepwise = !fused; // TEA windows are queued by maddy_run as well (force + prepare in one launch)
         const bool hydro = hp.hydrolysis && hp.hydrostep > 0;
         // One window per hydrolysis period: hydrolyse() for the NEXT event is evaluated on the host while the GPU runs
         // the current window (see below), so the events cost no GPU idle time.  (maddy_schedule_gtp can fold several

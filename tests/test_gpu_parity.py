@@ -727,3 +727,22 @@ def test_wide_path_reports_list_overflow(rundir, load_system, monkeypatch):
     e.rebuild_lj()
     with pytest.raises(MaddyError, match="overflow"):
         e.sync()
+
+
+def test_drop_in_tea_windows_equal_stepwise_host_loop(rundir):
+    """compute() with tea_on: windows queued by maddy_run (default) == the step-granular call sequence of the host loop
+    (fused=False), bit for bit, stride read-backs and DCD frames included."""
+    import mt_b200
+    from mt_b200 import HostSystem, workspace
+    out = {}
+    for mode in (True, False):
+        d = rundir("cylinder_tea", runnum=2, steps=260, stride=100)
+        with workspace.chdir(d):
+            s = HostSystem("config.conf", ["tea_epsilon_freq=40"], write_files=True)
+            s.srand(s.par.rseed)
+            s.compute(fused=mode)
+            out[mode] = (np.array(s.coords).copy(), np.array(s.energies).copy(), [mt_b200.read_dcd(d / "dcd" / f"run_{t}.dcd") for t in range(2)])
+            s.close()
+    a, b = out[True], out[False]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert all(np.array_equal(x, y) and x.shape[0] == 3 for x, y in zip(a[2], b[2]))
