@@ -746,3 +746,28 @@ def test_drop_in_tea_windows_equal_stepwise_host_loop(rundir):
     a, b = out[True], out[False]
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert all(np.array_equal(x, y) and x.shape[0] == 3 for x, y in zip(a[2], b[2]))
+
+
+def test_drop_in_loop_on_the_wide_path_equals_cta_path(rundir, monkeypatch):
+    """compute() end to end (hydrolysis uploads, overlapped stride snapshots, energies, DCD frames, tubule lengths) with
+    the library forced onto its wide path == the same run on the one-CTA path, bit for bit."""
+    import mt_b200
+    from mt_b200 import HostSystem, workspace
+    out = {}
+    for mode in ("cta", "wide"):
+        d = rundir("mt40_ensemble", runnum=3, steps=460, stride=200)
+        if mode == "wide":
+            monkeypatch.setenv("MADDY_FORCE_WIDE", "1")
+        with workspace.chdir(d):
+            s = HostSystem("config.conf", [], write_files=True)
+            s.srand(s.par.rseed)
+            s.compute()
+            out[mode] = (np.array(s.coords).copy(), np.array(s.gtp).copy(), np.array(s.on_tubule_cur).copy(),
+                         [mt_b200.read_dcd(d / "dcd" / f"run_{t}.dcd") for t in range(3)], (d / "mt_len.dat").read_text(),
+                         np.array(s.energies).copy())
+            s.close()
+    monkeypatch.delenv("MADDY_FORCE_WIDE")
+    a, b = out["cta"], out["wide"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert all(np.array_equal(x, y) and x.shape[0] == 3 for x, y in zip(a[3], b[3])) and a[4] == b[4]
+    assert np.allclose(a[5], b[5], rtol=1e-13, atol=1e-9)  # per-trajectory energy sums: different reduction order
