@@ -166,12 +166,25 @@ def run_own(args):
         eng = Engine(system, traj_first=rank * ntr_local, n_tr_local=ntr_local, device=local, stream=stream.cuda_stream)
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
+        stride = int(system.host.stride)
+        multi = bool(system.host.hydrolysis) and window < stride and not os.environ.get("MADDY_SINGLE_EVENT_WINDOWS")
+
         def run_steps(first, count, timed):
-            """count steps as fused windows; returns summed event time (ms) when timed"""
+            """count steps as fused windows; returns summed event time (ms) when timed.  The window lengths are those of
+            the drop-in loop (mt_b200/host/events.cpp): one hydrolysis period after a stride step, then one period longer
+            per window up to the next stride (100, 100, 200, 300, 300 steps at the template's periods)."""
             evs = []
             s = first
+            last = window
             while s < first + count:
-                n = min(window - (s % window), first + count - s)
+                if multi and s % stride != 0:
+                    room = stride - s % stride
+                    grow = 0 if (s - last) % stride == 0 else window  # the window after the post-stride one stays short
+                    n = min((last // window) * window + grow, room)
+                else:
+                    n = window - (s % window)
+                n = min(n, first + count - s)
+                last = n
                 with torch.cuda.stream(stream):
                     flush.zero_()  # L2 flush, outside the event pair
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -249,14 +262,15 @@ def run_own(args):
                 "config": {"workload": f"{args.workload}: 13-PF MT seed, {N} monomers x {ntr_local} trajectories per GPU "
                                        f"({ntr_global} total), Morse + LJ, dynamic bond lists, dt 200",
                            "ntot": N, "ntr_per_gpu": ntr_local, "ntr_total": ntr_global, "window_steps": window,
+                           "window_pattern": "per stride: one hydrolysis period, then one period longer per window (the drop-in loop's windows)" if multi else "one hydrolysis period",
                            "parallelism": f"trajectory-sharded x{world}",
                            "l2": "256 MiB flush write between fused windows (outside the timed event pairs); "
                                  "within a window the state is register/SMEM resident by design"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_PER_LAUNCH.get((args.workload, ntr_local, window)),
-                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_run_kernel_ncu_full.txt)",
-                             "algorithmic_bytes_per_launch": B_ALG * N * ntr_local * window, "peak_source": pk_src,
+                             "traffic_unit": "bytes per launch of a 100-step window (ncu dram read+write, profiles/r1_run_kernel_ncu_full.txt)",
+                             "algorithmic_bytes_per_launch": B_ALG * N * ntr_local * args.steps / max(launches, 1), "avg_steps_per_launch": args.steps / max(launches, 1), "peak_source": pk_src,
                              "kernel": "maddy::run_kernel<1,2> (one fused window of `window_steps` MD steps per launch; 92 % of the kernel time in the ncu launch list profiles/r1_launches.csv; the rest is the stride-step rebuild+energies launch and the L2 flush fill)",
                              "algorithmic_bytes_per_monomer_step": B_ALG, "terms": B_ALG_TERMS,
                              "note": "state stays on-chip across the fused steps, so DRAM traffic is far below the algorithmic bytes; "

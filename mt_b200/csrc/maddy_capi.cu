@@ -70,8 +70,15 @@ struct maddy_handle {
     LaunchCfg phase, run; // step-granular phase kernel / fused run kernel
     StepConsts consts{};
     // GTP schedule (maddy_schedule_gtp)
-    uint8_t *d_sched = nullptr;
+    uint8_t *d_sched = nullptr;   // the schedule the next maddy_run reads (one of d_sched_buf)
     size_t sched_capacity = 0;
+    // double-buffered, asynchronous upload: a schedule is converted into pinned memory and copied on the copy stream into
+    // the buffer the running window does NOT read, so the host can hand over the next window's events beside the current one
+    uint8_t *d_sched_buf[2] = {nullptr, nullptr};
+    uint8_t *h_sched_buf[2] = {nullptr, nullptr};
+    cudaEvent_t sched_copied[2] = {nullptr, nullptr};
+    cudaEvent_t sched_reader[2] = {nullptr, nullptr}; // recorded behind the last run that read buffer b
+    int sched_cur = 0;
     long long sched_first = 0, sched_period = 1;
     int sched_slots = 0;
     std::vector<uint16_t> amap, fmap;
@@ -393,7 +400,12 @@ extern "C" int maddy_destroy(maddy_handle *h)
     }
     for (void *q : h->allocs) cudaFree(q);
     if (h->h_status) cudaFreeHost(h->h_status);
-    if (h->d_sched) cudaFree(h->d_sched);
+    for (int b = 0; b < 2; b++) {
+        if (h->d_sched_buf[b]) cudaFree(h->d_sched_buf[b]);
+        if (h->h_sched_buf[b]) cudaFreeHost(h->h_sched_buf[b]);
+        if (h->sched_copied[b]) cudaEventDestroy(h->sched_copied[b]);
+        if (h->sched_reader[b]) cudaEventDestroy(h->sched_reader[b]);
+    }
     for (int k = 0; k < maddy_handle::kStage; k++) {
         if (h->stage[k]) cudaFreeHost(h->stage[k]);
         if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]);
@@ -775,7 +787,13 @@ extern "C" int maddy_run(maddy_handle *h, long long first_step, long long n_step
         if (m == first_step && skip_first) m += freq;
         if (m < first_step + n_steps) h->lj_maybe_stale = true;
     }
-    return launch(h, k);
+    int rc = launch(h, k);
+    if (!rc && k.sched_slots > 0) { // a later schedule upload into this buffer has to wait for this run
+        const int b = h->sched_cur;
+        if (!h->sched_reader[b]) CU(h, cudaEventCreateWithFlags(&h->sched_reader[b], cudaEventDisableTiming));
+        CU(h, cudaEventRecord(h->sched_reader[b], h->stream));
+    }
+    return rc;
 }
 
 static int energies_impl(maddy_handle *h, unsigned ops, double *out_per_traj, double *out_per_monomer);
@@ -1014,19 +1032,39 @@ extern "C" int maddy_schedule_gtp(maddy_handle *h, long long first_event, long l
     if (n_slots == 0) return MADDY_OK;
     CU(h, cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->a.ntr * h->a.N, bytes = n * (size_t)n_slots;
+    if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (bytes > h->sched_capacity) {
-        CU(h, cudaStreamSynchronize(h->stream)); // a running window may still read the old buffer
-        if (h->d_sched) cudaFree(h->d_sched);
-        h->d_sched = nullptr;
+        CU(h, cudaStreamSynchronize(h->stream)); // a running window may still read the old buffers
+        CU(h, cudaStreamSynchronize(h->copy_stream));
+        const size_t cap = bytes < 4 * n ? 4 * n : bytes; // room for a few events without another resize
+        for (int b = 0; b < 2; b++) {
+            if (h->d_sched_buf[b]) cudaFree(h->d_sched_buf[b]);
+            if (h->h_sched_buf[b]) cudaFreeHost(h->h_sched_buf[b]);
+            h->d_sched_buf[b] = h->h_sched_buf[b] = nullptr;
+        }
         h->sched_capacity = 0;
-        cudaError_t e = cudaMalloc(&h->d_sched, bytes);
-        if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "cudaMalloc(%zu bytes) for the GTP schedule: %s", bytes, cudaGetErrorString(e));
-        h->sched_capacity = bytes;
+        h->d_sched = nullptr;
+        for (int b = 0; b < 2; b++) {
+            cudaError_t e = cudaMalloc(&h->d_sched_buf[b], cap);
+            if (e == cudaSuccess) e = cudaMallocHost(&h->h_sched_buf[b], cap);
+            if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "%zu bytes for the GTP schedule: %s", cap, cudaGetErrorString(e));
+            if (!h->sched_copied[b]) CU(h, cudaEventCreateWithFlags(&h->sched_copied[b], cudaEventDisableTiming));
+        }
+        h->sched_capacity = cap;
     }
-    std::vector<uint8_t> v(bytes);
-    for (size_t q = 0; q < bytes; q++) v[q] = (uint8_t)(gtp_slots[q] == 1 ? 1 : (gtp_slots[q] == 0 ? 0 : 2));
-    CU(h, cudaMemcpyAsync(h->d_sched, v.data(), bytes, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream)); // v goes out of scope
+    // Fill the buffer the last scheduled run was NOT given (that run may still be executing).  The copy waits for the
+    // last run that did read this buffer (sched_reader), the next run for the copy (sched_copied).
+    const int b = h->sched_cur ^ 1;
+    CU(h, cudaEventSynchronize(h->sched_copied[b])); // the pinned buffer is free again (its last copy has completed)
+    uint8_t *v = h->h_sched_buf[b];
+    HOST_PARALLEL_FOR(bytes)
+    for (long long q = 0; q < (long long)bytes; q++) v[q] = (uint8_t)(gtp_slots[q] == 1 ? 1 : (gtp_slots[q] == 0 ? 0 : 2));
+    if (h->sched_reader[b]) CU(h, cudaStreamWaitEvent(h->copy_stream, h->sched_reader[b], 0)); // last run that read buffer b
+    CU(h, cudaMemcpyAsync(h->d_sched_buf[b], v, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CU(h, cudaEventRecord(h->sched_copied[b], h->copy_stream));
+    CU(h, cudaStreamWaitEvent(h->stream, h->sched_copied[b], 0)); // the next run starts after its schedule has landed
+    h->sched_cur = b;
+    h->d_sched = h->d_sched_buf[b];
     h->sched_first = first_event;
     h->sched_period = period;
     h->sched_slots = n_slots;

@@ -429,6 +429,13 @@ void compute(System &s, bool fused, ComputeStats *stats)
     };
     long long step = 0;
     long long hydrolysed_for = -1; // event step whose hydrolysis has already been evaluated on the host
+    // Windows that span several hydrolysis events (overlapped mode only).  Every event of a stride depends on the flags
+    // classified at that stride alone, so the events of the NEXT window are drawn (same rand() order) while the GPU runs the
+    // current one and handed over as a GTP schedule: window lengths grow by one event period per window inside a stride
+    // (100, 100, 200, 300, 300 steps at the template's periods) - fewer window boundaries, the host stays ahead of the GPU.
+    const bool multi_event = overlap_stride && hp.hydrolysis && hp.hydrostep > 0 && !getenv("MADDY_SINGLE_EVENT_WINDOWS");
+    std::vector<std::vector<int>> sched_gtp; // GTP state after each pre-drawn event of the next window, first at sched_first
+    long long sched_first = -1, sched_end = -1; // [sched_first, sched_end) = the window those events belong to
     if (hp.resume) {
         step = resume_state.step;
         hydrolysed_for = resume_state.hydrolysed_for;
@@ -542,11 +549,27 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.end("explicit rebuild");
         prof.begin();
         // ---- hydrolysis (compute_cuda.cu:1153-1160)
+        long long scheduled_end = -1;
         if (hp.hydrolysis && step % hp.hydrostep == 0 && step != 0) {
-            if (hydrolysed_for != step) hydrolyse(s);
-            for_each([&](Shard &d) { ck(maddy_upload_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_upload_gtp"); });
-            st.h2d_bytes += (double)n;
-            mark("gtp uploaded", step);
+            if (!sched_gtp.empty() && sched_first == step) {
+                // the events of this window were drawn beside the previous one: slot k becomes current at step + k periods
+                const int slots = (int)sched_gtp.size();
+                for_each([&](Shard &d) {
+                    const size_t cnt = (size_t)d.count * N, off = (size_t)d.first * N;
+                    std::vector<int> buf((size_t)slots * cnt);
+                    for (int k = 0; k < slots; k++) memcpy(&buf[(size_t)k * cnt], &sched_gtp[k][off], cnt * sizeof(int));
+                    ck(maddy_schedule_gtp(d.h, step, hp.hydrostep, slots, buf.data()), d.h, "maddy_schedule_gtp");
+                });
+                st.h2d_bytes += (double)n * slots;
+                scheduled_end = sched_end;
+                sched_gtp.clear();
+                mark("gtp schedule uploaded", step);
+            } else {
+                if (hydrolysed_for != step) hydrolyse(s);
+                for_each([&](Shard &d) { ck(maddy_upload_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_upload_gtp"); });
+                st.h2d_bytes += (double)n;
+                mark("gtp uploaded", step);
+            }
         }
         prof.end("upload gtp");
         prof.begin();
@@ -616,7 +639,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // One window per hydrolysis period: hydrolyse() for the NEXT event is evaluated on the host while the GPU runs
         // the current window (see below), so the events cost no GPU idle time.  (maddy_schedule_gtp can fold several
         // events into one launch, but their evaluation would then sit between two windows instead of beside one.)
-        if (hydro) next = std::min(next, (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
+        if (hydro) next = std::min(next, scheduled_end > step ? scheduled_end : (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
         const long long count = next - step;
         if (stepwise) {
             for (long long q = step; q < next; q++) {
@@ -696,8 +719,27 @@ void compute(System &s, bool fused, ComputeStats *stats)
         if (hydro && next < hp.steps && next % hp.hydrostep == 0 && next != 0) {
             if (pending_output) s.event_log = &pending_log;
             hydrolyse(s);
-            s.event_log = nullptr;
             hydrolysed_for = next;
+            // further events of the next window: only inside a stride (an event AT a stride step precedes that stride's
+            // energies and is uploaded on its own); the window is one event period longer than this one, in whole periods
+            // (not beside the window that follows a stride step: the host is busy with that stride's read-back there)
+            if (multi_event && next % hp.stride != 0 && step % hp.stride != 0) {
+                const long long h = hp.hydrostep;
+                const long long room = std::min((next / hp.stride + 1) * hp.stride, hp.steps) - next; // > 0
+                const long long n_ev = std::min(count / h + 1, (room + h - 1) / h);
+                sched_gtp.clear();
+                if (n_ev > 1) {
+                    sched_gtp.push_back(s.gtp);
+                    for (long long k = 1; k < n_ev; k++) {
+                        hydrolyse(s);
+                        hydrolysed_for = next + k * h;
+                        sched_gtp.push_back(s.gtp);
+                    }
+                    sched_first = next;
+                    sched_end = next + std::min(n_ev * h, room);
+                }
+            }
+            s.event_log = nullptr;
             mark("next hydrolysis evaluated", step);
         }
         prof.end("hydrolyse (host)");

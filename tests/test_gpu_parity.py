@@ -771,3 +771,24 @@ def test_drop_in_loop_on_the_wide_path_equals_cta_path(rundir, monkeypatch):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert all(np.array_equal(x, y) and x.shape[0] == 3 for x, y in zip(a[3], b[3])) and a[4] == b[4]
     assert np.allclose(a[5], b[5], rtol=1e-13, atol=1e-9)  # per-trajectory energy sums: different reduction order
+
+
+def test_gtp_schedules_back_to_back_are_double_buffered(rundir, load_system):
+    """maddy_schedule_gtp uploads on the copy stream into the buffer the running window does not read: schedules handed
+    over back to back (no synchronisation in between, a slot AT the window start included) == explicit uploads."""
+    s = load_system(rundir("mt40_ensemble", runnum=6), ["hydrolysis=no"])
+    rng = np.random.default_rng(8)
+    g = [(rng.random((6, s.Ntot // 2)) > p).astype(np.int32).repeat(2, axis=1) for p in (0.2, 0.5, 0.1, 0.7, 0.4, 0.3)]
+    a, b = Engine(s), Engine(s)
+    first = 0
+    for k, (ev, n) in enumerate(((30, 80), (80, 50), (130, 50))):  # events ev, ev + 25 inside each window
+        a.run(first, ev - first)
+        a.upload_gtp(g[2 * k])
+        a.run(ev, 25)
+        a.upload_gtp(g[2 * k + 1])
+        a.run(ev + 25, first + n - ev - 25)
+        b.schedule_gtp(ev, 25, np.stack(g[2 * k:2 * k + 2]))
+        b.run(first, n)
+        first += n
+    assert np.array_equal(a.coords(), b.coords()) and np.array_equal(a.rng_state(), b.rng_state())
+    assert np.array_equal(a.energies(), b.energies())
