@@ -164,7 +164,9 @@ int maddy_run(maddy_handle *h, long long first_step, long long n_steps, unsigned
  * in one call: slot k (gtp_slots + k * n_tr_local * n_tot ints, same layout as maddy_upload_gtp) becomes the
  * current GTP state at the START of step first_event + k * period, exactly as if maddy_upload_gtp had been called
  * before that step.  A following maddy_run may then span those steps in ONE launch.  The schedule is consumed by
- * the runs that cover it; maddy_upload_gtp clears it.  n_slots = 0 clears it. */
+ * the runs that cover it; maddy_upload_gtp clears it.  n_slots = 0 clears it.  The call does not wait for the GPU: the
+ * slots are copied out of gtp_slots before it returns and uploaded on a second stream into a buffer of their own, so it
+ * may be issued while the previous window (and its schedule) is still running. */
 int maddy_schedule_gtp(maddy_handle *h, long long first_event, long long period, int n_slots, const int *gtp_slots);
 
 /* ---- energies: energy_kernel + OutputAllEnergies (compute_cuda.cu:676-911,
