@@ -7,12 +7,13 @@
  * per-bead epsilon sums, a serial host loop for beta and an H2D every tea_epsilon_freq steps, and a host loop
  * over all particles every step.
  *
- * Here the O(N^2) work is spread over the whole GPU even for ONE trajectory: a WARP owns a bead, its 32 lanes
- * stride over the partners (coalesced float4 loads of the snapshot arrays, served by L1/L2: 25 KB per
- * trajectory), and the 3-vector is reduced with shuffles in a fixed order (deterministic).  520 beads = 520
- * warps = every SM busy at Ntr = 1.  epsilon is reduced per trajectory on the device and beta (eq. 26) is
- * evaluated there too, so nothing crosses PCIe.  The pair work is a generated 3x3 mat-vec per (i,j) whose
- * right-hand side (f_j + C_i o r_j) depends on i: not a GEMM, FP32-pipe bound; tensor cores do not apply.
+ * Here the O(N^2) work is spread over the whole GPU even for ONE trajectory.  The epsilon statistics (every
+ * tea_epsilon_freq steps) use a warp per bead, lanes striding over the partners; the pair kernel of every step gives a
+ * warp four beads as two packed pairs (FFMA2 / FMUL2 / FADD2), streams the partners through shared memory with cp.async
+ * and keeps two rounds of 32 partners in flight (see tea_pair_kernel).  All reductions are shuffles and shared-memory
+ * sums in a fixed order (deterministic, independent of the launch shape).  epsilon is reduced per trajectory on the
+ * device and beta (eq. 26) is evaluated there too, so nothing crosses PCIe.  The pair work is a generated 3x3 mat-vec
+ * per (i,j) whose right-hand side (f_j + C_i o r_j) depends on i: not a GEMM, FP32-pipe bound; tensor cores do not apply.
  *
  * Summation order differs from the reference's sequential j loop (lane-strided partial sums + butterfly), so
  * TEA displacements agree with the reference to float rounding (~1e-7 relative), not bit for bit.
