@@ -437,15 +437,22 @@ __device__ __forceinline__ E7 monomer_energy(const KArgs &k, const S &s, int tra
         if (p.lj_on) {
             const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
             const int n = a.ljcnt[(size_t)traj * a.Npad + i];
-            for (int kk = 0; kk < n; kk++) {
-                const int j = lj[(size_t)kk * a.Npad];
-                const float4 Pj = s.P(j);
-                const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
-                const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
-                    const float dr = (float)sqrt(dist2_exact(dx, dy, dz));
-                    const double dr2 = (double)dr * (double)dr;
-                    U_lj = (float)((double)U_lj + (double)(p.ljscale * p.ljsigma6) / (dr2 * dr2 * dr2));
+            // 16 index loads per round trip (the list lives in HBM/L2), then the pairs in list order
+            for (int k0 = 0; k0 < n; k0 += 16) {
+                int jv[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) jv[q] = k0 + q < n ? (int)lj[(size_t)(k0 + q) * a.Npad] : -1;
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    if (jv[q] < 0) continue;
+                    const float4 Pj = s.P(jv[q]);
+                    const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
+                    const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (inside_cut(k.cut_force, dx, dy, dz, sf)) {
+                        const float dr = (float)sqrt(dist2_exact(dx, dy, dz));
+                        const double dr2 = (double)dr * (double)dr;
+                        U_lj = (float)((double)U_lj + (double)(p.ljscale * p.ljsigma6) / (dr2 * dr2 * dr2));
+                    }
                 }
             }
         }
