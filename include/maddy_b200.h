@@ -149,6 +149,10 @@ int maddy_integrate(maddy_handle *h);      /* integrate_kernel launch, compute_c
 int maddy_tea_update(maddy_handle *h, long long step); /* updateTea, bdhitea.cu:57-118  */
 int maddy_tea_integrate(maddy_handle *h);              /* integrateTea, bdhitea.cu:37-42 */
 
+/* TEA state as the reference's updateTea() sees it (bdhitea.cu:59-60,72-76,115: d_ci, d_epsilon, d_beta_ij): ci4 [n][4]
+ * floats (per-bead C_i in .x/.y/.z), epsilon [n], beta [n_tr_local]; any pointer may be NULL. */
+int maddy_download_tea(maddy_handle *h, float *ci4, float *epsilon, float *beta);
+
 /* ---- fused execution of steps [first_step, first_step + n_steps): the body of the
  * for(step) loop of compute() between two host events (compute_cuda.cu:1137-1238 minus
  * the hydrolysis / stride blocks).  Lists are rebuilt in-kernel at every step with
@@ -246,6 +250,17 @@ int maddy_tea_beta(double epsilon_sum, int n_noextra, int capricious, float tea_
  * handle; on return every values[g] holds the element-wise sum over handles.  The
  * reduction itself runs on the GPUs with ncclAllReduce. */
 int maddy_ensemble_allreduce(maddy_handle **handles, int n, double **values, int count);
+
+/* Device-resident form for the stride block of the step loop: each handle reduces the per-trajectory energies it
+ * evaluated last (maddy_energies, maddy_rebuild_and_energies or maddy_snapshot_begin with MADDY_SNAP_ENERGIES) to
+ * MADDY_ENSEMBLE_STATS doubles {sum of each of the 7 terms, sum of squares of each, trajectory count, 0} on its own
+ * stream, the records are summed over the handles with ncclAllReduce in stream order (n == 1: no collective), and the
+ * result is copied to pinned memory beside the work queued next.  _begin returns at once; _end blocks until the copy
+ * has landed and returns the all-reduced record (identical on every handle).  Replaces nothing in the reference (its MPI
+ * ranks never exchange data, main.cpp:27-50); it is the periodic ensemble reduction of SURVEY 8e. */
+#define MADDY_ENSEMBLE_STATS 16
+int maddy_ensemble_stats_begin(maddy_handle **handles, int n);
+int maddy_ensemble_stats_end(maddy_handle **handles, int n, double *out16);
 
 /* number of kernels this handle has launched since creation (bench bookkeeping) */
 long long maddy_launch_count(const maddy_handle *h);

@@ -42,6 +42,9 @@ int *mt_system_gtp(mt_system *s);
 int *mt_system_on_tubule(mt_system *s, int prev);
 unsigned char *mt_system_extra(mt_system *s);
 double *mt_system_energies(mt_system *s);         /* [n_tr][7] after a compute with output_energy */
+/* ensemble statistics of the last stride with energies: MADDY_ENSEMBLE_STATS doubles (maddy_ensemble_stats_end), or NULL when the
+ * run did not reduce them (one GPU and MADDY_ENSEMBLE_STATS unset) */
+const double *mt_system_ensemble_stats(const mt_system *s);
 /* srand(seed) of the reference main (main.cpp:67) for this system's host events (same sequence as libc rand()) */
 int mt_system_srand(mt_system *s, unsigned seed);
 int mt_system_set_ngpus(mt_system *s, int n_gpus);

@@ -120,6 +120,12 @@ class HostSystem:
     def energies(self):
         return self._view(capi.hostlib.mt_system_energies(self._h), (self.Ntr, 7), np.float64)
 
+    @property
+    def ensemble_stats(self):
+        """[16] all-reduced energy statistics of the last stride (sum(7), sum of squares(7), count, 0), or None"""
+        p = capi.hostlib.mt_system_ensemble_stats(self._h)
+        return np.ctypeslib.as_array(p, shape=(16,)).copy() if p else None
+
     def topology(self, traj_first: int = 0) -> MaddyTopology:
         """maddy_topology for the trajectories starting at traj_first (pointer arithmetic on the live arrays)."""
         t = MaddyTopology()
@@ -241,6 +247,14 @@ class Engine:
 
     def tea_integrate(self):
         self._ck(capi.lib.maddy_tea_integrate(self._h))
+
+    def tea_state(self):
+        """(C_i [ntr*N, 4], epsilon [ntr*N], beta [ntr]) of the TEA integrator (d_ci, d_epsilon, d_beta_ij of the reference)"""
+        ci = np.empty((self.ntr * self.N, 4), dtype=np.float32)
+        eps = np.empty(self.ntr * self.N, dtype=np.float32)
+        beta = np.empty(self.ntr, dtype=np.float32)
+        self._ck(capi.lib.maddy_download_tea(self._h, as_ptr(ci, C.c_float), as_ptr(eps, C.c_float), as_ptr(beta, C.c_float)))
+        return ci, eps, beta
 
     def run(self, first_step: int, n_steps: int, skip_first_rebuild: bool = False):
         self._ck(capi.lib.maddy_run(self._h, int(first_step), int(n_steps),

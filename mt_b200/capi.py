@@ -98,11 +98,11 @@ KERNEL_SYMBOLS = [
     "maddy_download_rng", "maddy_upload_rng", "maddy_generate_seeds", "maddy_tea_beta", "maddy_ensemble_allreduce",
     "maddy_launch_count", "maddy_schedule_gtp", "maddy_rebuild_and_energies", "maddy_snapshot_begin", "maddy_snapshot_end",
     "maddy_list_stats", "maddy_analysis_setup", "maddy_analysis_reference", "maddy_analysis_temperature", "maddy_analysis_project",
-    "maddy_analysis_protofilaments",
+    "maddy_analysis_protofilaments", "maddy_ensemble_stats_begin", "maddy_ensemble_stats_end", "maddy_download_tea",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
-    "mt_system_gtp", "mt_system_on_tubule", "mt_system_extra", "mt_system_energies", "mt_system_set_ngpus", "mt_system_srand",
+    "mt_system_gtp", "mt_system_on_tubule", "mt_system_extra", "mt_system_energies", "mt_system_ensemble_stats", "mt_system_set_ngpus", "mt_system_srand",
     "mt_system_set_steps", "mt_system_compute", "mt_system_mt_length", "mt_system_hydrolyse", "mt_system_change_conc",
     "mt_system_save_pdb", "mt_dcd_read", "mt_pdb_count",
 ]
@@ -133,6 +133,9 @@ _sig(lib.maddy_generate_seeds, None, [C.POINTER(C.c_uint), _i, _ll])
 _sig(lib.maddy_tea_beta, _i, [C.c_double, _i, _i, C.c_float, C.c_float, _pf, _pd])
 _sig(lib.maddy_ensemble_allreduce, _i, [C.POINTER(_vp), _i, C.POINTER(_pd), _i])
 _sig(lib.maddy_launch_count, _ll, [_vp])
+_sig(lib.maddy_download_tea, _i, [_vp, _pf, _pf, _pf])
+_sig(lib.maddy_ensemble_stats_begin, _i, [C.POINTER(_vp), _i])
+_sig(lib.maddy_ensemble_stats_end, _i, [C.POINTER(_vp), _i, _pd])
 _sig(lib.maddy_schedule_gtp, _i, [_vp, _ll, _ll, _i, _pi])
 _sig(lib.maddy_list_stats, _i, [_vp, C.POINTER(C.c_ulonglong), _i])
 _sig(lib.maddy_analysis_setup, _i, [_vp, _pi, _pi, C.c_char_p, _i])
@@ -153,6 +156,7 @@ _sig(hostlib.mt_system_gtp, _pi, [_vp])
 _sig(hostlib.mt_system_on_tubule, _pi, [_vp, _i])
 _sig(hostlib.mt_system_extra, _pu8, [_vp])
 _sig(hostlib.mt_system_energies, _pd, [_vp])
+_sig(hostlib.mt_system_ensemble_stats, _pd, [_vp])
 _sig(hostlib.mt_system_set_ngpus, _i, [_vp, _i])
 _sig(hostlib.mt_system_srand, _i, [_vp, _u])
 _sig(hostlib.mt_system_set_steps, _i, [_vp, _ll])

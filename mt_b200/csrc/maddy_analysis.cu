@@ -127,6 +127,40 @@ __global__ void __launch_bounds__(AN_THREADS) analysis_protofilament_kernel(Anal
     }
 }
 
+// ensemble statistics of the per-trajectory energies: out[0..6] = sum over the local trajectories of each
+// term, out[7..13] = sum of squares, out[14] = trajectory count, out[15] = 0.  One CTA; the result is all-reduced over
+// the handles with NCCL (maddy_ensemble_stats_begin).
+__global__ void __launch_bounds__(AN_THREADS) ensemble_stats_kernel(const double *__restrict__ en_traj, int ntr, double *__restrict__ out)
+{
+    __shared__ double scratch[AN_THREADS / 32];
+    double s[14];
+#pragma unroll
+    for (int q = 0; q < 14; q++) s[q] = 0.0;
+    for (int t = threadIdx.x; t < ntr; t += AN_THREADS) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+            const double e = en_traj[(size_t)t * 7 + q];
+            s[q] += e;
+            s[7 + q] += e * e;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 14; q++) {
+        const double r = block_sum(s[q], scratch);
+        if (threadIdx.x == 0) out[q] = r;
+    }
+    if (threadIdx.x == 0) {
+        out[14] = (double)ntr;
+        out[15] = 0.0;
+    }
+}
+
+cudaError_t launch_ensemble_stats(const double *en_traj, int ntr, double *out, cudaStream_t st)
+{
+    ensemble_stats_kernel<<<1, AN_THREADS, 0, st>>>(en_traj, ntr, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_analysis(int which, const AnalysisArgs &a, cudaStream_t st)
 {
     if (which == 0) analysis_temperature_kernel<<<a.ntr, AN_THREADS, 0, st>>>(a);

@@ -32,6 +32,7 @@ cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_analysis(int which, const AnalysisArgs &a, cudaStream_t st);
+cudaError_t launch_ensemble_stats(const double *en_traj, int ntr, double *out, cudaStream_t st);
 } // namespace maddy
 
 using namespace maddy;
@@ -109,6 +110,10 @@ struct maddy_handle {
     double *snap_en = nullptr;
     cudaEvent_t snap_done = nullptr;
     unsigned snap_what = 0;
+    // ensemble statistics (maddy_ensemble_stats_begin/_end): 16 doubles on the device, pinned mirror, events
+    double *d_ens = nullptr, *h_ens = nullptr;
+    cudaEvent_t ens_ready = nullptr, ens_done = nullptr;
+    bool ens_pending = false;
     // MADDY_GPU_PROFILE=1: event pair around every kernel launch, summarised by maddy_destroy (development aid)
     bool gpu_prof = getenv("MADDY_GPU_PROFILE") != nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -414,6 +419,10 @@ extern "C" int maddy_destroy(maddy_handle *h)
         if (q) cudaFreeHost(q);
     if (h->snap_done) cudaEventDestroy(h->snap_done);
     if (h->snap_staged) cudaEventDestroy(h->snap_staged);
+    if (h->ens_ready) cudaEventDestroy(h->ens_ready);
+    if (h->ens_done) cudaEventDestroy(h->ens_done);
+    if (h->d_ens) cudaFree(h->d_ens);
+    if (h->h_ens) cudaFreeHost(h->h_ens);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamDestroy(h->copy_stream);
@@ -899,11 +908,10 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
     // state -> AoS-7 staging on the device (a few microseconds on the main stream), then the PCIe leg on a second
     // stream so that the window queued next does not wait for it
     const size_t aos_bytes = n * MADDY_COORD_STRIDE * sizeof(float);
-    if (!h->copy_stream) {
-        CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        CU(h, cudaEventCreateWithFlags(&h->snap_staged, cudaEventDisableTiming));
-        CU(h, cudaMalloc(&h->d_snap_status, sizeof(int)));
-    }
+    // each resource under its own check: maddy_schedule_gtp may have created the copy stream already
+    if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->snap_staged) CU(h, cudaEventCreateWithFlags(&h->snap_staged, cudaEventDisableTiming));
+    if (!h->d_snap_status) CU(h, cudaMalloc(&h->d_snap_status, sizeof(int)));
     if (what & MADDY_SNAP_COORDS) {
         if (!h->snap_r) {
             CU(h, cudaMallocHost(&h->snap_r, aos_bytes));
@@ -1279,6 +1287,18 @@ extern "C" int maddy_tea_update(maddy_handle *h, long long step)
     }
     return check_status(h);
 }
+extern "C" int maddy_download_tea(maddy_handle *h, float *ci4, float *epsilon, float *beta)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!h->p.tea_on) return fail(h, MADDY_EINVAL, "maddy_download_tea: tea_on is off");
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    if (ci4) CU(h, cudaMemcpyAsync(ci4, h->a.tea_ci, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (epsilon) CU(h, cudaMemcpyAsync(epsilon, h->a.tea_eps, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (beta) CU(h, cudaMemcpyAsync(beta, h->a.tea_beta, (size_t)h->a.ntr * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
 extern "C" int maddy_tea_integrate(maddy_handle *h)
 {
     if (!h) return MADDY_EINVAL;
@@ -1467,5 +1487,81 @@ extern "C" int maddy_ensemble_allreduce(maddy_handle **hs, int n, double **value
         CU(hs[g], cudaStreamSynchronize(hs[g]->stream));
         cudaFree(dbuf[g]);
     }
+    return MADDY_OK;
+}
+
+// Ensemble statistics of the per-trajectory energies over ALL handles, device-resident: every handle reduces the energies it
+// evaluated last (maddy_energies / maddy_rebuild_and_energies / maddy_snapshot_begin with MADDY_SNAP_ENERGIES) to
+// [sum(7), sum of squares(7), count, 0] with one small kernel on its own stream, the 16 doubles are all-reduced with
+// ncclAllReduce (one group call, in stream order, so nothing waits on the host), and the result travels to pinned memory on
+// the copy stream beside whatever the handle's stream runs next.  _end blocks only until that copy has landed.
+extern "C" int maddy_ensemble_stats_begin(maddy_handle **hs, int n)
+{
+    if (!hs || n <= 0) return MADDY_EINVAL;
+    maddy_handle *h0 = hs[0];
+    for (int g = 0; g < n; g++)
+        if (!hs[g]) return MADDY_EINVAL;
+    if (n > 1) {
+        if (!g_nccl.load()) return fail(h0, MADDY_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+        std::vector<int> devs(n);
+        for (int g = 0; g < n; g++) devs[g] = hs[g]->p.device;
+        if (g_comm_devs != devs) {
+            for (ncclComm_t c : g_comms) g_nccl.CommDestroy(c);
+            g_comms.assign(n, nullptr);
+            int r = g_nccl.CommInitAll(g_comms.data(), n, devs.data());
+            if (r != 0) {
+                g_comms.clear();
+                g_comm_devs.clear();
+                return fail(h0, MADDY_ENCCL, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+            }
+            g_comm_devs = devs;
+        }
+    }
+    for (int g = 0; g < n; g++) {
+        maddy_handle *h = hs[g];
+        CU(h, cudaSetDevice(h->p.device));
+        if (!h->d_ens) CU(h, cudaMalloc(&h->d_ens, 16 * sizeof(double)));
+        if (!h->h_ens) CU(h, cudaMallocHost(&h->h_ens, 16 * sizeof(double)));
+        if (!h->ens_ready) CU(h, cudaEventCreateWithFlags(&h->ens_ready, cudaEventDisableTiming));
+        if (!h->ens_done) CU(h, cudaEventCreateWithFlags(&h->ens_done, cudaEventDisableTiming));
+        if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        cudaError_t e = launch_ensemble_stats(h->a.en_traj, h->a.ntr, h->d_ens, h->stream);
+        if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "ensemble_stats_kernel launch: %s", cudaGetErrorString(e));
+        h->launches++;
+    }
+    if (n > 1) {
+        g_nccl.GroupStart();
+        int rr = 0;
+        for (int g = 0; g < n; g++) {
+            cudaSetDevice(hs[g]->p.device);
+            int r = g_nccl.AllReduce(hs[g]->d_ens, hs[g]->d_ens, 16, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_comms[g], hs[g]->stream);
+            if (r) rr = r;
+        }
+        int r2 = g_nccl.GroupEnd();
+        if (rr || r2) return fail(h0, MADDY_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rr ? rr : r2) : "error");
+    }
+    for (int g = 0; g < n; g++) {
+        maddy_handle *h = hs[g];
+        CU(h, cudaSetDevice(h->p.device));
+        CU(h, cudaEventRecord(h->ens_ready, h->stream));
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->ens_ready, 0));
+        CU(h, cudaMemcpyAsync(h->h_ens, h->d_ens, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(h, cudaEventRecord(h->ens_done, h->copy_stream));
+        h->ens_pending = true;
+    }
+    return MADDY_OK;
+}
+extern "C" int maddy_ensemble_stats_end(maddy_handle **hs, int n, double *out16)
+{
+    if (!hs || n <= 0 || !out16) return MADDY_EINVAL;
+    for (int g = 0; g < n; g++) {
+        maddy_handle *h = hs[g];
+        if (!h) return MADDY_EINVAL;
+        if (!h->ens_pending) return fail(h, MADDY_EINVAL, "maddy_ensemble_stats_end without maddy_ensemble_stats_begin");
+        CU(h, cudaSetDevice(h->p.device));
+        CU(h, cudaEventSynchronize(h->ens_done));
+        h->ens_pending = false;
+    }
+    memcpy(out16, hs[0]->h_ens, 16 * sizeof(double)); // every handle holds the same all-reduced record
     return MADDY_OK;
 }

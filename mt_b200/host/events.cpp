@@ -401,6 +401,39 @@ void compute(System &s, bool fused, ComputeStats *stats)
         }
     } writer_scope(s);
     s.energies.assign((size_t)Ntr * 7, 0.0);
+    // periodic ensemble reduction: per-term sum / sum of squares / count of the per-trajectory energies, reduced
+    // on the GPUs and all-reduced with NCCL in every stride block with energies; one line per stride in ensemble.dat
+    const bool ens_on = hp.out_energy && (G > 1 || getenv("MADDY_ENSEMBLE_STATS"));
+    std::vector<maddy_handle *> ens_handles;
+    for (Shard &d : sh.v) ens_handles.push_back(d.h);
+    FILE *ens_file = nullptr;
+    struct EnsClose {
+        FILE *&f;
+        ~EnsClose() { if (f) fclose(f); }
+    } ens_close{ens_file};
+    if (ens_on) {
+        s.ensemble_stats.assign(MADDY_ENSEMBLE_STATS, 0.0);
+        if (s.write_files) ens_file = fopen("ensemble.dat", hp.resume ? "a" : "w");
+    }
+    auto ens_begin = [&] {
+        if (!ens_on) return;
+        int rc = maddy_ensemble_stats_begin(ens_handles.data(), G);
+        if (rc != MADDY_OK) die("maddy_ensemble_stats_begin failed (%d): %s", rc, maddy_last_error(ens_handles[0]));
+    };
+    auto ens_end = [&](long long at) {
+        if (!ens_on) return;
+        int rc = maddy_ensemble_stats_end(ens_handles.data(), G, s.ensemble_stats.data());
+        if (rc != MADDY_OK) die("maddy_ensemble_stats_end failed (%d): %s", rc, maddy_last_error(ens_handles[0]));
+        st.d2h_bytes += (double)G * MADDY_ENSEMBLE_STATS * 8;
+        if (!ens_file) return;
+        const double *q = s.ensemble_stats.data(), cnt = q[14] > 0 ? q[14] : 1.0;
+        fprintf(ens_file, "%lld\t%d", at, (int)q[14]); // step, trajectories, then mean and standard deviation of each energy term
+        for (int k = 0; k < 7; k++) {
+            const double mean = q[k] / cnt, var = q[7 + k] / cnt - mean * mean;
+            fprintf(ens_file, "\t%f\t%f", mean, var > 0 ? sqrt(var) : 0.0);
+        }
+        fputc('\n', ens_file);
+    };
 
     std::vector<int> mt_len(Ntr, 0), mt_len_prev(Ntr, 0);
     auto for_each = [&](auto fn) {
@@ -584,6 +617,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
             // zero), so the read-back is only QUEUED here; it is collected after the next window has been launched.
             const unsigned what = MADDY_SNAP_COORDS | (hp.out_energy ? MADDY_SNAP_ENERGIES : 0u) | (fused_stride_energy ? MADDY_SNAP_REBUILD : 0u);
             for_each([&](Shard &d) { ck(maddy_snapshot_begin(d.h, what), d.h, "maddy_snapshot_begin"); });
+            if (hp.out_energy) ens_begin();
             st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0);
         } else if (stride_now) {
             if (hp.out_energy) {
@@ -593,6 +627,8 @@ void compute(System &s, bool fused, ComputeStats *stats)
                     else ck(maddy_energies(d.h, out, nullptr), d.h, "maddy_energies");
                 });
                 st.d2h_bytes += (double)Ntr * 7 * 8;
+                ens_begin();
+                ens_end(step);
             }
             if (hp.out_force) {
                 for_each([&](Shard &d) { ck(maddy_download_forces(d.h, &s.f[(size_t)d.first * N * 7]), d.h, "maddy_download_forces"); });
@@ -676,6 +712,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
                 ck(maddy_snapshot_end(d.h, &s.r[(size_t)d.first * N * 7], nullptr, hp.out_energy ? &s.energies[(size_t)d.first * 7] : nullptr),
                    d.h, "maddy_snapshot_end");
             });
+            if (hp.out_energy) ens_end(step);
             prof.end("stride collect (wait + transpose)");
             mark("snapshot collected", step);
             prof.begin();

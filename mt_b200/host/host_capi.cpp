@@ -77,6 +77,7 @@ int *mt_system_gtp(mt_system *s) { return s->sys.gtp.data(); }
 int *mt_system_on_tubule(mt_system *s, int prev) { return prev ? s->sys.on_tubule_prev.data() : s->sys.on_tubule_cur.data(); }
 unsigned char *mt_system_extra(mt_system *s) { return s->sys.extra.data(); }
 double *mt_system_energies(mt_system *s) { return s->sys.energies.data(); }
+const double *mt_system_ensemble_stats(const mt_system *s) { return s->sys.ensemble_stats.empty() ? nullptr : s->sys.ensemble_stats.data(); }
 int mt_system_srand(mt_system *s, unsigned seed)
 {
     s->sys.rng.seed(seed);

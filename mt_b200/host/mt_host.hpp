@@ -195,6 +195,9 @@ struct System {
     std::vector<unsigned char> fixed, extra;
     std::vector<int> mon_type, gtp, on_tubule_cur, on_tubule_prev;
     std::vector<double> energies; // [Ntr][7] per-trajectory sums of the last energy evaluation
+    // ensemble statistics of the last stride with energies (maddy_ensemble_stats: sum(7), sum of squares(7), count, 0),
+    // all-reduced over the GPUs with NCCL; filled when the run is sharded over more than one GPU (or MADDY_ENSEMBLE_STATS=1)
+    std::vector<double> ensemble_stats;
     bool quiet = false;           // suppress the reference's stdout chatter (tests / bench)
     std::string *event_log = nullptr; // when set, hydrolyse() appends its messages here instead of printing them (the
                                       // step loop evaluates events ahead of time and prints them in the reference's order)

@@ -47,6 +47,7 @@ def make_rundir(root, structure=("lattice", 40, 0), config: Optional[Dict[str, o
     """Create <root>/{config.conf,morse.conf,cond.conf,dcd/xyz.pdb,dcd/ang.pdb,restart/} and return <root>.
 
     structure: ("lattice", mt_len, tail_len) | ("reserve", mt_len, mt_extra) | ("free", n_dimers, radius, height, seed)
+               | ("files", xyz.pdb, ang.pdb)
     """
     root = Path(root)
     (root / "dcd").mkdir(parents=True, exist_ok=True)
@@ -58,9 +59,15 @@ def make_rundir(root, structure=("lattice", 40, 0), config: Optional[Dict[str, o
         xyz, ang = structures.lattice_with_reserve(structure[1], structure[2])
     elif kind == "free":
         xyz, ang = structures.free_dimers(*structure[1:])
+    elif kind == "files":  # an existing PDB pair (e.g. the reference's initial/*.pdb), copied byte for byte
+        import shutil
+        shutil.copyfile(structure[1], root / "dcd" / "xyz.pdb")
+        shutil.copyfile(structure[2], root / "dcd" / "ang.pdb")
+        xyz = None
     else:
         raise ValueError(kind)
-    structures.write_pair(xyz, ang, root / "dcd" / "xyz.pdb", root / "dcd" / "ang.pdb")
+    if xyz is not None:
+        structures.write_pair(xyz, ang, root / "dcd" / "xyz.pdb", root / "dcd" / "ang.pdb")
     cfg = dict(CONFIG_DEFAULT)
     cfg.update(config or {})
     ff = dict(FORCEFIELD_DEFAULT)

@@ -43,3 +43,18 @@ def test_ensemble_allreduce_nccl(rundir, load_system):
     rc = capi.lib.maddy_ensemble_allreduce(hs, 2, bufs, 7)
     assert rc == 0, capi.lib.maddy_last_error(e0._h)
     assert np.allclose(v0, want, rtol=1e-14) and np.allclose(v1, want, rtol=1e-14)
+
+
+def test_ensemble_stats_two_gpus_equal_host_statistics(rundir, load_system):
+    """maddy_ensemble_stats in the stride block of the one-host loop (NCCL all-reduce over the shards) against numpy
+    statistics of the per-trajectory energies the same run returns."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = rundir("mt40_single", runnum=6, steps=201, stride=100)
+    s = load_system(d)
+    s.srand(1234567)
+    s.compute(n_gpus=2)
+    st, e = s.ensemble_stats, s.energies
+    assert st is not None and st[14] == 6
+    assert np.allclose(st[:7], e.sum(axis=0), rtol=1e-13, atol=1e-9)
+    assert np.allclose(st[7:14], (e * e).sum(axis=0), rtol=1e-13, atol=1e-9)

@@ -467,6 +467,45 @@ def test_gtp_schedule_equals_explicit_uploads(rundir, load_system):
     assert np.array_equal(c.coords(), d.coords())
 
 
+def test_snapshot_after_schedule_gtp_on_fresh_handle(rundir, load_system):
+    """maddy_schedule_gtp and maddy_snapshot_begin are documented as independent: a schedule handed over BEFORE the
+    first snapshot of a handle (both lazily create the copy stream) must not break the snapshot."""
+    s = load_system(rundir("mt40_ensemble", runnum=3), ["hydrolysis=no"])
+    rng = np.random.default_rng(5)
+    g = (rng.random((3, s.Ntot // 2)) > 0.3).astype(np.int32).repeat(2, axis=1)
+    a, b = Engine(s), Engine(s)
+    a.schedule_gtp(20, 20, g[None])
+    a.run(0, 40)
+    a.snapshot_begin(coords=True, energies=True, rebuild=True)
+    snap = a.snapshot_end()
+    b.run(0, 20)
+    b.upload_gtp(g)
+    b.run(20, 20)
+    assert np.array_equal(snap["coords"], b.coords())
+    assert np.array_equal(snap["energies"], b.rebuild_and_energies())
+
+
+def test_ensemble_stats_single_gpu(rundir, load_system, monkeypatch):
+    """device-side ensemble reduction of the stride block (no collective at one GPU) == numpy over the energies of that stride"""
+    monkeypatch.setenv("MADDY_ENSEMBLE_STATS", "1")
+    s = load_system(rundir("mt40_single", runnum=5, steps=201, stride=100))
+    s.srand(1234567)
+    s.compute()
+    st, e = s.ensemble_stats, s.energies
+    assert st is not None and st[14] == 5 and st[15] == 0
+    assert np.allclose(st[:7], e.sum(axis=0), rtol=1e-13, atol=1e-9)
+    assert np.allclose(st[7:14], (e * e).sum(axis=0), rtol=1e-13, atol=1e-9)
+    # C-ABI, two handles on the same device: n = 1 calls need no communicator
+    a = Engine(s, traj_first=0, n_tr_local=3)
+    ea = a.energies()
+    hs = (C.c_void_p * 1)(a._h)
+    out = np.zeros(16)
+    assert capi.lib.maddy_ensemble_stats_begin(hs, 1) == 0
+    assert capi.lib.maddy_ensemble_stats_end(hs, 1, as_ptr(out, C.c_double)) == 0
+    assert np.allclose(out[:7], ea.sum(axis=0), rtol=1e-13, atol=1e-9) and out[14] == 3
+    assert capi.lib.maddy_ensemble_stats_end(hs, 1, as_ptr(out, C.c_double)) != 0  # nothing pending
+
+
 def test_drop_in_const_conc_vs_reference_executable(rundir):
     """BASELINE configs[2] shape (long MT + reserve dimers, walls, constant concentration): the insertion events of
     change_conc() consume the libc rand() stream interleaved with hydrolysis; both executables must print the same
