@@ -6,6 +6,8 @@
   oracle/_build/libmaddy_oracle.so   CPU restatement used by tests / smoke / cpu_baseline (gcc)
   oracle/_ref/{mt,ref_probe} the reference's own CUDA build, compiled IN PLACE from
                              /root/reference/src when that tree is present (nvcc)
+  oracle/_ref/mt_stub        the reference's own HOST (main/preparator/updater/...) with compute() replaced by
+                             oracle/compute_b200_stub.cpp, linked against libmaddy_b200.so
   oracle/_ref/{disc,p3d22d,temp_calc}  the reference's analysis tools (scripts/), same rule (g++)
 
 Run:  python -m mt_b200.build [--force] [--no-ref]
@@ -34,6 +36,7 @@ MT_BIN = PKG / "mt"
 LIB_ORACLE = ORACLE / "_build" / "libmaddy_oracle.so"
 REF_MT = ORACLE / "_ref" / "mt"
 REF_PROBE = ORACLE / "_ref" / "ref_probe"
+REF_STUB = ORACLE / "_ref" / "mt_stub"
 
 
 def _stale(target: Path, sources) -> bool:
@@ -123,6 +126,14 @@ def build_reference(force=False):
         sdir = REFERENCE / "scripts" / d
         if sdir.is_dir() and (force or not (REF_MT.parent / out).exists()):
             _run(["g++", "-O3", "-w", "-o", REF_MT.parent / out, sdir / main, sdir / "dcdio.cpp", sdir / "pdbio.cpp"])
+    # the reference's own host with compute() swapped for the C-ABI binding: every reference
+    # source except its four CUDA units, plus oracle/compute_b200_stub.cpp, linked against libmaddy_b200.so
+    stub_src = ORACLE / "compute_b200_stub.cpp"
+    if stub_src.exists() and (force or _stale(REF_STUB, [stub_src, LIB_KERNELS, ROOT / "include" / "maddy_b200.h"])):
+        build_kernels()
+        host_only = [f for f in common if not f.endswith(".cu")]
+        _run([NVCC, "-O2", "-DCUDA", "-DMORSE", "-w", f"-I{src}", f"-I{ROOT / 'include'}", "-o", REF_STUB, *[src / f for f in host_only],
+              src / "main.cpp", stub_src, f"-L{PKG}", "-lmaddy_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../mt_b200"])
     probe_src = ORACLE / "ref_probe.cu"
     if probe_src.exists() and (force or _stale(REF_PROBE, [probe_src])):
         _run([NVCC, *flags, "-o", REF_PROBE, *[src / f for f in common], probe_src])

@@ -4,7 +4,10 @@
  * The reference's restart path reads coordinates from XYZ text files (preparator.cpp:664-684) and its writer
  * (writeRestart, :686-714) is never called; a run resumed that way starts a different random trajectory.  A
  * checkpoint here holds everything the step loop's future depends on, so that
- *     run(0 .. T)   ==   run(0 .. S), checkpoint, new process, resume(S .. T)        bit for bit:
+ *     run(0 .. T)   ==   run(0 .. S), checkpoint, new process, resume(S .. T)        bit for bit
+ * in the state, the DCD trajectories and mt_len.dat (both trimmed back to the checkpoint step on resume).  NOT covered:
+ * dcd/hydrolysis.pdb and the in-situ analysis files are appended as they stand (frames a crashed run wrote after its last
+ * checkpoint stay, in-situ frame numbers restart at 1 and the first resumed frame has no temperature line).  Held:
  * coordinates as raw float bits (no text round trip, no angle re-wrapping), both HybridTaus streams of every
  * monomer, GTP / reserve / on-tubule flags (current and previous stride), the tubule lengths, the state of the host
  * rand() generator that drives hydrolysis and insertion, the step, and whether the hydrolysis event of that step has
@@ -16,6 +19,8 @@
 #include <cstdio>
 #include <unistd.h>
 #include <cstring>
+#include <string>
+#include <cstdlib>
 #include "mt_host.hpp"
 
 namespace mt {
@@ -157,6 +162,28 @@ void checkpoint_trim_outputs(System &s, long long step)
             if (size < want) die("Resuming at step %lld: '%s' holds fewer than %lld frames", step, name->c_str(), frames);
             if (size > want && truncate(name->c_str(), want) != 0) die("Truncating '%s'", name->c_str());
         }
+    // mt_len.dat (one line per stride step, first field = step; updater.cpp:213-219): lines of strides at or after `step` go
+    {
+        FILE *f = fopen("mt_len.dat", "rb");
+        if (f) {
+            std::string keep;
+            char *line = nullptr;
+            size_t cap = 0;
+            ssize_t len;
+            while ((len = getline(&line, &cap, f)) > 0) {
+                char *end = nullptr;
+                const long long at = strtoll(line, &end, 10);
+                if (end == line || at >= step) break;
+                keep.append(line, (size_t)len);
+            }
+            free(line);
+            fclose(f);
+            f = fopen("mt_len.dat", "wb");
+            if (!f) die("Rewriting mt_len.dat");
+            fwrite(keep.data(), 1, keep.size(), f);
+            fclose(f);
+        }
+    }
 }
 
 } // namespace mt

@@ -477,7 +477,10 @@ void compute(System &s, bool fused, ComputeStats *stats)
     }
     const long long start_step = step;
     // checkpoint = the state at the TOP of step `at`, before any of that step's events
+    // Invariant: checkpoints are taken only at window boundaries that are stride steps (system.cpp forces checkpoint_freq to be
+    // a multiple of stride), where no pre-drawn hydrolysis schedule is pending; CheckpointState does not carry sched_gtp.
     auto write_checkpoint = [&](long long at) {
+        if (!sched_gtp.empty()) die("checkpoint at step %lld with a pending GTP schedule (checkpoint_freq must be a multiple of stride)", at);
         if (pending_output) flush_pending();
         CheckpointState out;
         out.step = at;

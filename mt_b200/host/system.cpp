@@ -223,6 +223,9 @@ void init_parameters(System &s, const std::string &config, const std::vector<std
     hp.insitu = tb.yesno("insitu_analysis", 0);
     long long resume_step = 0;
     hp.resume = hp.is_restart && !hp.checkpoint.empty() && checkpoint_peek(hp.checkpoint, &resume_step);
+    // every modulus of the step loop, checked before anything divides by it (the reference would die with SIGFPE)
+    if (hp.stride <= 0) die("stride must be positive");
+    if (par.ljpairsupdatefreq <= 0) die("LJPairsUpdateFreq must be positive");
     if (!hp.checkpoint.empty()) {
         if (hp.steps % par.ljpairsupdatefreq != 0)
             die("checkpoint: steps (%lld) must be a multiple of LJPairsUpdateFreq (%d)", hp.steps, par.ljpairsupdatefreq);
@@ -312,6 +315,7 @@ void init_parameters(System &s, const std::string &config, const std::vector<std
         hp.hydrolysis = true;
         hp.khydro = tb.real("khydro");
         hp.hydrostep = (long)(0.02 * 1000000000000 / (par.dt * hp.khydro)); // 2 % probability threshold
+        if (hp.hydrostep <= 0) die("hydrolysis: dt * khydro = %g gives a hydrolysis period of %lld steps (must be >= 1)", (double)(par.dt * hp.khydro), (long long)hp.hydrostep);
     } else hp.hydrolysis = false;
     for (size_t q = 0; q < s.gtp.size(); q++) s.gtp[q] = 1;
 

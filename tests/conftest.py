@@ -1,4 +1,5 @@
 """pytest configuration: the `gpu` marker, in-tree build of the native libraries, shared fixtures."""
+import hashlib
 import os
 import sys
 import tempfile
@@ -35,7 +36,8 @@ def rundir(tmp_root, request):
 
     def make(name="mt40_single", structure=None, forcefield=None, conditions=None, **config):
         counter["n"] += 1
-        d = tmp_root / f"{request.node.name[:40]}_{counter['n']}"
+        tag = hashlib.sha1(request.node.nodeid.encode()).hexdigest()[:6]  # parametrized ids share their first 40 characters
+        d = tmp_root / f"{request.node.name[:40]}_{tag}_{counter['n']}"
         if structure is None:
             return workspace.make_baseline_rundir(d, name, **config)
         spec = workspace.BASELINE_CONFIGS[name]

@@ -605,6 +605,8 @@ def test_checkpoint_restart_is_bit_exact(case, stride, over, rundir):
     # a crashed run may have written frames past its last checkpoint: resuming drops them
     with open(d_part / "dcd" / "run_0.dcd", "ab") as f:
         f.write(b"\0" * 100)
+    with open(d_part / "mt_len.dat", "a") as f:  # ... and a tubule-length line of a stride past the checkpoint
+        f.write("200\t9.900000\t9.900000\t9.900000\t\n")
     part = run(d_part, ["steps=400", "checkpoint=ck.bin", "is_restart=yes"])
     for a, b in zip(full, part):
         assert np.array_equal(a, b)

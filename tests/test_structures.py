@@ -28,15 +28,32 @@ def test_lattice_matches_reference_files(key, tmp_path):
     assert (tmp_path / "a.pdb").read_bytes() == (REF / SHA[key][1]).read_bytes()
 
 
-def test_lattice_checksums_are_stable(tmp_path):
-    """Recorded digests (valid without the reference tree)."""
-    xyz, ang = structures.lattice(40, 0)
+DIGESTS = dict(l.split() for l in (Path(__file__).parent / "golden" / "structure_sha256.txt").read_text().splitlines() if l.strip())
+SHA_ALL = dict(SHA)
+SHA_ALL[(70, 0)] = ("xyz_70.pdb", "ang_70.pdb")
+
+
+@pytest.mark.parametrize("key", list(SHA_ALL), ids=str)
+def test_lattice_checksums_are_stable(key, tmp_path):
+    """Digests recorded while the generated files compared byte-equal to /root/reference/initial/{xyz,ang}_N.pdb: the
+    byte-identity claim holds where the reference tree is absent (GPU box) too — every lattice the BASELINE configs use."""
+    xyz, ang = structures.lattice(*key)
     structures.write_pair(xyz, ang, tmp_path / "x.pdb", tmp_path / "a.pdb")
-    hx = hashlib.sha256((tmp_path / "x.pdb").read_bytes()).hexdigest()
-    ha = hashlib.sha256((tmp_path / "a.pdb").read_bytes()).hexdigest()
-    digests = (Path(__file__).parent / "golden" / "structure_sha256.txt")
-    rec = dict(l.split() for l in digests.read_text().splitlines())
-    assert rec["xyz_40"] == hx and rec["ang_40"] == ha
+    nx, na = (n[:-4] for n in SHA_ALL[key])
+    assert DIGESTS[nx] == hashlib.sha256((tmp_path / "x.pdb").read_bytes()).hexdigest()
+    assert DIGESTS[na] == hashlib.sha256((tmp_path / "a.pdb").read_bytes()).hexdigest()
+
+
+def test_reference_input_fixtures_are_the_reference_files():
+    """tests/golden/inputs/*.pdb: digests recorded from /root/reference/initial; byte-compared where that tree exists"""
+    inputs = Path(__file__).parent / "golden" / "inputs"
+    names = {"cylinder_xyz.pdb": "cylinder_xyz.pdb", "cylinder_ang.pdb": "cylinder_ang.pdb",
+             "constconc125_xyz.pdb": "constconc/125/xyz.pdb", "constconc125_ang.pdb": "constconc/125/ang.pdb"}
+    for here, there in names.items():
+        data = (inputs / here).read_bytes()
+        assert DIGESTS["inputs/" + here] == hashlib.sha256(data).hexdigest()
+        if REF.is_dir():
+            assert data == (REF / there).read_bytes()
 
 
 def test_lattice_geometry():
