@@ -191,8 +191,28 @@ int maddy_rebuild_and_energies(maddy_handle *h, double *out_per_traj, double *ou
 #define MADDY_SNAP_FORCES 2u
 #define MADDY_SNAP_ENERGIES 4u
 #define MADDY_SNAP_REBUILD 8u /* with ENERGIES: rebuild the lists first, as maddy_rebuild_and_energies does */
+/* MADDY_SNAP_ONTUBULE: mt_length()'s classification (updater.cpp:154-227, the predicate of :161) of the state being
+ * snapshotted, evaluated on the device AFTER the energies (which read the flags of the previous stride, as
+ * compute_cuda.cu:1165 precedes :1186-1190).  Exact, not approximate: the radius test is IEEE float arithmetic and the
+ * `cosf(theta) > cosf(ANG_THRES)` test is applied as intervals of |theta| whose end points were bisected with the
+ * calling process's own cosf at maddy_create.  MADDY_SNAP_ONTUBULE_APPLY additionally makes the result the handle's
+ * current on-tubule flags, as maddy_upload_on_tubule of the same values would (compute_cuda.cu:1190) - without the
+ * host round trip.  Results: maddy_snapshot_tubule_lengths (counts only, available first) and
+ * maddy_snapshot_on_tubule (flags, after maddy_snapshot_end). */
+#define MADDY_SNAP_ONTUBULE 16u
+#define MADDY_SNAP_ONTUBULE_APPLY 32u
 int maddy_snapshot_begin(maddy_handle *h, unsigned what);
 int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *forces_aos7, double *energies_per_traj);
+/* Per-trajectory on-tubule counts (`sum` of updater.cpp:164-170) of the snapshot in flight: blocks only until the
+ * (n_tr_local + 1)-int record at the head of the read-back has landed, i.e. a few microseconds behind the classification
+ * kernel, long before the coordinates (also valid for the snapshot collected last).  *undecided != 0: some |theta| lies beyond the range the exact rule covers
+ * (several turns away from zero); the caller must then classify on the host and upload (nothing is guessed). */
+int maddy_snapshot_tubule_lengths(maddy_handle *h, int *mt_len, int *undecided);
+/* 1 when the exact on-tubule rule could be derived from this process's cosf (it then is, for every libm seen so far);
+ * 0: MADDY_SNAP_ONTUBULE is refused and the caller classifies on the host. */
+int maddy_has_exact_on_tubule(const maddy_handle *h);
+/* on_tubule_cur[n_tr_local * n_tot] / mt_len[n_tr_local] of the snapshot collected last by maddy_snapshot_end. */
+int maddy_snapshot_on_tubule(maddy_handle *h, int *on_tubule_cur, int *mt_len);
 /* device-resident result of the last maddy_energies call: [n_tr_local][7] doubles */
 void *maddy_energies_device(maddy_handle *h);
 
@@ -203,6 +223,13 @@ int maddy_upload_coords(maddy_handle *h, const float *coords_aos7); /* no angle 
 int maddy_upload_gtp(maddy_handle *h, const int *gtp);
 int maddy_upload_on_tubule(maddy_handle *h, const int *on_tubule_cur);
 int maddy_upload_extra(maddy_handle *h, const unsigned char *extra);
+/* change_conc()'s insertions (updater.cpp:118-135) as a sparse update: for k < n_insert the reserve dimer
+ * (index[k], index[k] + 1) - LOCAL monomer indices traj_local * n_tot + i - leaves the reserve; its first monomer is
+ * placed at {xyzz[4k], xyzz[4k+1], xyzz[4k+2]}, its second at {xyzz[4k], xyzz[4k+1], xyzz[4k+3]} (angles untouched; the
+ * caller evaluates z + 2 r_mon itself, updater.cpp:133).  Same device state afterwards as maddy_upload_extra +
+ * maddy_upload_coords of the host arrays change_conc() modified (compute_cuda.cu:1202-1204), without moving the whole
+ * ensemble over PCIe twice.  Asynchronous (the arrays are copied before the call returns). */
+int maddy_insert_dimers(maddy_handle *h, int n_insert, const int *index, const float *xyzz);
 /* lists in the reference layout [traj][i][capacity] / [traj][i], capacity =
  * max_longitudinal / max_lateral / MADDY_LJ_CAPACITY */
 int maddy_download_list(maddy_handle *h, int kind, int *counts, int *entries);

@@ -277,10 +277,11 @@ class Engine:
         self._ck(capi.lib.maddy_list_stats(self._h, out, int(reset)))
         return {"near_refresh": out[0], "candidate_rescan": out[1], "all_pairs_fallback": out[2], "near_overflow": out[3]}
 
-    def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False):
+    def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False, on_tubule=False, apply_on_tubule=False):
         """queue the stride read-back (maddy_snapshot_begin); work queued afterwards overlaps with snapshot_end()"""
         what = (capi.SNAP_COORDS if coords else 0) | (capi.SNAP_FORCES if forces else 0) | (capi.SNAP_ENERGIES if energies else 0) \
-            | (capi.SNAP_REBUILD if rebuild else 0)
+            | (capi.SNAP_REBUILD if rebuild else 0) | (capi.SNAP_ONTUBULE if on_tubule or apply_on_tubule else 0) \
+            | (capi.SNAP_ONTUBULE_APPLY if apply_on_tubule else 0)
         self._snap = what
         self._ck(capi.lib.maddy_snapshot_begin(self._h, what))
 
@@ -293,7 +294,26 @@ class Engine:
         self._ck(capi.lib.maddy_snapshot_end(self._h, as_ptr(c, C.c_float) if c is not None else None,
                                              as_ptr(f, C.c_float) if f is not None else None,
                                              as_ptr(e, C.c_double) if e is not None else None))
-        return {"coords": c, "forces": f, "energies": e}
+        out = {"coords": c, "forces": f, "energies": e}
+        if what & capi.SNAP_ONTUBULE:
+            on = np.empty((self.ntr, self.N), dtype=np.int32)
+            ln = np.empty(self.ntr, dtype=np.int32)
+            self._ck(capi.lib.maddy_snapshot_on_tubule(self._h, as_ptr(on, C.c_int), as_ptr(ln, C.c_int)))
+            out["on_tubule"], out["mt_len"] = on, ln
+        return out
+
+    def snapshot_tubule_lengths(self):
+        """(mt_len [ntr], undecided) of the snapshot in flight: waits for the counts only (maddy_snapshot_tubule_lengths)"""
+        ln = np.empty(self.ntr, dtype=np.int32)
+        und = C.c_int()
+        self._ck(capi.lib.maddy_snapshot_tubule_lengths(self._h, as_ptr(ln, C.c_int), C.byref(und)))
+        return ln, und.value
+
+    def insert_dimers(self, index, xyzz):
+        """sparse constant-concentration insertion (maddy_insert_dimers): index [k] local first-monomer ids, xyzz [k, 4]"""
+        idx = np.ascontiguousarray(index, dtype=np.int32)
+        v = np.ascontiguousarray(xyzz, dtype=np.float32).reshape(-1, 4)
+        self._ck(capi.lib.maddy_insert_dimers(self._h, int(idx.size), as_ptr(idx, C.c_int), as_ptr(v, C.c_float)))
 
     # ---- in-situ analysis (SURVEY 8 f4; scripts/temp_calc, scripts/disas_speed of the reference)
     def analysis_setup(self, chain, resid, name1, n_pf: int = 13):

@@ -19,6 +19,7 @@ ZERO_SENTINEL = 999999
 LJ_CAPACITY = 256
 RUN_SKIP_FIRST_REBUILD = 1
 SNAP_COORDS, SNAP_FORCES, SNAP_ENERGIES, SNAP_REBUILD = 1, 2, 4, 8
+SNAP_ONTUBULE, SNAP_ONTUBULE_APPLY = 16, 32
 LIST_LONGITUDINAL, LIST_LATERAL, LIST_LJ = 0, 1, 2
 LOAD_QUIET, LOAD_NO_FILES = 1, 2
 
@@ -99,6 +100,7 @@ KERNEL_SYMBOLS = [
     "maddy_launch_count", "maddy_schedule_gtp", "maddy_rebuild_and_energies", "maddy_snapshot_begin", "maddy_snapshot_end",
     "maddy_list_stats", "maddy_analysis_setup", "maddy_analysis_reference", "maddy_analysis_temperature", "maddy_analysis_project",
     "maddy_analysis_protofilaments", "maddy_ensemble_stats_begin", "maddy_ensemble_stats_end", "maddy_download_tea",
+    "maddy_snapshot_tubule_lengths", "maddy_snapshot_on_tubule", "maddy_insert_dimers", "maddy_has_exact_on_tubule",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
@@ -145,6 +147,10 @@ _sig(lib.maddy_analysis_project, _i, [_vp, _pf])
 _sig(lib.maddy_analysis_protofilaments, _i, [_vp, _pi])
 _sig(lib.maddy_snapshot_begin, _i, [_vp, _u])
 _sig(lib.maddy_snapshot_end, _i, [_vp, _pf, _pf, _pd])
+_sig(lib.maddy_snapshot_tubule_lengths, _i, [_vp, _pi, _pi])
+_sig(lib.maddy_snapshot_on_tubule, _i, [_vp, _pi, _pi])
+_sig(lib.maddy_insert_dimers, _i, [_vp, _i, _pi, _pf])
+_sig(lib.maddy_has_exact_on_tubule, _i, [_vp])
 
 _sig(hostlib.mt_host_last_error, C.c_char_p, [])
 _sig(hostlib.mt_system_load, _i, [C.c_char_p, _i, C.POINTER(C.c_char_p), _u, C.POINTER(_vp)])

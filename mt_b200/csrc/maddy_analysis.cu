@@ -155,6 +155,89 @@ __global__ void __launch_bounds__(AN_THREADS) ensemble_stats_kernel(const double
     }
 }
 
+// mt_length() of the reference (updater.cpp:154-227) on the device, EXACTLY: on the tubule iff
+//   rad < R_MT + R_THRES  &&  rad > 1.0  &&  cosf(theta) > cosf(ANG_THRES),   rad = sqrtf(x*x + y*y)  (float products, float sum).
+// The radius part is IEEE arithmetic (__fmul_rn/__fadd_rn/__fsqrt_rn = what the host compiler emits without contraction).
+// The cosine part cannot be evaluated here (the host's libm cosf is the authority), so the caller hands over the float
+// thresholds at which ITS cosf crosses cosf(ANG_THRES) on each monotone branch (maddy_ontub_rule, bisected on the host):
+// with a = |theta|, on iff a in [0, e0) U (e1, e2) U (e3, e4) ...; a >= a_max (several turns away) is reported as
+// undecided in the status word.  One CTA per trajectory; flags to out_flags (and to live_flags when apply != 0), the
+// per-trajectory count to out_count.
+__global__ void __launch_bounds__(AN_THREADS) ontubule_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ ang, int N, OnTubRule rule,
+                                                              uint8_t *__restrict__ out_flags, uint8_t *__restrict__ live_flags, int apply,
+                                                              int *__restrict__ out_count, int *__restrict__ status)
+{
+    __shared__ int wsum[AN_THREADS / 32];
+    const int traj = blockIdx.x;
+    const size_t base = (size_t)traj * N;
+    int sum = 0, undecided = 0;
+    for (int i = threadIdx.x; i < N; i += AN_THREADS) {
+        const float4 p = pos[base + i];
+        const float theta = ang[base + i].z;
+        const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y)));
+        bool on = rad < rule.rad_hi && (double)rad > 1.0;
+        if (on) {
+            const float a = fabsf(theta);
+            if (!(a < rule.a_max)) { // also NaN
+                undecided = 1;
+                on = false;
+            } else {
+                // number of edges below or at a decides the branch: inside [0,e0): 0 edges passed -> on; (e0..e1]: off; ...
+                bool in = a < rule.edge[0];
+#pragma unroll
+                for (int k = 1; k + 1 < ONTUB_EDGES; k += 2) in = in || (a > rule.edge[k] && a < rule.edge[k + 1]);
+                on = in;
+            }
+        }
+        out_flags[base + i] = on ? 1 : 0;
+        if (apply) live_flags[base + i] = on ? 1 : 0;
+        sum += on;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < AN_THREADS / 32; w++) t += wsum[w];
+        out_count[traj] = t;
+    }
+    if (undecided) atomicOr(status, 1); // the word behind the counts: some |theta| was beyond the rule's range
+}
+
+cudaError_t launch_ontubule(const float4 *pos, const float4 *ang, int ntr, int N, const OnTubRule &rule, uint8_t *out_flags, uint8_t *live_flags,
+                            int apply, int *out_count, int *status, cudaStream_t st)
+{
+    ontubule_kernel<<<ntr, AN_THREADS, 0, st>>>(pos, ang, N, rule, out_flags, live_flags, apply, out_count, status);
+    return cudaGetLastError();
+}
+
+// change_conc()'s insertions (updater.cpp:118-135) as a sparse update (maddy_insert_dimers): dimer (q, q+1) leaves the
+// reserve at the drawn position; the candidate lists of its trajectory refer to the old positions from here on.
+__global__ void insert_dimers_kernel(float4 *__restrict__ pos, float4 *__restrict__ rpos, uint8_t *__restrict__ extra, int *__restrict__ cand_valid,
+                                     int N, int n_insert, const int *__restrict__ index, const float4 *__restrict__ xyzz)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_insert) return;
+    const int q = index[k];
+    const float4 v = xyzz[k];
+    const float4 a = make_float4(v.x, v.y, v.z, 0.f), b = make_float4(v.x, v.y, v.w, 0.f);
+    pos[q] = a;
+    pos[q + 1] = b;
+    rpos[q] = a;
+    rpos[q + 1] = b;
+    extra[q] = 0;
+    extra[q + 1] = 0;
+    if (cand_valid) cand_valid[q / N] = 0;
+}
+
+cudaError_t launch_insert_dimers(float4 *pos, float4 *rpos, uint8_t *extra, int *cand_valid, int N, int n_insert, const int *index,
+                                 const float4 *xyzz, cudaStream_t st)
+{
+    insert_dimers_kernel<<<(n_insert + 127) / 128, 128, 0, st>>>(pos, rpos, extra, cand_valid, N, n_insert, index, xyzz);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ensemble_stats(const double *en_traj, int ntr, double *out, cudaStream_t st)
 {
     ensemble_stats_kernel<<<1, AN_THREADS, 0, st>>>(en_traj, ntr, out);

@@ -11,6 +11,8 @@
 #include <omp.h>
 #endif
 #include <thread>
+#include <mutex>
+#include <memory>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -33,6 +35,10 @@ cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_analysis(int which, const AnalysisArgs &a, cudaStream_t st);
 cudaError_t launch_ensemble_stats(const double *en_traj, int ntr, double *out, cudaStream_t st);
+cudaError_t launch_ontubule(const float4 *pos, const float4 *ang, int ntr, int N, const OnTubRule &rule, uint8_t *out_flags, uint8_t *live_flags,
+                            int apply, int *out_count, int *status, cudaStream_t st);
+cudaError_t launch_insert_dimers(float4 *pos, float4 *rpos, uint8_t *extra, int *cand_valid, int N, int n_insert, const int *index,
+                                 const float4 *xyzz, cudaStream_t st);
 } // namespace maddy
 
 using namespace maddy;
@@ -114,6 +120,17 @@ struct maddy_handle {
     double *d_ens = nullptr, *h_ens = nullptr;
     cudaEvent_t ens_ready = nullptr, ens_done = nullptr;
     bool ens_pending = false;
+    // on-tubule classification with the snapshot (MADDY_SNAP_ONTUBULE): rule, device results, pinned mirrors
+    OnTubRule ontub_rule{};
+    bool ontub_rule_ok = false;
+    uint8_t *d_cls_flags = nullptr, *h_cls_flags = nullptr;
+    int *d_cls_count = nullptr, *h_cls_count = nullptr; // [ntr + 1]: per-trajectory counts, then the undecided word
+    unsigned cls_what = 0;                              // classification bits of the snapshot collected last
+    cudaEvent_t cls_staged = nullptr, cls_done = nullptr; // counts written on the main stream / landed in h_cls_count
+    // sparse insertions (maddy_insert_dimers): pinned + device record buffers {index, then float4 xyzz}, reuse event
+    char *h_ins = nullptr, *d_ins = nullptr;
+    size_t ins_capacity = 0;
+    cudaEvent_t ins_done = nullptr;
     // MADDY_GPU_PROFILE=1: event pair around every kernel launch, summarised by maddy_destroy (development aid)
     bool gpu_prof = getenv("MADDY_GPU_PROFILE") != nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -419,6 +436,15 @@ extern "C" int maddy_destroy(maddy_handle *h)
         if (q) cudaFreeHost(q);
     if (h->snap_done) cudaEventDestroy(h->snap_done);
     if (h->snap_staged) cudaEventDestroy(h->snap_staged);
+    if (h->cls_staged) cudaEventDestroy(h->cls_staged);
+    if (h->cls_done) cudaEventDestroy(h->cls_done);
+    if (h->ins_done) cudaEventDestroy(h->ins_done);
+    if (h->d_ins) cudaFree(h->d_ins);
+    if (h->h_ins) cudaFreeHost(h->h_ins);
+    if (h->d_cls_flags) cudaFree(h->d_cls_flags);
+    if (h->d_cls_count) cudaFree(h->d_cls_count);
+    if (h->h_cls_flags) cudaFreeHost(h->h_cls_flags);
+    if (h->h_cls_count) cudaFreeHost(h->h_cls_count);
     if (h->ens_ready) cudaEventDestroy(h->ens_ready);
     if (h->ens_done) cudaEventDestroy(h->ens_done);
     if (h->d_ens) cudaFree(h->d_ens);
@@ -435,6 +461,7 @@ extern "C" int maddy_destroy(maddy_handle *h)
 }
 
 extern "C" int maddy_upload_list(maddy_handle *h, int kind, const int *counts, const int *entries);
+static bool make_ontub_rule(OnTubRule &r);
 
 extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, const float *coords, void *stream,
                             maddy_handle **out)
@@ -694,15 +721,37 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
 
         // RNG: the GLOBAL table of 2*Ntot*Ntr states, sliced (HybridTaus.cu:21-31, compute_cuda.cu:1097)
         {
+            // (ran2 is sequential: the table is generated once per process and ensemble, not once per shard)
             const long long np = 2LL * N * par->n_tr;
-            std::vector<unsigned> seeds((size_t)np * 4);
-            maddy_generate_seeds(seeds.data(), par->rseed, np);
+            static std::mutex seed_mutex;
+            static std::shared_ptr<std::vector<unsigned>> seed_cache;
+            static int seed_cache_rseed = 0;
+            std::shared_ptr<std::vector<unsigned>> table;
+            {
+                std::lock_guard<std::mutex> lock(seed_mutex);
+                if (!seed_cache || seed_cache_rseed != par->rseed || (long long)seed_cache->size() != np * 4) {
+                    seed_cache = std::make_shared<std::vector<unsigned>>((size_t)np * 4);
+                    maddy_generate_seeds(seed_cache->data(), par->rseed, np);
+                    seed_cache_rseed = par->rseed;
+                }
+                table = seed_cache;
+            }
+            const std::vector<unsigned> &seeds = *table;
             const size_t off_xyz = (size_t)par->traj_first * N;
             const size_t off_ang = (size_t)N * par->n_tr + off_xyz;
             CUK(cudaMemcpyAsync(a.rng_xyz, seeds.data() + off_xyz * 4, n * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
             CUK(cudaMemcpyAsync(a.rng_ang, seeds.data() + off_ang * 4, n * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
             CUK(cudaStreamSynchronize(h->stream));
         }
+    }
+    {
+        // exact on-tubule rule of this process's cosf (MADDY_SNAP_ONTUBULE): bisected once
+        static std::once_flag once;
+        static OnTubRule rule;
+        static bool rule_ok = false;
+        std::call_once(once, [] { rule_ok = make_ontub_rule(rule); });
+        h->ontub_rule = rule;
+        h->ontub_rule_ok = rule_ok;
     }
     *out = h;
     return MADDY_OK;
@@ -874,11 +923,54 @@ extern "C" int maddy_download_forces(maddy_handle *h, float *aos)
     soa_to_aos(pos, ang, aos);
     return MADDY_OK;
 }
+// ------------------------------------------------------------------ exact on-tubule rule
+// `cosf(theta) > cosf(ANG_THRES)` (updater.cpp:161) as intervals of a = |theta| (cosf is even).  The authority is the C
+// library's cosf of THIS process (the one the host's mt_length() calls), so the crossing on every monotone branch of the
+// cosine is bisected over the float bit patterns with that function, and the neighbourhood of each crossing is then
+// checked value by value: the predicate must switch exactly once there, otherwise the rule is refused (the device never
+// guesses) and MADDY_SNAP_ONTUBULE reports MADDY_EINVAL.
+static bool make_ontub_rule(OnTubRule &r)
+{
+    const float ang_thres = 1.0f, r_mt = 8.12f, r_thres = 2.0f * 8; // mt.h:23-30
+    volatile float one = ang_thres;
+    const float thr = cosf(ang_thres);
+    if (thr != cosf(one)) return false; // compile-time and run-time evaluation of the threshold must agree
+    r.rad_hi = r_mt + r_thres;
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto flt = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+    auto pred = [&](float a) { return cosf(a) > thr; };
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < ONTUB_EDGES; k++) {
+        // branch k: [k pi, (k+1) pi]; cos decreasing for even k (on -> off), increasing for odd k (off -> on)
+        uint32_t lo = bits((float)(k * pi)), hi = bits((float)((k + 1) * pi));
+        const bool on_at_lo = (k % 2 == 0);
+        if (pred(flt(lo)) != on_at_lo || pred(flt(hi)) == on_at_lo) return false;
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (pred(flt(mid)) == on_at_lo) lo = mid;
+            else hi = mid;
+        }
+        // exactly one switch within +-4096 ulps of the crossing
+        for (uint32_t u = lo - 4096; u <= lo; u++)
+            if (pred(flt(u)) != on_at_lo) return false;
+        for (uint32_t u = hi; u <= hi + 4096; u++)
+            if (pred(flt(u)) == on_at_lo) return false;
+        // even k: on iff a < edge (edge = first "off" value); odd k: on iff a > edge (edge = last "off" value)
+        r.edge[k] = on_at_lo ? flt(hi) : flt(lo);
+    }
+    r.a_max = (float)(ONTUB_EDGES * pi); // the end of the last branch that was bisected
+    return true;
+}
+
 // ------------------------------------------------------------------ asynchronous stride snapshot
 extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
 {
-    if (!h || !(what & (MADDY_SNAP_COORDS | MADDY_SNAP_FORCES | MADDY_SNAP_ENERGIES))) return MADDY_EINVAL;
+    if (!h || !(what & (MADDY_SNAP_COORDS | MADDY_SNAP_FORCES | MADDY_SNAP_ENERGIES | MADDY_SNAP_ONTUBULE))) return MADDY_EINVAL;
     if (h->snap_what) return fail(h, MADDY_EINVAL, "maddy_snapshot_begin: the previous snapshot has not been collected");
+    if ((what & MADDY_SNAP_ONTUBULE_APPLY) && !(what & MADDY_SNAP_ONTUBULE))
+        return fail(h, MADDY_EINVAL, "maddy_snapshot_begin: MADDY_SNAP_ONTUBULE_APPLY needs MADDY_SNAP_ONTUBULE");
+    if ((what & MADDY_SNAP_ONTUBULE) && !h->ontub_rule_ok)
+        return fail(h, MADDY_EINVAL, "maddy_snapshot_begin: the C library's cosf is not monotone around cosf(ANG_THRES); classify on the host");
     CU(h, cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->a.ntr * h->a.N;
     if (!h->snap_done) CU(h, cudaEventCreateWithFlags(&h->snap_done, cudaEventDisableTiming));
@@ -912,6 +1004,29 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
     if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (!h->snap_staged) CU(h, cudaEventCreateWithFlags(&h->snap_staged, cudaEventDisableTiming));
     if (!h->d_snap_status) CU(h, cudaMalloc(&h->d_snap_status, sizeof(int)));
+    if (what & MADDY_SNAP_ONTUBULE) {
+        // mt_length()'s classification of the state being snapshotted, after the energies above (which read the flags of
+        // the previous stride, as in the reference: compute_cuda.cu:1165 precedes :1186-1190).  The counts travel first, on
+        // their own event, so a caller that needs them before it may queue the next window waits microseconds, not for the
+        // coordinates.
+        if (!h->d_cls_flags) {
+            CU(h, cudaMalloc(&h->d_cls_flags, n));
+            CU(h, cudaMalloc(&h->d_cls_count, ((size_t)h->a.ntr + 1) * sizeof(int)));
+            CU(h, cudaMallocHost(&h->h_cls_flags, n));
+            CU(h, cudaMallocHost(&h->h_cls_count, ((size_t)h->a.ntr + 1) * sizeof(int)));
+            CU(h, cudaEventCreateWithFlags(&h->cls_staged, cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->cls_done, cudaEventDisableTiming));
+        }
+        CU(h, cudaMemsetAsync(h->d_cls_count + h->a.ntr, 0, sizeof(int), h->stream));
+        cudaError_t e = launch_ontubule(h->a.pos, h->a.ang, h->a.ntr, h->a.N, h->ontub_rule, h->d_cls_flags, h->a.ontub,
+                                        (what & MADDY_SNAP_ONTUBULE_APPLY) ? 1 : 0, h->d_cls_count, h->d_cls_count + h->a.ntr, h->stream);
+        if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "ontubule kernel launch: %s", cudaGetErrorString(e));
+        h->launches++;
+        CU(h, cudaEventRecord(h->cls_staged, h->stream));
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->cls_staged, 0));
+        CU(h, cudaMemcpyAsync(h->h_cls_count, h->d_cls_count, ((size_t)h->a.ntr + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(h, cudaEventRecord(h->cls_done, h->copy_stream));
+    }
     if (what & MADDY_SNAP_COORDS) {
         if (!h->snap_r) {
             CU(h, cudaMallocHost(&h->snap_r, aos_bytes));
@@ -938,6 +1053,7 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
     if (what & MADDY_SNAP_FORCES) CU(h, cudaMemcpyAsync(h->snap_f, h->d_snap_f, aos_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
     if (what & MADDY_SNAP_ENERGIES)
         CU(h, cudaMemcpyAsync(h->snap_en, h->d_snap_en, (size_t)h->a.ntr * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    if (what & MADDY_SNAP_ONTUBULE) CU(h, cudaMemcpyAsync(h->h_cls_flags, h->d_cls_flags, n, cudaMemcpyDeviceToHost, h->copy_stream));
     CU(h, cudaMemcpyAsync(h->h_status + 1, h->d_snap_status, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
     CU(h, cudaEventRecord(h->snap_done, h->copy_stream));
     if (h->gpu_prof) {
@@ -975,6 +1091,7 @@ extern "C" int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *fo
     if (!h->snap_what) return fail(h, MADDY_EINVAL, "maddy_snapshot_end without maddy_snapshot_begin");
     const unsigned what = h->snap_what;
     h->snap_what = 0;
+    h->cls_what = what & (MADDY_SNAP_ONTUBULE | MADDY_SNAP_ONTUBULE_APPLY);
     CU(h, cudaSetDevice(h->p.device));
     CU(h, cudaEventSynchronize(h->snap_done));
     // the status word copied with the snapshot covers everything queued before it; later launches may already be
@@ -992,6 +1109,37 @@ extern "C" int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *fo
     return MADDY_OK;
 }
 
+extern "C" int maddy_has_exact_on_tubule(const maddy_handle *h) { return h && h->ontub_rule_ok ? 1 : 0; }
+
+extern "C" int maddy_snapshot_tubule_lengths(maddy_handle *h, int *mt_len, int *undecided)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!((h->snap_what | h->cls_what) & MADDY_SNAP_ONTUBULE))
+        return fail(h, MADDY_EINVAL, "maddy_snapshot_tubule_lengths: neither the snapshot in flight nor the one collected last classified");
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaEventSynchronize(h->cls_done));
+    if (mt_len) memcpy(mt_len, h->h_cls_count, (size_t)h->a.ntr * sizeof(int));
+    if (undecided) *undecided = h->h_cls_count[h->a.ntr];
+    return MADDY_OK;
+}
+
+extern "C" int maddy_snapshot_on_tubule(maddy_handle *h, int *on_tubule_cur, int *mt_len)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!(h->cls_what & MADDY_SNAP_ONTUBULE)) return fail(h, MADDY_EINVAL, "maddy_snapshot_on_tubule: the last collected snapshot did not classify");
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    if (h->h_cls_count[h->a.ntr])
+        return fail(h, MADDY_EINVAL, "on-tubule classification: some |theta| is beyond %g rad, outside the range of the exact rule; classify on the host",
+                    (double)h->ontub_rule.a_max);
+    if (on_tubule_cur) {
+        const uint8_t *v = h->h_cls_flags;
+        HOST_PARALLEL_FOR(n)
+        for (size_t q = 0; q < n; q++) on_tubule_cur[q] = v[q];
+    }
+    if (mt_len) memcpy(mt_len, h->h_cls_count, (size_t)h->a.ntr * sizeof(int));
+    return MADDY_OK;
+}
+
 extern "C" int maddy_upload_coords(maddy_handle *h, const float *aos)
 {
     if (!h || !aos) return MADDY_EINVAL;
@@ -1006,6 +1154,44 @@ extern "C" int maddy_upload_coords(maddy_handle *h, const float *aos)
     CU(h, cudaMemcpyAsync(h->a.ang, ang.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->a.rpos, h->a.pos, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return MADDY_OK;
+}
+
+extern "C" int maddy_insert_dimers(maddy_handle *h, int n_insert, const int *index, const float *xyzz)
+{
+    if (!h || n_insert < 0 || (n_insert > 0 && (!index || !xyzz))) return MADDY_EINVAL;
+    if (n_insert == 0) return MADDY_OK;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    for (int k = 0; k < n_insert; k++)
+        if (index[k] < 0 || (size_t)index[k] + 1 >= n || index[k] % h->a.N == h->a.N - 1)
+            return fail(h, MADDY_EINVAL, "maddy_insert_dimers: index[%d] = %d is not the first monomer of a dimer of this handle", k, index[k]);
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = ensure_lj(h); // the Verlet list keeps referring to the old positions until the next list-update step
+    if (rc) return rc;
+    const size_t idx_bytes = ((size_t)n_insert * sizeof(int) + 15) & ~(size_t)15, bytes = idx_bytes + (size_t)n_insert * sizeof(float4);
+    if (bytes > h->ins_capacity) {
+        if (h->ins_done) CU(h, cudaEventSynchronize(h->ins_done));
+        else CU(h, cudaEventCreateWithFlags(&h->ins_done, cudaEventDisableTiming));
+        if (h->d_ins) cudaFree(h->d_ins);
+        if (h->h_ins) cudaFreeHost(h->h_ins);
+        h->d_ins = h->h_ins = nullptr;
+        h->ins_capacity = 0;
+        const size_t cap = bytes < 4096 ? 4096 : 2 * bytes;
+        cudaError_t e = cudaMalloc(&h->d_ins, cap);
+        if (e == cudaSuccess) e = cudaMallocHost(&h->h_ins, cap);
+        if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "%zu bytes for the insertion records: %s", cap, cudaGetErrorString(e));
+        h->ins_capacity = cap;
+    } else {
+        CU(h, cudaEventSynchronize(h->ins_done)); // the previous call's copy has left the pinned buffer
+    }
+    memcpy(h->h_ins, index, (size_t)n_insert * sizeof(int));
+    memcpy(h->h_ins + idx_bytes, xyzz, (size_t)n_insert * sizeof(float4));
+    CU(h, cudaMemcpyAsync(h->d_ins, h->h_ins, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaEventRecord(h->ins_done, h->stream));
+    cudaError_t e = launch_insert_dimers(h->a.pos, h->a.rpos, h->a.extra, h->a.cand_valid, h->a.N, n_insert, (const int *)h->d_ins,
+                                         (const float4 *)(h->d_ins + idx_bytes), h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "insertion kernel launch: %s", cudaGetErrorString(e));
+    h->launches++;
     return MADDY_OK;
 }
 

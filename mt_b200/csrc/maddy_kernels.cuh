@@ -130,6 +130,14 @@ struct KArgs {
     CutTest cut_force; // LJ force cut-off (6.0)
 };
 
+// exact on-tubule classification on the device (ontubule_kernel, maddy_analysis.cu): thresholds bisected on the host
+#define ONTUB_EDGES 7
+struct OnTubRule {
+    float rad_hi;            // R_MT + R_THRES (mt.h:23,30)
+    float a_max;             // |theta| at or beyond this is reported as undecided
+    float edge[ONTUB_EDGES]; // on iff |theta| in [0, e0) U (e1, e2) U (e3, e4) U (e5, e6)
+};
+
 // in-situ analysis (maddy_analysis.cu)
 struct AnalysisArgs {
     const float4 *pos, *ang;   // current state

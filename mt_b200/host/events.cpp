@@ -25,18 +25,30 @@ namespace mt {
 static const float R_MT = 8.12f, R_MON = 2.0f, ANG_THRES = 1.0f, R_THRES = R_MON * 8;
 static const int PF_NUMBER = 13;
 
+// Threads for the host-side loops over the ensemble (flag classification, hydrolysis tests, conversions).  One GPU:
+// OMP_NUM_THREADS if it asks for several threads; launchers that pin it to 1 per rank (torchrun) still get a share of a
+// many-core host (one sixteenth of the hardware threads), at most 8.  When ONE host thread drives G GPUs (n_gpus = G) the
+// per-stride host work is G times larger while the GPU time per stride stays the same, so the share grows with G, up to
+// half the hardware threads (at most 32).  MADDY_HOST_THREADS overrides.
+static int g_host_gpus = 1;
 static int host_threads()
 {
 #ifdef _OPENMP
-    static const int k = [] {
-        // OMP_NUM_THREADS if it asks for several threads; launchers that pin it to 1 per rank (torchrun) still get a
-        // share of a many-core host: one sixteenth of the hardware threads, at most 8
-        int m = omp_get_max_threads();
-        const int share = (int)(std::thread::hardware_concurrency() / 16);
-        if (m < share) m = share;
-        return m > 8 ? 8 : (m < 1 ? 1 : m);
-    }();
-    return k;
+    if (const char *e = getenv("MADDY_HOST_THREADS")) {
+        const int k = atoi(e);
+        if (k > 0) return k;
+    }
+    const int hw = (int)std::thread::hardware_concurrency();
+    int m = omp_get_max_threads();
+    if (m < hw / 16) m = hw / 16;
+    if (m > 8) m = 8;
+    if (m < 1) m = 1;
+    if (g_host_gpus > 1) {
+        int cap = hw / 2 < 32 ? hw / 2 : 32;
+        if (cap < m) cap = m;
+        m = m * g_host_gpus < cap ? m * g_host_gpus : cap;
+    }
+    return m;
 #else
     return 1;
 #endif
@@ -131,13 +143,9 @@ void update(System &s, long long step, std::vector<int> &)
 }
 
 // ---------------------------------------------------------------- tubule length (updater.cpp:154-227)
-void mt_length(System &s, long long step, std::vector<int> &mt_len)
+void mt_length_classify(System &s, std::vector<int> &mt_len)
 {
     const int N = s.par.n_tot;
-    if (step == 0 && s.write_files) {
-        FILE *first = fopen("mt_len.dat", "w");
-        if (first) fclose(first);
-    }
     // Same predicate as the reference, `rad < r_mt + r_thres && rad > 1 && cosf(theta) > cosf(ang_thres)`; the libm
     // calls are only made where their rounding could matter (cos is even and monotone on [0, pi], sqrt is monotone), so
     // the classification is bit-identical at a fraction of the cost.  Trajectories are independent: split over threads.
@@ -167,6 +175,10 @@ void mt_length(System &s, long long step, std::vector<int> &mt_len)
         }
         mt_len[t] = sum;
     }
+}
+void mt_length_output(System &s, long long step, const std::vector<int> &mt_len)
+{
+    const int Ntr = s.par.n_tr;
     if (!s.quiet)
         for (int t = 0; t < Ntr; t++) printf("tubule[%d]: %d\n", t, mt_len[t]);
     if (s.write_files) {
@@ -179,9 +191,18 @@ void mt_length(System &s, long long step, std::vector<int> &mt_len)
         }
     }
 }
+void mt_length(System &s, long long step, std::vector<int> &mt_len)
+{
+    if (step == 0 && s.write_files) {
+        FILE *first = fopen("mt_len.dat", "w");
+        if (first) fclose(first);
+    }
+    mt_length_classify(s, mt_len);
+    mt_length_output(s, step, mt_len);
+}
 
 // ---------------------------------------------------------------- constant concentration (updater.cpp:97-152)
-int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len)
+int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len, std::vector<Insertion> *log)
 {
     const maddy_params &par = s.par;
     const int N = par.n_tot;
@@ -216,6 +237,7 @@ int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len)
                     s.r[(q + 1) * 7 + 0] = x;
                     s.r[(q + 1) * 7 + 1] = y;
                     s.r[(q + 1) * 7 + 2] = z + 2 * R_MON;
+                    if (log) log->push_back({q, x, y, z, s.r[(q + 1) * 7 + 2]});
                     flag++;
                     break;
                 }
@@ -247,11 +269,14 @@ static void event_message(System &s, const char *fmt, int a, int b)
 // ---------------------------------------------------------------- hydrolysis (updater.cpp:229-257)
 void hydrolyse(System &s)
 {
-    // Same events, same draw order (dimer-outer / trajectory-inner, one draw per eligible dimer) as the reference;
-    // the eligibility test is hoisted into a memory-order pre-pass so the draw loop walks a dense byte table
-    // instead of four arrays with a stride of Ntot ints.
+    // Same events, same draw order (dimer-outer / trajectory-inner, one draw per eligible dimer) as the reference.  A draw
+    // never changes the eligibility of ANOTHER dimer, so the number of draws and the position of every dimer's draw in
+    // the stream follow from the eligibility table alone: the table is built in parallel (memory order), the stream of the
+    // whole event is pre-drawn by one thread (HostRand::fill), and the 2 % tests run in parallel over the dimer rows.
     const int N = s.par.n_tot, Ntr = s.par.n_tr, nd = N / 2;
     std::vector<unsigned char> elig((size_t)nd * Ntr);
+    const bool par = (size_t)N * Ntr > 65536;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
     for (int tr = 0; tr < Ntr; tr++) {
         const size_t o = (size_t)tr * N;
         for (int d = 0; d < nd; d++) {
@@ -259,20 +284,39 @@ void hydrolyse(System &s)
             elig[(size_t)d * Ntr + tr] = s.gtp[q] == 1 && !s.extra[q] && s.on_tubule_cur[q] * s.on_tubule_prev[q] == 1;
         }
     }
-    const unsigned char *e = elig.data();
-    for (int d = 0; d < nd; d++)
-        for (int tr = 0; tr < Ntr; tr++, e++) {
-            if (!*e) continue;
-            double prob = s.rng.next() / (double)RAND_MAX;
+    std::vector<size_t> row_first((size_t)nd + 1, 0);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
+    for (int d = 0; d < nd; d++) {
+        size_t c = 0;
+        const unsigned char *e = &elig[(size_t)d * Ntr];
+        for (int tr = 0; tr < Ntr; tr++) c += e[tr];
+        row_first[d + 1] = c;
+    }
+    for (int d = 0; d < nd; d++) row_first[d + 1] += row_first[d];
+    std::vector<uint32_t> draws(row_first[nd]);
+    s.rng.fill(draws.data(), draws.size());
+    std::vector<std::vector<int>> hits(s.quiet ? 0 : nd); // trajectories hydrolysed per dimer, for the messages
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
+    for (int d = 0; d < nd; d++) {
+        const unsigned char *e = &elig[(size_t)d * Ntr];
+        const uint32_t *v = &draws[row_first[d]];
+        for (int tr = 0; tr < Ntr; tr++) {
+            if (!e[tr]) continue;
+            const double prob = (int)*v++ / (double)RAND_MAX;
             if (prob < 0.02) {
                 const size_t q = 2 * d + (size_t)tr * N;
                 s.gtp[q] = 0;
                 s.gtp[q + 1] = 0;
-                if (!s.quiet) event_message(s, "*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", d, tr);
+                if (!s.quiet) hits[d].push_back(tr);
             }
         }
+    }
+    if (!s.quiet)
+        for (int d = 0; d < nd; d++)
+            for (int tr : hits[d]) event_message(s, "*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", d, tr);
     // GDP dimers that are off the tubule now and at the previous stride return to GTP (no draw)
     if (s.quiet) {
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
         for (int tr = 0; tr < Ntr; tr++) {
             const size_t o = (size_t)tr * N;
             for (int d = 0; d < nd; d++) {
@@ -368,6 +412,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
     if (G > Ntr) G = Ntr;
     Shards sh;
     sh.v.resize(G);
+    g_host_gpus = G;
     for (int g = 0; g < G; g++) {
         Shard &d = sh.v[g];
         d.first = (int)((long long)Ntr * g / G);
@@ -448,8 +493,16 @@ void compute(System &s, bool fused, ComputeStats *stats)
     //    while the GPU runs the current window (same rand() order: it follows every event of the current step).
     // Overlapped stride read-back: possible whenever the host results of a stride (on-tubule flags, insertion) cannot
     // change the forces of the following steps.
+    // Where they CAN (on-tubule flags with a non-zero barrier amplitude, constant-concentration insertion), the events run
+    // on the device side of the boundary: mt_length()'s classification is evaluated by the snapshot itself
+    // (MADDY_SNAP_ONTUBULE, exact) and applied in place, the host waits only for the Ntr counts (microseconds) and hands
+    // insertions over as sparse records (maddy_insert_dimers) - no full-coordinate round trip stands between two windows.
     const bool flags_matter = par.barrier && (par.a_barr_long != 0.f || par.a_barr_lat != 0.f);
-    const bool overlap_stride = fused && !par.tea_on && !hp.is_const_conc && !hp.out_force && !flags_matter && !getenv("MADDY_NO_OVERLAP");
+    bool dev_classify = fused && hp.tub_length && !getenv("MADDY_HOST_EVENTS");
+    for (Shard &d : sh.v) dev_classify = dev_classify && maddy_has_exact_on_tubule(d.h);
+    const bool feedback = flags_matter || (hp.is_const_conc && hp.tub_length); // host results of a stride change the next forces
+    const bool overlap_stride = fused && !par.tea_on && !hp.out_force && (!feedback || dev_classify) && !getenv("MADDY_NO_OVERLAP");
+    const bool counts_first = overlap_stride && dev_classify && feedback; // the next window waits for the counts (not the coordinates)
     int pending_output = 0; // an overlapped stride whose update() is still to be written
     long long pending_step = 0;
     std::string pending_log;
@@ -615,13 +668,84 @@ void compute(System &s, bool fused, ComputeStats *stats)
         if (hp.insitu && stride_now) insitu_frame(step);
         int deferred_output = 0;
         const bool overlapped = stride_now && overlap_stride;
+        const bool classify = overlapped && dev_classify && step != 0; // mt_length()'s classification rides on the snapshot
+        bool collected = false;                                        // the snapshot has been collected before the window launch
+        std::vector<Insertion> inserted;                               // this stride's insertions (re-applied to the collected frame)
+        // the host events of a stride once its coordinates are in s.r (compute_cuda.cu:1181-1219); returns deferred_output
+        auto host_events = [&]() -> int {
+            if (!hp.tub_length) return 1;
+            s.on_tubule_prev = s.on_tubule_cur;
+            if (step == 0) return 2; // step 0: update() first, then mt_length() (host flags only, nothing is uploaded)
+            mt_len_prev = mt_len;
+            mt_length(s, step, mt_len);
+            if (par.barrier) {
+                for_each([&](Shard &d) { ck(maddy_upload_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N]), d.h, "maddy_upload_on_tubule"); });
+                st.h2d_bytes += (double)n;
+            }
+            if (hp.is_const_conc) {
+                for (int t = 0; t < Ntr; t++) mt_len_prev[t] = mt_len[t] - mt_len_prev[t];
+                if (change_conc(s, mt_len_prev, mt_len)) {
+                    for_each([&](Shard &d) {
+                        ck(maddy_upload_extra(d.h, &s.extra[(size_t)d.first * N]), d.h, "maddy_upload_extra");
+                        ck(maddy_upload_coords(d.h, &s.r[(size_t)d.first * N * 7]), d.h, "maddy_upload_coords");
+                    });
+                    st.h2d_bytes += (double)n * 33;
+                }
+            }
+            return 1;
+        };
+        auto collect = [&] {
+            for_each([&](Shard &d) {
+                ck(maddy_snapshot_end(d.h, &s.r[(size_t)d.first * N * 7], nullptr, hp.out_energy ? &s.energies[(size_t)d.first * 7] : nullptr),
+                   d.h, "maddy_snapshot_end");
+            });
+            if (hp.out_energy) ens_end(step);
+        };
         if (overlapped) {
-            // Nothing the host derives from this snapshot feeds back into the forces (no insertion, barrier amplitudes
-            // zero), so the read-back is only QUEUED here; it is collected after the next window has been launched.
-            const unsigned what = MADDY_SNAP_COORDS | (hp.out_energy ? MADDY_SNAP_ENERGIES : 0u) | (fused_stride_energy ? MADDY_SNAP_REBUILD : 0u);
+            // The read-back is only QUEUED here; it is collected after the next window has been launched.
+            const unsigned what = MADDY_SNAP_COORDS | (hp.out_energy ? MADDY_SNAP_ENERGIES : 0u) | (fused_stride_energy ? MADDY_SNAP_REBUILD : 0u) |
+                                  (classify ? MADDY_SNAP_ONTUBULE | (par.barrier ? MADDY_SNAP_ONTUBULE_APPLY : 0u) : 0u);
             for_each([&](Shard &d) { ck(maddy_snapshot_begin(d.h, what), d.h, "maddy_snapshot_begin"); });
             if (hp.out_energy) ens_begin();
-            st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0);
+            st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0) + (classify ? (double)n + 4.0 * Ntr : 0.0);
+            if (classify && counts_first) {
+                // What the host derives from this stride feeds back into the next forces (non-zero barrier: the flags, already
+                // applied on the device; constant concentration: the insertions).  Only the Ntr counts are waited for.
+                std::vector<int> counts(Ntr);
+                int undecided = 0;
+                for_each([&](Shard &d) {
+                    int u = 0;
+                    ck(maddy_snapshot_tubule_lengths(d.h, &counts[d.first], &u), d.h, "maddy_snapshot_tubule_lengths");
+                    undecided |= u;
+                });
+                mark("tubule lengths collected", step);
+                if (undecided) { // some |theta| outside the exact rule's range: this stride takes the reference's serial block
+                    collect();
+                    collected = true;
+                    deferred_output = host_events();
+                } else {
+                    mt_len_prev = mt_len;
+                    mt_len = counts;
+                    mt_length_output(s, step, mt_len);
+                    if (hp.is_const_conc) {
+                        for (int t = 0; t < Ntr; t++) mt_len_prev[t] = mt_len[t] - mt_len_prev[t];
+                        if (change_conc(s, mt_len_prev, mt_len, &inserted)) {
+                            for_each([&](Shard &d) {
+                                std::vector<int> idx;
+                                std::vector<float> xyzz;
+                                const size_t lo = (size_t)d.first * N, hi = lo + (size_t)d.count * N;
+                                for (const Insertion &e : inserted)
+                                    if (e.q >= lo && e.q < hi) {
+                                        idx.push_back((int)(e.q - lo));
+                                        xyzz.insert(xyzz.end(), {e.x, e.y, e.z, e.z2});
+                                    }
+                                ck(maddy_insert_dimers(d.h, (int)idx.size(), idx.data(), xyzz.data()), d.h, "maddy_insert_dimers");
+                            });
+                            st.h2d_bytes += (double)inserted.size() * 20;
+                        }
+                    }
+                }
+            }
         } else if (stride_now) {
             if (hp.out_energy) {
                 for_each([&](Shard &d) {
@@ -639,34 +763,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
             }
             for_each([&](Shard &d) { ck(maddy_download_coords(d.h, &s.r[(size_t)d.first * N * 7]), d.h, "maddy_download_coords"); });
             st.d2h_bytes += (double)n * 32;
-            if (hp.tub_length) {
-                s.on_tubule_prev = s.on_tubule_cur;
-                if (step != 0) {
-                    mt_len_prev = mt_len;
-                    mt_length(s, step, mt_len);
-                    if (par.barrier) {
-                        for_each([&](Shard &d) {
-                            ck(maddy_upload_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N]), d.h, "maddy_upload_on_tubule");
-                        });
-                        st.h2d_bytes += (double)n;
-                    }
-                    if (hp.is_const_conc) {
-                        for (int t = 0; t < Ntr; t++) mt_len_prev[t] = mt_len[t] - mt_len_prev[t];
-                        if (change_conc(s, mt_len_prev, mt_len)) {
-                            for_each([&](Shard &d) {
-                                ck(maddy_upload_extra(d.h, &s.extra[(size_t)d.first * N]), d.h, "maddy_upload_extra");
-                                ck(maddy_upload_coords(d.h, &s.r[(size_t)d.first * N * 7]), d.h, "maddy_upload_coords");
-                            });
-                            st.h2d_bytes += (double)n * 33;
-                        }
-                    }
-                    deferred_output = 1;
-                } else {
-                    deferred_output = 2; // step 0: update() first, then mt_length() (host flags only, nothing is uploaded)
-                }
-            } else {
-                deferred_output = 1;
-            }
+            deferred_output = host_events();
         }
         prof.end("stride block");
         prof.begin();
@@ -710,31 +807,44 @@ void compute(System &s, bool fused, ComputeStats *stats)
         }
         prof.end("stride output");
         prof.begin();
-        if (overlapped) {
-            for_each([&](Shard &d) {
-                ck(maddy_snapshot_end(d.h, &s.r[(size_t)d.first * N * 7], nullptr, hp.out_energy ? &s.energies[(size_t)d.first * 7] : nullptr),
-                   d.h, "maddy_snapshot_end");
-            });
-            if (hp.out_energy) ens_end(step);
+        if (overlapped && !collected) {
+            collect();
             prof.end("stride collect (wait + transpose)");
             mark("snapshot collected", step);
             prof.begin();
-            if (hp.tub_length) {
+            if (!classify) {
+                deferred_output = host_events(); // flags cannot change a force here: the upload only keeps the device copy current
+            } else {
                 s.on_tubule_prev = s.on_tubule_cur;
-                if (step != 0) {
+                int undecided = 0;
+                if (!counts_first) { // nobody needed the counts before the launch: look at the undecided word now
+                    for_each([&](Shard &d) {
+                        int u = 0;
+                        ck(maddy_snapshot_tubule_lengths(d.h, nullptr, &u), d.h, "maddy_snapshot_tubule_lengths");
+                        undecided |= u;
+                    });
                     mt_len_prev = mt_len;
+                }
+                if (undecided) { // classify this stride on the host (no force depends on it in this mode)
                     mt_length(s, step, mt_len);
-                    if (par.barrier) { // keeps the device copy current (it cannot change a force: both amplitudes are zero)
-                        for_each([&](Shard &d) {
-                            ck(maddy_upload_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N]), d.h, "maddy_upload_on_tubule");
-                        });
+                    if (par.barrier) {
+                        for_each([&](Shard &d) { ck(maddy_upload_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N]), d.h, "maddy_upload_on_tubule"); });
                         st.h2d_bytes += (double)n;
                     }
-                    deferred_output = 1;
                 } else {
-                    deferred_output = 2;
+                    for_each([&](Shard &d) {
+                        ck(maddy_snapshot_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N], &mt_len[d.first]), d.h, "maddy_snapshot_on_tubule");
+                    });
+                    if (!counts_first) mt_length_output(s, step, mt_len);
                 }
-            } else {
+                // the frame that was read back predates this stride's insertions; the reference writes the frame after them
+                for (const Insertion &e : inserted) {
+                    float *a0 = &s.r[e.q * 7], *a1 = &s.r[(e.q + 1) * 7];
+                    a0[0] = a1[0] = e.x;
+                    a0[1] = a1[1] = e.y;
+                    a0[2] = e.z;
+                    a1[2] = e.z2;
+                }
                 deferred_output = 1;
             }
         }

@@ -20,6 +20,7 @@
 #include <thread>
 #include <stdexcept>
 #include <string>
+#include <cstddef>
 #include <vector>
 #include "maddy_b200.h"
 
@@ -159,6 +160,25 @@ class HostRand {
         return (int)(v >> 1);
     }
 
+    // The next `count` raw outputs (what `count` calls of next() would return, in order) written to out[], and the
+    // generator advanced past them.  The recurrence x[n] = x[n-31] + x[n-3] is unrolled over a linear buffer (no cursor
+    // wrap, no store-to-load stall on a 31-word ring): ~0.4 ns per draw, so one thread can pre-draw the stream of a whole
+    // hydrolysis event and the per-dimer tests can then run in parallel with the reference's draw order preserved.
+    void fill(uint32_t *out, size_t count)
+    {
+        if (count == 0) return;
+        std::vector<uint32_t> x(31 + count);
+        for (int i = 0; i < 31; i++) x[i] = (uint32_t)r_[(f_ + i) % 31]; // oldest first: r_[f_] is x[n-31] (overwritten next), r_[b_] is x[n-3]
+        uint32_t *p = x.data() + 31;
+        for (size_t n = 0; n < count; n++) p[n] = p[(ptrdiff_t)n - 31] + p[(ptrdiff_t)n - 3];
+        for (size_t n = 0; n < count; n++) out[n] = p[n] >> 1;
+        // the ring afterwards: the newest 31 values, cursors advanced by count
+        const int nb = (int)((b_ + count) % 31), nf = (int)((f_ + count) % 31);
+        for (int i = 0; i < 31; i++) r_[(nf + i) % 31] = (int32_t)x[count + i];
+        b_ = nb;
+        f_ = nf;
+    }
+
     // full generator state, for checkpoints: 31 words + the two cursors
     void get_state(int32_t out[33]) const
     {
@@ -221,7 +241,15 @@ void write_restart(System &s, long long step); // :686-714
 
 // updater.cpp
 void mt_length(System &s, long long step, std::vector<int> &mt_len);
-int change_conc(System &s, std::vector<int> &delta, std::vector<int> &mt_len);
+// the two halves of mt_length(): the classification (on_tubule_cur, counts) and its output (tubule[] lines, mt_len.dat);
+// the step loop uses the second half alone when the device classified (MADDY_SNAP_ONTUBULE)
+void mt_length_classify(System &s, std::vector<int> &mt_len);
+void mt_length_output(System &s, long long step, const std::vector<int> &mt_len);
+struct Insertion { // one dimer placed by change_conc(): global monomer index of its first monomer, position, z of the second
+    size_t q;
+    float x, y, z, z2;
+};
+int change_conc(System &s, std::vector<int> &delta, std::vector<int> &mt_len, std::vector<Insertion> *log = nullptr);
 void hydrolyse(System &s);
 void output_all_energies(System &s, long long step);
 void output_sum_force(System &s);

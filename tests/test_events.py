@@ -65,3 +65,33 @@ def test_change_conc_inserts_reserve_dimers(rundir, load_system):
     for i in freed[::2]:
         assert s.mon_type[i] == 0 and c[0, i, 0] ** 2 + c[0, i, 1] ** 2 <= 400.0
         assert c[0, i, 2] == 60 + 0.0 + 12 and c[0, i + 1, 2] == c[0, i, 2] + 4 and c[0, i + 1, 0] == c[0, i, 0]
+
+
+def test_consecutive_hydrolysis_events_continue_the_libc_stream(rundir, load_system):
+    """The draws of an event are pre-drawn in bulk (HostRand::fill) and tested in parallel: two consecutive events on an
+    ensemble large enough for the parallel path consume exactly the libc rand() sequence, in the reference's order."""
+    ntr = 130
+    s = load_system(rundir(runnum=ntr))
+    s.on_tubule_cur[:] = 1
+    s.on_tubule_prev[:] = 1
+    rng = np.random.default_rng(0)
+    off = rng.random((ntr, 260)) < 0.1   # some dimers are off the tubule: no draw for them
+    s.on_tubule_cur[:] = np.where(off.repeat(2, axis=1), 0, 1)
+    s.srand(42)
+    s.hydrolyse()
+    first = s.gtp.copy()
+    s.hydrolyse()
+    second = s.gtp.copy()
+    libc.srand(42)
+    exp = np.ones((ntr, 520), dtype=np.int32)
+    snaps = []
+    for event in range(2):
+        for i in range(0, 520, 2):
+            for tr in range(ntr):
+                if exp[tr, i] != 1 or off[tr, i // 2]:
+                    continue
+                if libc.rand() / 2147483647.0 < 0.02:
+                    exp[tr, i] = exp[tr, i + 1] = 0
+        snaps.append(exp.copy())
+    assert np.array_equal(first, snaps[0]) and np.array_equal(second, snaps[1])
+    assert (second == 0).sum() > (first == 0).sum() > 0
