@@ -35,3 +35,17 @@ rows.sort(reverse=True)
 for dt, t, stats, mind, fin in rows[:12]:
     print(f"traj {t:3d}: {dt / 200 * 1e6:7.1f} us/step  finite {fin}  min free-free {mind:5.2f}  {stats}")
 print("median", sorted(r[0] for r in rows)[64] / 200 * 1e6)
+# whole ensemble: before and after the insertions
+def timed(e, first, nsteps):
+    e.run(first, 20); e.sync(); e.list_stats(reset=True)
+    t0 = time.perf_counter(); e.run(first + 20, nsteps); e.sync(); dt = time.perf_counter() - t0
+    return dt / nsteps * 1e6, e.list_stats()
+e = Engine(s)
+print("after insertion, 128 traj:", timed(e, 1000, 980))
+e.close()
+workspace.make_baseline_rundir(d / "b", "mt120_constconc", runnum=128, steps=1001)
+with workspace.chdir(d / "b"):
+    s0 = HostSystem("config.conf")
+e = Engine(s0)
+print("before insertion, 128 traj:", timed(e, 0, 980))
+e.close()

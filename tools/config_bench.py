@@ -2,6 +2,7 @@
 
 usage: python tools/config_bench.py <config> <ntr> <steps> [ref_ntr] [overrides...]
 Prints monomer-steps/s for both (the reference by the difference of two run lengths)."""
+import os
 import shutil
 import subprocess
 import sys
@@ -33,7 +34,7 @@ def main():
         dt = time.perf_counter() - t0
     N = s.Ntot
     print(f"{name}: N={N} Ntr={ntr} steps={steps}  own e2e {N * ntr * steps / dt / 1e9:.3f} G monomer-steps/s  ({dt / steps * 1e6:.1f} us/step, launches {st['launches']})")
-    if refprobe.REF_MT.exists():
+    if refprobe.REF_MT.exists() and not os.environ.get('NO_REF'):
         def run(k):
             r = d / f"ref{k}"
             workspace.make_baseline_rundir(r, name, runnum=ref_ntr, steps=k)
