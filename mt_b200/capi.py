@@ -73,6 +73,8 @@ class HostParams(C.Structure):
 
 def _load(name: str) -> C.CDLL:
     path = PKG / name
+    if name == "libmaddy_b200.so" and os.environ.get("MADDY_B200_LIB"):  # development: A/B builds of the kernels
+        path = Path(os.environ["MADDY_B200_LIB"])
     if not path.exists():
         raise ImportError(f"{path} is not built; run `python -m mt_b200.build` (there is no Python/CPU fallback)")
     return C.CDLL(str(path), mode=C.RTLD_GLOBAL)

@@ -237,6 +237,9 @@ static KArgs kargs(const maddy_handle *h, unsigned ops)
         k.rcand2 = rb * rb;
     }
     k.lazy = (ops & OP_RUN) && h->lazy;
+    k.near_all_listed = h->p.lj_on && h->p.ljpairscutoff >= 7.5f; // near radius 7.0 (MD_NEAR_R2)
+    k.band_mid = 0.5f * (h->cut_force.lo + h->cut_force.hi);
+    k.band_hw = h->cut_force.hi - h->cut_force.lo; // twice the half-width: a superset of the band whatever the rounding
     k.cut_pairs = h->cut_pairs;
     k.cut_force = h->cut_force;
     return k;

@@ -97,9 +97,10 @@ __device__ __forceinline__ Frame make_frame(float fi, float psi, float theta, co
 // approximate float sqrt.  (compute_cuda.cu:89-96, :208-215, :337-350)
 __device__ __forceinline__ float site_distance(const F3 &d)
 {
+    // (products of two floats are exact in fp64, so fma() rounds exactly like the reference's multiply-then-add)
     double s = (double)d.z * (double)d.z;
-    s += (double)d.x * (double)d.x;
-    s += (double)d.y * (double)d.y;
+    s = fma((double)d.x, (double)d.x, s);
+    s = fma((double)d.y, (double)d.y, s);
     return sqrtf((float)s);
 }
 // variant used by energy_kernel: fp64 sqrt, then rounded to float (compute_cuda.cu:731,:791,:858)
@@ -167,8 +168,9 @@ __device__ __forceinline__ unsigned hybrid_taus(uint4 &s)
 // low 23 bits as the mantissa of a float in [1,2), minus 1; 0 -> 1e-8 (HybridTaus.cu:53-61)
 __device__ __forceinline__ float uint_to_unit_float(unsigned u)
 {
-    float r = __uint_as_float(0x3f800000u | (0x007fffffu & u)) - 1.0f;
-    return r == 0 ? 1.0e-8f : r;
+    // r is 0 or >= 2^-23 > 1e-8, so the reference's `r == 0 ? 1e-8 : r` is a maximum
+    const float r = __uint_as_float(0x3f800000u | (0x007fffffu & u)) - 1.0f;
+    return fmaxf(r, 1.0e-8f);
 }
 // Two Box-Muller pairs from four draws; .w is produced and discarded by the callers, as in
 // the reference (HybridTaus.cu:85-98): r = sqrtf(-2 logf(u1)), angle = float(2*pi (double) * u2).

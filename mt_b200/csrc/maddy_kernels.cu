@@ -23,6 +23,10 @@
  */
 #include "maddy_kernels.cuh"
 
+#ifndef MADDY_OPT_LJ
+#define MADDY_OPT_LJ 1
+#endif
+
 namespace maddy {
 
 #define KB_BOLTZ 0.0019872041f // kcal/(mol*K), mt.h:39
@@ -240,6 +244,25 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
             const int16_t *nl = reinterpret_cast<const int16_t *>(near.list) + i; // bit 15 (LJ-listed) read as the sign
             const float lo = k.cut_force.lo, hi = k.cut_force.hi;
             bool band = false;
+            if (MADDY_OPT_LJ && k.near_all_listed) {
+                // every entry is LJ-listed (pairs cut-off beyond the near radius): no flag test, no index mask, and the
+                // band check is one subtract + compare (a superset of [lo, hi]; a hit only triggers the exact redo below)
+                const uint16_t *nu = near.list + i;
+                const float mid = k.band_mid, hw = k.band_hw;
+#pragma unroll 4
+                for (int kk = 0; kk < n; kk++) {
+                    const float4 Pj = s.P(nu[kk * a.N] & 0x7fffu);
+                    const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
+                    const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    band |= fabsf(sf - mid) <= hw;
+                    const float inv = 1.0f / sf;
+                    const float inv2 = inv * inv;
+                    const float c = sf < lo ? amp * (6.0f * (inv2 * inv2)) : 0.0f; // 6 / dr^8
+                    fx = fmaf(c, dx, fx);
+                    fy = fmaf(c, dy, fy);
+                    fz = fmaf(c, dz, fz);
+                }
+            } else
             for (int kk = 0; kk < n; kk++) {
                 const int e = nl[kk * a.N];
                 const float4 Pj = s.P(e & 0x7fff);
@@ -1168,7 +1191,6 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     cs.valid = near.cap > 0 ? a.cand_valid[traj] : 0;
     cs.dirty = false;
 
-    int buf = 0;
     int near_state = 0; // 0: not built, 1: valid, 2: overflowed (full list until the next rebuild)
     float gx[MPT], gy[MPT], gz[MPT]; // positions when the near list was formed (displacement guard)
 #pragma unroll
@@ -1179,12 +1201,37 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     bool stale = a.lj_stale[traj] != 0;   // the Verlet list in HBM predates the last list-update step
     int fixed_flags_dirty = 0; // stage buffers whose copy of a fixed monomer's GTP bit is stale
     bool gtp_changed = false;
+    // Step bookkeeping without 64-bit divisions in the loop: steps left until the next list-update step and until the next
+    // scheduled hydrolysis event are counted down (the modulo of a long long costs ~30 instructions per warp and step).
+    const int freq = p.ljpairsupdatefreq > 0 ? p.ljpairsupdatefreq : 1;
+    int to_update = (int)((freq - k.first_step % freq) % freq); // 0: this step is a list-update step
+    int sched_slot = 0;                                         // slot that becomes current at the next event
+    int to_event = -1;                                          // steps until that event; < 0: none (left) in this launch
+    if (k.sched_slots > 0) {
+        const long long rel = k.first_step - k.sched_first;
+        const long long slot0 = rel <= 0 ? 0 : (rel + k.sched_period - 1) / k.sched_period;
+        const long long wait = k.sched_first + slot0 * k.sched_period - k.first_step;
+        if (slot0 < k.sched_slots && wait < k.n_steps) {
+            sched_slot = (int)slot0;
+            to_event = (int)wait;
+        }
+    }
+    const int period_m1 = k.sched_period - 1 > 0x7ffffff0LL ? 0x7ffffff0 : (int)(k.sched_period - 1);
+    const int stage_toggle = k.nbuf == 2 ? 4 * N : 0;
+    int boff = 0; // float4 offset of the current stage buffer (replaces buf * 4 * N)
     for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
-        const Stage s = stage_at(N, buf);
+        Stage s;
+        s.oP = boff;
+        s.oE = boff + N;
+        s.oL1 = boff + 2 * N;
+        s.oL2 = boff + 3 * N;
         // scheduled hydrolysis event: the GTP flags uploaded for this step become current (maddy_schedule_gtp)
-        if (k.sched_slots > 0 && step >= k.sched_first && (step - k.sched_first) % k.sched_period == 0) {
-            const long long slot = (step - k.sched_first) / k.sched_period;
-            if (slot < k.sched_slots) {
+        const bool event_now = to_event == 0;
+        if (to_event >= 0) to_event--;
+        if (event_now) {
+            const int slot = sched_slot++;
+            to_event = sched_slot < k.sched_slots ? period_m1 : -1;
+            {
                 const uint8_t *g = a.gtp_sched + (size_t)slot * a.ntr * N + base;
 #pragma unroll
                 for (int t = 0; t < MPT; t++)
@@ -1195,7 +1242,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
         }
         if (fixed_flags_dirty > 0) {
             if ((int)threadIdx.x < a.n_fixed) {
-                const long long slot = (step - k.sched_first) / k.sched_period; // latest slot at or before this step
+                const int slot = sched_slot - 1; // latest slot at or before this step
                 const uint8_t *g = a.gtp_sched + (size_t)slot * a.ntr * N + base;
                 const int i = (int)a.fmap[threadIdx.x];
                 int jf = __float_as_int(s.L2(i).w);
@@ -1215,8 +1262,9 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
             }
         }
         const bool any_moved = __syncthreads_or(moved && near_state == 1) != 0;
-        const bool do_rebuild = rops != 0 && step % p.ljpairsupdatefreq == 0 &&
-                                !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
+        const bool update_now = to_update == 0;
+        to_update = update_now ? freq - 1 : to_update - 1;
+        const bool do_rebuild = rops != 0 && update_now && !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
         bool formed = false;
         if (do_rebuild) {
             bool lj_exact;
@@ -1274,8 +1322,8 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                 }
             }
         }
-        if (k.nbuf == 2) buf ^= 1;
-        else __syncthreads();
+        boff ^= stage_toggle;
+        if (k.nbuf != 2) __syncthreads();
     }
 #pragma unroll
     for (int t = 0; t < MPT; t++) {

@@ -125,6 +125,8 @@ struct KArgs {
     int rng_smem_offset; // byte offset of the shared-memory RNG area (two-CTA shape only)
     int topo_smem_offset; // byte offset of the packed per-monomer topology words, or -1
     int lazy;          // fused loop: list-update steps only refresh the near/bond lists; the exact Verlet list is materialised on demand
+    int near_all_listed; // LJ pairs cut-off > near radius: every near-list entry is LJ-listed (no per-entry flag test in the force loop)
+    float band_mid, band_hw; // |sf - band_mid| <= band_hw covers [cut_force.lo, cut_force.hi]: pairs that need the fp64 tie-break
     float rcand2;      // squared candidate radius: (max(LJ pairs cut-off, near radius) + MD_CAND_SKIN)^2
     CutTest cut_pairs; // LJ list cut-off (ljpairscutoff)
     CutTest cut_force; // LJ force cut-off (6.0)

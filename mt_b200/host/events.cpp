@@ -230,14 +230,19 @@ int change_conc(System &s, std::vector<int> &, std::vector<int> &mt_len, std::ve
                             break;
                         }
                     }
-                    float z = zs + par.rep_leftborder + 3 * 2 * R_MON;
-                    s.r[q * 7 + 0] = x;
-                    s.r[q * 7 + 1] = y;
-                    s.r[q * 7 + 2] = z;
-                    s.r[(q + 1) * 7 + 0] = x;
-                    s.r[(q + 1) * 7 + 1] = y;
-                    s.r[(q + 1) * 7 + 2] = z + 2 * R_MON;
-                    if (log) log->push_back({q, x, y, z, s.r[(q + 1) * 7 + 2]});
+                    const float z = zs + par.rep_leftborder + 3 * 2 * R_MON, z2 = z + 2 * R_MON;
+                    if (log) {
+                        // the caller applies the record (device: maddy_insert_dimers; host frame: once the snapshot of THIS
+                        // stride has been collected - s.r may still hold the previous stride's frame, whose output is pending)
+                        log->push_back({q, x, y, z, z2});
+                    } else {
+                        s.r[q * 7 + 0] = x;
+                        s.r[q * 7 + 1] = y;
+                        s.r[q * 7 + 2] = z;
+                        s.r[(q + 1) * 7 + 0] = x;
+                        s.r[(q + 1) * 7 + 1] = y;
+                        s.r[(q + 1) * 7 + 2] = z2;
+                    }
                     flag++;
                     break;
                 }
