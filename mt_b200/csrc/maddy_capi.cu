@@ -30,6 +30,7 @@ cudaError_t launch_integrate_kernel(const KArgs &k, cudaStream_t st);
 cudaError_t launch_snapshot_kernel(const float4 *pos, const float4 *ang, float *out_mapped, size_t n_monomers, cudaStream_t st);
 cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
+int tea_partner_segments(int N);
 cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
@@ -658,11 +659,14 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             pool_req(&a.tea_co, n);
             pool_req(&a.tea_mf, n);
             pool_req(&a.tea_rf, n);
+            pool_req(&a.tea_part, tea_partner_segments(N) > 1 ? n * tea_partner_segments(N) : 1);
+            pool_req(&a.tea_cnt, (size_t)ntr * ((N + 31) / 32));
         }
         if (wide) pool_req(&a.gstage, 8 * n);
         if (wide && !getenv("MADDY_WIDE_ALL_PAIRS")) // WGrid header + count/start/cursor[32768] + members[Npad] per trajectory (maddy_wide.cuh)
             pool_req(reinterpret_cast<char **>(&a.wgrid), (size_t)ntr * (64 + (size_t)3 * 32768 * 4 + (size_t)a.Npad * 2));
         CK(pool_commit(h, reqs));
+        if (par->tea_on) CUK(cudaMemsetAsync(a.tea_cnt, 0, (size_t)ntr * ((N + 31) / 32) * sizeof(unsigned), h->stream));
         CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.lj_stale, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.status, 0, sizeof(int), h->stream));

@@ -180,47 +180,52 @@ __global__ void __launch_bounds__(256) tea_prepare_kernel(const __grid_constant_
 }
 
 // ---- integrateTea_kernel_unlisted (bdhitea_kernel.cu:148-213)
-// Work split: a group of TEA_IB = 4 beads is shared by TEA_S = 4 warps ("parts"); part s takes every 4th round of 32
-// partners, so even ONE trajectory of a few thousand beads puts ~8 warps on every SM sub-partition.  A CTA holds TEA_G
-// groups and streams the partners through shared memory in tiles of 512 (two-stage cp.async ring).  The partial sums of the parts are combined in a fixed order ((p0+p1)+(p2+p3), then a lane butterfly), so
-// the result does not depend on the launch shape.
-// Arithmetic: the four beads of a group are two PACKED pairs: sm_100a's FFMA2 / FMUL2 / FADD2 (fma.rn.f32x2) do the same
-// operation for both beads of a pair in one instruction - measured 66 TFLOP/s against 42 TFLOP/s for three-register
-// scalar FFMA on this GPU (tools/micro/ffma2_bench.cu).  A partner's component enters as a scalar register broadcast to
-// both halves (the .F32 operand form), so the tile holds the plain records.  Per pair the tensor is applied in its dyadic form  D g = cii g + crr (u.g) u
-// (eq. 3-5 of the paper; the reference multiplies the six entries out, bdhitea_kernel.cu:38-58) with one MUFU (rsqrt):
-// 1/ra = a / w needs no division.  Reserve beads carry zero force records (exact zero contribution); the overlap
-// branch ra <= 2, the self pair and the padding beyond N are handled in a warp-uniform slow path.
-#define TEA_IB 4
-#define TEA_THREADS 256
-#define TEA_TILE 512
-#define TEA_STAGES 2
-#define TEA_SPLIT_NTOT 2048 // trajectories at least this long split the partners of a bead group over 4 warps
-
-struct TeaBeads { // per warp: two packed bead pairs
-    float2 npx[2], npy[2], npz[2]; // negated positions
-    float2 cx[2], cy[2], cz[2];    // beta * C_i
-    float2 ax[2], ay[2], az[2];    // accumulators
-};
+// Mapping: LANES ARE BEADS.  A warp owns a block of 32 beads (one per lane) and walks partners four at a time; the partner
+// records live in shared memory as structure-of-arrays, so one broadcast LDS.128 per component hands every lane the same
+// four partners as two PACKED pairs: sm_100a's FFMA2 / FMUL2 / FADD2 (fma.rn.f32x2) then do the same operation for two
+// partners of the lane's bead in one instruction - measured 66 TFLOP/s against 42 TFLOP/s for three-register scalar FFMA
+// on this GPU (tools/micro/ffma2_bench.cu) - while the bead's own quantities enter as scalars broadcast to both halves.
+// Nothing is reduced across lanes (the previous mapping - partners on lanes, four beads per warp - spent more instructions
+// on its butterfly reductions, its per-group prologue / epilogue with 4 of 32 lanes active and its padding rounds than on
+// the pairs: 2196 warp instructions per 2080 pairs, 43 % of them in the pair loop).
+// Per pair the tensor is applied in its dyadic form  D g = cii g + crr (u.g) u  (eq. 3-5 of the paper; the reference
+// multiplies the six entries out, bdhitea_kernel.cu:38-58) with one MUFU (rsqrt): 1/ra = a / w needs no division.
+// Reserve beads carry zero force records and the padding up to a multiple of four partners is a far-away bead with zero
+// forces (exact zero contributions, no test); the overlap branch ra <= 2 is a warp-voted slow path and the self pair is
+// masked only in the eight steps that cover the warp's own block.
+// Work split (functions of N alone, so a trajectory's result never depends on how many trajectories share the launch):
+// TEA_S warps of a CTA share one bead block and take every TEA_S-th step; for long trajectories the partners are also cut
+// into Z segments handled by different CTAs, whose partial sums meet in HBM and are added in segment order by the CTA that
+// finishes last (ticket counter), so even ONE trajectory of a few thousand beads fills the GPU.
+#define TEA_BLOCK 32
+#define TEA_TILE 512 // partners per shared-memory tile (9 floats each: 18 KB)
+#define TEA_SPLIT_NTOT 2048 // trajectories at least this long use 4 warps per bead block and partner segments
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
+struct TeaAcc { float2 x[2], y[2], z[2]; }; // [h]: partners 4k+2h (.x) and 4k+2h+1 (.y)
+
+// One step = partners j..j+3 of the tile against the lane's bead.  i: the lane's bead (global index in the trajectory).
 template <bool MASKED>
-__device__ __forceinline__ void tea_round(TeaBeads &B, const float4 *sco, const float4 *smf, const float4 *srf, int jj, int j, int i0, int N, float ta,
-                                          float inv_a, float near2)
+__device__ __forceinline__ void tea_step(TeaAcc &A, const float (*T)[TEA_TILE], int jj, int j, int i, float npx, float npy, float npz, float Cx,
+                                         float Cy, float Cz, float ta, float inv_a, float near2)
 {
-    const float4 c = sco[jj], m = smf[jj], r = srf[jj];
+    const float4 X = *reinterpret_cast<const float4 *>(&T[0][jj]), Y = *reinterpret_cast<const float4 *>(&T[1][jj]),
+                 Z = *reinterpret_cast<const float4 *>(&T[2][jj]);
+    const float4 MX = *reinterpret_cast<const float4 *>(&T[3][jj]), MY = *reinterpret_cast<const float4 *>(&T[4][jj]),
+                 MZ = *reinterpret_cast<const float4 *>(&T[5][jj]);
+    const float4 RX = *reinterpret_cast<const float4 *>(&T[6][jj]), RY = *reinterpret_cast<const float4 *>(&T[7][jj]),
+                 RZ = *reinterpret_cast<const float4 *>(&T[8][jj]);
 #pragma unroll
-    for (int pk = 0; pk < 2; pk++) {
-        // (v, v) operands: FADD2 / FFMA2 take a scalar register broadcast to both halves, no move needed
-        const float2 dx = __fadd2_rn(f2(c.x, c.x), B.npx[pk]);
-        const float2 dy = __fadd2_rn(f2(c.y, c.y), B.npy[pk]);
-        const float2 dz = __fadd2_rn(f2(c.z, c.z), B.npz[pk]);
+    for (int h = 0; h < 2; h++) {
+        const float2 dx = __fadd2_rn(h ? f2(X.z, X.w) : f2(X.x, X.y), f2(npx, npx));
+        const float2 dy = __fadd2_rn(h ? f2(Y.z, Y.w) : f2(Y.x, Y.y), f2(npy, npy));
+        const float2 dz = __fadd2_rn(h ? f2(Z.z, Z.w) : f2(Z.x, Z.y), f2(npz, npz));
         float2 w2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
         bool on0 = true, on1 = true;
-        if (MASKED) { // the self pair and the padding beyond N
-            on0 = j != i0 + 2 * pk && j < N;
-            on1 = j != i0 + 2 * pk + 1 && j < N;
+        if (MASKED) { // the self pair
+            on0 = j + 2 * h != i;
+            on1 = j + 2 * h + 1 != i;
             w2.x = on0 ? w2.x : 1.f;
             w2.y = on1 ? w2.y : 1.f;
         }
@@ -231,8 +236,8 @@ __device__ __forceinline__ void tea_round(TeaBeads &B, const float4 *sco, const 
         const float2 far = __fmul2_rn(f2(0.75f, 0.75f), ira);
         float2 crr = __fmul2_rn(far, __ffma2_rn(f2(-2.f, -2.f), ira2, f2(1.f, 1.f)));
         float2 cii = __fmul2_rn(far, __ffma2_rn(f2(2.f / 3.f, 2.f / 3.f), ira2, f2(1.f, 1.f)));
-        const bool near = w2.x <= near2 || w2.y <= near2;
-        if (MASKED || __any_sync(0xffffffffu, near)) { // overlapping beads (ra <= 2) and excluded pairs: rare, scalar
+        const bool near = fminf(w2.x, w2.y) <= near2;
+        if (MASKED || __any_sync(0xffffffffu, near)) { // overlapping beads (ra <= 2) and the self pair: rare, scalar
             if (w2.x <= near2) {
                 const float ra = (w2.x * iw.x) * inv_a;
                 crr.x = (3.f / 32.f) * ra;
@@ -246,215 +251,202 @@ __device__ __forceinline__ void tea_round(TeaBeads &B, const float4 *sco, const 
             if (!on0) crr.x = cii.x = 0.f;
             if (!on1) crr.y = cii.y = 0.f;
         }
-        const float2 gx = __ffma2_rn(f2(r.x, r.x), B.cx[pk], f2(m.x, m.x));
-        const float2 gy = __ffma2_rn(f2(r.y, r.y), B.cy[pk], f2(m.y, m.y));
-        const float2 gz = __ffma2_rn(f2(r.z, r.z), B.cz[pk], f2(m.z, m.z));
+        const float2 gx = __ffma2_rn(h ? f2(RX.z, RX.w) : f2(RX.x, RX.y), f2(Cx, Cx), h ? f2(MX.z, MX.w) : f2(MX.x, MX.y));
+        const float2 gy = __ffma2_rn(h ? f2(RY.z, RY.w) : f2(RY.x, RY.y), f2(Cy, Cy), h ? f2(MY.z, MY.w) : f2(MY.x, MY.y));
+        const float2 gz = __ffma2_rn(h ? f2(RZ.z, RZ.w) : f2(RZ.x, RZ.y), f2(Cz, Cz), h ? f2(MZ.z, MZ.w) : f2(MZ.x, MZ.y));
         const float2 pr = __fmul2_rn(crr, __ffma2_rn(uz, gz, __ffma2_rn(uy, gy, __fmul2_rn(ux, gx))));
-        B.ax[pk] = __ffma2_rn(cii, gx, __ffma2_rn(pr, ux, B.ax[pk]));
-        B.ay[pk] = __ffma2_rn(cii, gy, __ffma2_rn(pr, uy, B.ay[pk]));
-        B.az[pk] = __ffma2_rn(cii, gz, __ffma2_rn(pr, uz, B.az[pk]));
+        A.x[h] = __ffma2_rn(cii, gx, __ffma2_rn(pr, ux, A.x[h]));
+        A.y[h] = __ffma2_rn(cii, gy, __ffma2_rn(pr, uy, A.y[h]));
+        A.z[h] = __ffma2_rn(cii, gz, __ffma2_rn(pr, uz, A.z[h]));
     }
 }
 
-// Two rounds of 32 partners at once, common case only (no self pair, no padding): the four bead-pair streams are
-// independent until the accumulators, which doubles the instruction-level parallelism a warp offers (the top stall of
-// the one-round version was `wait`: dependent packed operations).  Accumulation order = round A, then round B, as when
-// the rounds are taken one by one, so the result is bit-identical.
-__device__ __forceinline__ void tea_round2(TeaBeads &B, const float4 *sco, const float4 *smf, const float4 *srf, int jjA, int jjB, float ta, float inv_a,
-                                           float near2)
+// TEA_NS steps (4 * TEA_NS partners) at once, common case only (no self pair): 2 * TEA_NS independent packed streams.
+// A warp issues one dependent packed operation every ~10 cycles (measured: `wait` is the top stall with two streams) and
+// registers cap the SM at ~4 warps per scheduler, so the parallelism has to come from inside the warp.  Only the squared
+// distances are formed before the ONE overlap vote (8 registers per stream); behind it the streams share nothing but the
+// accumulators, so the compiler interleaves them freely.  A hit (rare) redoes the steps one by one with the scalar
+// fix-ups.  Accumulation order = step 0 (h = 0, 1), step 1, ... as when the steps are taken one by one: bit-identical.
+#define TEA_NS 2
+__device__ __forceinline__ void tea_steps(TeaAcc &A, const float (*T)[TEA_TILE], int jj0, int jstride, int j0, int i, float npx, float npy, float npz,
+                                          float Cx, float Cy, float Cz, float ta, float inv_a, float near2)
 {
-    const float4 c[2] = {sco[jjA], sco[jjB]}, m[2] = {smf[jjA], smf[jjB]}, r[2] = {srf[jjA], srf[jjB]};
-    float2 ux[4], uy[4], uz[4], crr[4], cii[4], w2[4], iw[4];
-    bool near = false;
+    float2 dx[2 * TEA_NS], dy[2 * TEA_NS], dz[2 * TEA_NS], w2[2 * TEA_NS];
+    float wmin = 3.0e38f;
 #pragma unroll
-    for (int q = 0; q < 4; q++) { // q = 2 * round + pair
-        const int rd = q >> 1, pk = q & 1;
-        const float2 dx = __fadd2_rn(f2(c[rd].x, c[rd].x), B.npx[pk]);
-        const float2 dy = __fadd2_rn(f2(c[rd].y, c[rd].y), B.npy[pk]);
-        const float2 dz = __fadd2_rn(f2(c[rd].z, c[rd].z), B.npz[pk]);
-        w2[q] = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-        iw[q] = f2(rsqrtf(w2[q].x), rsqrtf(w2[q].y));
-        ux[q] = __fmul2_rn(dx, iw[q]);
-        uy[q] = __fmul2_rn(dy, iw[q]);
-        uz[q] = __fmul2_rn(dz, iw[q]);
-        const float2 ira = __fmul2_rn(f2(ta, ta), iw[q]);
+    for (int q = 0; q < 2 * TEA_NS; q++) { // q = 2 * step + h
+        const int jj = jj0 + (q >> 1) * jstride + 2 * (q & 1);
+        dx[q] = __fadd2_rn(*reinterpret_cast<const float2 *>(&T[0][jj]), f2(npx, npx));
+        dy[q] = __fadd2_rn(*reinterpret_cast<const float2 *>(&T[1][jj]), f2(npy, npy));
+        dz[q] = __fadd2_rn(*reinterpret_cast<const float2 *>(&T[2][jj]), f2(npz, npz));
+        w2[q] = __ffma2_rn(dz[q], dz[q], __ffma2_rn(dy[q], dy[q], __fmul2_rn(dx[q], dx[q])));
+        wmin = fminf(wmin, fminf(w2[q].x, w2[q].y));
+    }
+    if (__any_sync(0xffffffffu, wmin <= near2)) { // overlapping beads (ra <= 2) somewhere in the warp: rare
+#pragma unroll 1
+        for (int st = 0; st < TEA_NS; st++)
+            tea_step<false>(A, T, jj0 + st * jstride, j0 + st * jstride, i, npx, npy, npz, Cx, Cy, Cz, ta, inv_a, near2);
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 2 * TEA_NS; q++) {
+        const int jj = jj0 + (q >> 1) * jstride + 2 * (q & 1), h = q & 1;
+        const float2 iw = f2(rsqrtf(w2[q].x), rsqrtf(w2[q].y));
+        const float2 ux = __fmul2_rn(dx[q], iw), uy = __fmul2_rn(dy[q], iw), uz = __fmul2_rn(dz[q], iw);
+        const float2 ira = __fmul2_rn(f2(ta, ta), iw); // 1 / ra
         const float2 ira2 = __fmul2_rn(ira, ira);
         const float2 far = __fmul2_rn(f2(0.75f, 0.75f), ira);
-        crr[q] = __fmul2_rn(far, __ffma2_rn(f2(-2.f, -2.f), ira2, f2(1.f, 1.f)));
-        cii[q] = __fmul2_rn(far, __ffma2_rn(f2(2.f / 3.f, 2.f / 3.f), ira2, f2(1.f, 1.f)));
-        near |= fminf(w2[q].x, w2[q].y) <= near2;
-    }
-    if (__any_sync(0xffffffffu, near)) { // overlapping beads (ra <= 2): rare, scalar
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (w2[q].x <= near2) {
-                const float ra = (w2[q].x * iw[q].x) * inv_a;
-                crr[q].x = (3.f / 32.f) * ra;
-                cii[q].x = 1.f - (9.f / 32.f) * ra;
-            }
-            if (w2[q].y <= near2) {
-                const float ra = (w2[q].y * iw[q].y) * inv_a;
-                crr[q].y = (3.f / 32.f) * ra;
-                cii[q].y = 1.f - (9.f / 32.f) * ra;
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int rd = q >> 1, pk = q & 1;
-        const float2 gx = __ffma2_rn(f2(r[rd].x, r[rd].x), B.cx[pk], f2(m[rd].x, m[rd].x));
-        const float2 gy = __ffma2_rn(f2(r[rd].y, r[rd].y), B.cy[pk], f2(m[rd].y, m[rd].y));
-        const float2 gz = __ffma2_rn(f2(r[rd].z, r[rd].z), B.cz[pk], f2(m[rd].z, m[rd].z));
-        const float2 pr = __fmul2_rn(crr[q], __ffma2_rn(uz[q], gz, __ffma2_rn(uy[q], gy, __fmul2_rn(ux[q], gx))));
-        B.ax[pk] = __ffma2_rn(cii[q], gx, __ffma2_rn(pr, ux[q], B.ax[pk]));
-        B.ay[pk] = __ffma2_rn(cii[q], gy, __ffma2_rn(pr, uy[q], B.ay[pk]));
-        B.az[pk] = __ffma2_rn(cii[q], gz, __ffma2_rn(pr, uz[q], B.az[pk]));
+        const float2 crr = __fmul2_rn(far, __ffma2_rn(f2(-2.f, -2.f), ira2, f2(1.f, 1.f)));
+        const float2 cii = __fmul2_rn(far, __ffma2_rn(f2(2.f / 3.f, 2.f / 3.f), ira2, f2(1.f, 1.f)));
+        const float2 gx = __ffma2_rn(*reinterpret_cast<const float2 *>(&T[6][jj]), f2(Cx, Cx), *reinterpret_cast<const float2 *>(&T[3][jj]));
+        const float2 gy = __ffma2_rn(*reinterpret_cast<const float2 *>(&T[7][jj]), f2(Cy, Cy), *reinterpret_cast<const float2 *>(&T[4][jj]));
+        const float2 gz = __ffma2_rn(*reinterpret_cast<const float2 *>(&T[8][jj]), f2(Cz, Cz), *reinterpret_cast<const float2 *>(&T[5][jj]));
+        const float2 pr = __fmul2_rn(crr, __ffma2_rn(uz, gz, __ffma2_rn(uy, gy, __fmul2_rn(ux, gx))));
+        A.x[h] = __ffma2_rn(cii, gx, __ffma2_rn(pr, ux, A.x[h]));
+        A.y[h] = __ffma2_rn(cii, gy, __ffma2_rn(pr, uy, A.y[h]));
+        A.z[h] = __ffma2_rn(cii, gz, __ffma2_rn(pr, uz, A.z[h]));
     }
 }
 
-// 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 fills zeros
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+// number of partner segments for a trajectory of N beads (a function of N alone, see above)
+__host__ __device__ inline int tea_segments(int N) { return N < TEA_SPLIT_NTOT ? 1 : ((N + 384) / 768 > 16 ? 16 : (N + 384) / 768); }
 
-// TEA_S parts per bead group, TEA_G groups per CTA (TEA_S * TEA_G = 8 warps).  <4, 2> for long trajectories, <1, 8> for
-// short ones (their ensembles have warps to spare, and a part would only see a handful of rounds).  The choice depends
-// on N alone, so a trajectory's result does not depend on how many trajectories share the launch.
-template <int TEA_S, int TEA_G>
-__global__ void __launch_bounds__(TEA_THREADS, 2) tea_pair_kernel(const __grid_constant__ KArgs k)
+template <int TEA_S>
+__global__ void __launch_bounds__(TEA_S * 32, 16 / TEA_S) tea_pair_kernel(const __grid_constant__ KArgs k)
 {
-    constexpr int TEA_ROUNDS = TEA_TILE / 32 / TEA_S;
     const maddy_params &p = k.p;
     const DevSys &a = k.a;
-    const int N = a.N, traj = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = warp / TEA_S, part = warp % TEA_S;
-    const int i0 = (blockIdx.x * TEA_G + grp) * TEA_IB; // may be >= N: the warp still loads tiles and meets the barriers
+    const int N = a.N, traj = blockIdx.z, seg = blockIdx.y, nseg = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
+    const int i0 = blockIdx.x * TEA_BLOCK;
+    const int i = min(i0 + lane, N - 1); // lanes beyond N shadow the last bead (their results are dropped)
     const size_t base = (size_t)traj * N;
     const float4 *co = a.tea_co + base, *mf = a.tea_mf + base, *rf = a.tea_rf + base;
-    // partner tiles {position, molecular force, random force}: TEA_STAGES-deep ring filled with cp.async
-    __shared__ float4 tile[TEA_STAGES][3][TEA_TILE];
+    // partner tile, structure of arrays: x, y, z | molecular force x, y, z | random force x, y, z
+    __shared__ __align__(16) float tile[9][TEA_TILE];
+    __shared__ bool last_cta;
 
     const float beta = a.tea_beta[traj];
     const float b2 = beta * beta;
-    TeaBeads B;
-#pragma unroll
-    for (int pk = 0; pk < 2; pk++) {
-        float q[2][6];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int i = min(i0 + 2 * pk + h, N - 1);
-            const float4 raw = a.tea_ci[base + i], ci = co[i];
-            q[h][0] = -ci.x; q[h][1] = -ci.y; q[h][2] = -ci.z;
-            q[h][3] = beta * (1.f / sqrtf(1.f + b2 * raw.x));
-            q[h][4] = beta * (1.f / sqrtf(1.f + b2 * raw.y));
-            q[h][5] = beta * (1.f / sqrtf(1.f + b2 * raw.z));
-        }
-        B.npx[pk] = f2(q[0][0], q[1][0]); B.npy[pk] = f2(q[0][1], q[1][1]); B.npz[pk] = f2(q[0][2], q[1][2]);
-        B.cx[pk] = f2(q[0][3], q[1][3]); B.cy[pk] = f2(q[0][4], q[1][4]); B.cz[pk] = f2(q[0][5], q[1][5]);
-        B.ax[pk] = B.ay[pk] = B.az[pk] = f2(0.f, 0.f);
-    }
+    const float4 ci = co[i], raw = a.tea_ci[base + i];
+    const float npx = -ci.x, npy = -ci.y, npz = -ci.z;
+    const float sxc = 1.f / sqrtf(1.f + b2 * raw.x), syc = 1.f / sqrtf(1.f + b2 * raw.y), szc = 1.f / sqrtf(1.f + b2 * raw.z);
+    const float Cx = beta * sxc, Cy = beta * syc, Cz = beta * szc; // beta * C_i
     const float ta = p.tea_a, inv_a = 1.f / p.tea_a, near2 = 4.f * p.tea_a * p.tea_a;
+    TeaAcc A;
+#pragma unroll
+    for (int h = 0; h < 2; h++) A.x[h] = A.y[h] = A.z[h] = f2(0.f, 0.f);
 
-    const int ntiles = (N + TEA_TILE - 1) / TEA_TILE;
-    auto fetch = [&](int t) { // tile t -> stage t % TEA_STAGES; TEA_TILE / TEA_THREADS partners per thread
-        if (t < ntiles) {
-            float4(*T)[TEA_TILE] = tile[t % TEA_STAGES];
-#pragma unroll
-            for (int u = 0; u < TEA_TILE / TEA_THREADS; u++) {
-                const int jj = u * TEA_THREADS + tid, j = t * TEA_TILE + jj, jc = min(j, N - 1), nb = j < N ? 16 : 0;
-                cp_async16(&T[0][jj], co + jc, nb);
-                cp_async16(&T[1][jj], mf + jc, nb);
-                cp_async16(&T[2][jj], rf + jc, nb);
+    // this CTA's partner segment, in steps of four partners
+    const int steps_all = (N + 3) / 4;
+    const int per_seg = (steps_all + nseg - 1) / nseg;
+    const int st_lo = seg * per_seg, st_hi = min(st_lo + per_seg, steps_all);
+    const int self_lo = i0 / 4; // steps self_lo .. self_lo + 7 hold the warp's own beads
+    for (int t0 = st_lo; t0 < st_hi; t0 += TEA_TILE / 4) {
+        const int nst = min(TEA_TILE / 4, st_hi - t0);
+        if (t0 != st_lo) __syncthreads(); // everybody is done with the previous tile
+        for (int jj = tid; jj < nst * 4; jj += TEA_S * 32) {
+            const int j = t0 * 4 + jj;
+            float4 c = make_float4(3.0e5f, 3.0e5f, 3.0e5f, 0.f), m = make_float4(0.f, 0.f, 0.f, 0.f), r = m; // padding: far away, no force
+            if (j < N) {
+                c = co[j];
+                m = mf[j];
+                r = rf[j];
             }
+            tile[0][jj] = c.x; tile[1][jj] = c.y; tile[2][jj] = c.z;
+            tile[3][jj] = m.x; tile[4][jj] = m.y; tile[5][jj] = m.z;
+            tile[6][jj] = r.x; tile[7][jj] = r.y; tile[8][jj] = r.z;
         }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int t = 0; t < TEA_STAGES - 1; t++) fetch(t);
-    for (int t = 0; t < ntiles; t++) {
-        cp_async_wait<TEA_STAGES - 2>(); // this thread's part of tile t has landed
-        __syncthreads();                 // everybody's has; and everybody is done with the stage refilled below
-        fetch(t + TEA_STAGES - 1);
-        const float4(*T)[TEA_TILE] = tile[t % TEA_STAGES];
-        auto special = [&](int j0) { return (j0 <= i0 + TEA_IB - 1 && i0 <= j0 + 31) || j0 + 31 >= N; }; // self pair or padding inside
-        auto one = [&](int jj0, int j0) {
-            if (special(j0)) tea_round<true>(B, T[0], T[1], T[2], jj0 + lane, j0 + lane, i0, N, ta, inv_a, near2);
-            else tea_round<false>(B, T[0], T[1], T[2], jj0 + lane, j0 + lane, i0, N, ta, inv_a, near2);
+        __syncthreads();
+        auto one = [&](int st) {
+            const int gs = t0 + st;
+            if ((unsigned)(gs - self_lo) < 8u) tea_step<true>(A, tile, st * 4, gs * 4, i, npx, npy, npz, Cx, Cy, Cz, ta, inv_a, near2);
+            else tea_step<false>(A, tile, st * 4, gs * 4, i, npx, npy, npz, Cx, Cy, Cz, ta, inv_a, near2);
         };
+        int st = part;
 #pragma unroll 1
-        for (int r = 0; r < TEA_ROUNDS; r += 2) {
-            const int jjA = (part + TEA_S * r) * 32, jA = t * TEA_TILE + jjA;
-            const int jjB = jjA + TEA_S * 32, jB = jA + TEA_S * 32;
-            if (jA >= N) break;
-            if (jB < N && !special(jA) && !special(jB)) tea_round2(B, T[0], T[1], T[2], jjA + lane, jjB + lane, ta, inv_a, near2);
-            else {
-                one(jjA, jA);
-                if (jB < N) one(jjB, jB);
+        for (; st + (TEA_NS - 1) * TEA_S < nst; st += TEA_NS * TEA_S) {
+            const int g0 = t0 + st - self_lo; // the group covers steps g0, g0 + TEA_S, ... relative to the warp's own block
+            if (g0 < 8 && g0 + (TEA_NS - 1) * TEA_S >= 0) {
+#pragma unroll 1
+                for (int q = 0; q < TEA_NS; q++) one(st + q * TEA_S);
+            } else {
+                tea_steps(A, tile, st * 4, TEA_S * 4, (t0 + st) * 4, i, npx, npy, npz, Cx, Cy, Cz, ta, inv_a, near2);
             }
         }
+#pragma unroll 1
+        for (; st + TEA_S < nst; st += TEA_S) one(st);
+        if (st < nst) one(st);
     }
-    cp_async_wait<0>();
-    __syncthreads();
-    // combine the parts of a group in a fixed order (the tile buffers are free now)
-    static_assert(TEA_S == 1 || TEA_S == 4, "parts per bead group");
-    float sum[6][2];
-    if (TEA_S == 4) {
-        float2 *ps = reinterpret_cast<float2 *>(&tile[0][0][0]);
-        float2 *mine = ps + ((grp * TEA_S + part) * 6) * 32 + lane;
-        mine[0 * 32] = B.ax[0]; mine[1 * 32] = B.ay[0]; mine[2 * 32] = B.az[0];
-        mine[3 * 32] = B.ax[1]; mine[4 * 32] = B.ay[1]; mine[5 * 32] = B.az[1];
+    // per lane: the four partner streams in a fixed order, then the parts of the CTA in part order
+    float sx = (A.x[0].x + A.x[0].y) + (A.x[1].x + A.x[1].y);
+    float sy = (A.y[0].x + A.y[0].y) + (A.y[1].x + A.y[1].y);
+    float sz = (A.z[0].x + A.z[0].y) + (A.z[1].x + A.z[1].y);
+    if (TEA_S > 1) {
+        __syncthreads(); // the tile is free
+        float *ps = &tile[0][0];
+        ps[(part * 3 + 0) * 32 + lane] = sx;
+        ps[(part * 3 + 1) * 32 + lane] = sy;
+        ps[(part * 3 + 2) * 32 + lane] = sz;
         __syncthreads();
         if (part != 0) return;
+        sx = ps[0 * 32 + lane];
+        sy = ps[1 * 32 + lane];
+        sz = ps[2 * 32 + lane];
 #pragma unroll
-        for (int c = 0; c < 6; c++) {
-            const float2 p0 = ps[((grp * TEA_S + 0) * 6 + c) * 32 + lane], p1 = ps[((grp * TEA_S + 1) * 6 + c) * 32 + lane];
-            const float2 p2 = ps[((grp * TEA_S + 2) * 6 + c) * 32 + lane], p3 = ps[((grp * TEA_S + 3) * 6 + c) * 32 + lane];
-            sum[c][0] = warp_sum((p0.x + p1.x) + (p2.x + p3.x));
-            sum[c][1] = warp_sum((p0.y + p1.y) + (p2.y + p3.y));
-        }
-    } else {
-        const float2 acc[6] = {B.ax[0], B.ay[0], B.az[0], B.ax[1], B.ay[1], B.az[1]};
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            sum[c][0] = warp_sum(acc[c].x);
-            sum[c][1] = warp_sum(acc[c].y);
+        for (int q = 1; q < TEA_S; q++) {
+            sx += ps[(q * 3 + 0) * 32 + lane];
+            sy += ps[(q * 3 + 1) * 32 + lane];
+            sz += ps[(q * 3 + 2) * 32 + lane];
         }
     }
-    const int i = i0 + lane;
-    if (lane >= TEA_IB || i >= N) return;
-    // lane b finishes bead i0 + b = pair b / 2, half b % 2
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll
-    for (int b = 0; b < TEA_IB; b++)
-        if (lane == b) {
-            sx = sum[3 * (b / 2) + 0][b % 2];
-            sy = sum[3 * (b / 2) + 1][b % 2];
-            sz = sum[3 * (b / 2) + 2][b % 2];
+    // (one warp from here on)
+    if (nseg > 1) {
+        // partial sums of the segments meet in HBM; the CTA whose ticket is the last one adds them in segment order
+        float4 *mine = a.tea_part + ((size_t)traj * nseg + seg) * N;
+        if (i0 + lane < N) mine[i0 + lane] = make_float4(sx, sy, sz, 0.f);
+        __threadfence();
+        __syncwarp();
+        unsigned *cnt = a.tea_cnt + (size_t)traj * gridDim.x + blockIdx.x;
+        if (lane == 0) {
+            const unsigned ticket = atomicAdd(cnt, 1u);
+            last_cta = ticket == (unsigned)nseg - 1;
+            if (last_cta) *cnt = 0; // ready for the next step
         }
-    const float4 ci = co[i], fm = mf[i], fr = rf[i], raw = a.tea_ci[base + i];
-    sx += fm.x + fr.x * (1.f / sqrtf(1.f + b2 * raw.x));
-    sy += fm.y + fr.y * (1.f / sqrtf(1.f + b2 * raw.y));
-    sz += fm.z + fr.z * (1.f / sqrtf(1.f + b2 * raw.z));
+        __syncwarp();
+        if (!last_cta) return;
+        __threadfence();
+        sx = sy = sz = 0.f;
+        if (i0 + lane < N)
+            for (int q = 0; q < nseg; q++) {
+                const float4 v = __ldcg(a.tea_part + ((size_t)traj * nseg + q) * N + i0 + lane);
+                sx += v.x;
+                sy += v.y;
+                sz += v.z;
+            }
+    }
+    if (i0 + lane >= N) return;
+    const float4 fm = mf[i], fr = rf[i];
+    sx += fm.x + fr.x * sxc;
+    sy += fm.y + fr.y * syc;
+    sz += fm.z + fr.z * szc;
     // The angular stream advances for every bead (:194), the update only for free ones (:196-204)
     uint4 st = a.rng_ang[base + i];
     const float4 rf_ang = rforce(st);
     a.rng_ang[base + i] = st;
     if (!(a.sflags[i] & 1) && ci.w == 0.f) {
         const float mult = p.dt / p.gammaR;
-        const float4 A = a.ang[base + i], FA = a.fang[base + i];
+        const float4 AN = a.ang[base + i], FA = a.fang[base + i];
         a.pos[base + i] = make_float4(ci.x + mult * sx, ci.y + mult * sy, ci.z + mult * sz, 0.f);
-        float fi = A.x, psi = A.y, theta = A.z;
+        float fi = AN.x, psi = AN.y, theta = AN.z;
         fi += (p.dt / (p.gammaTheta * p.alpha)) * FA.x + (p.varTheta * sqrtf(p.freeze_temp / p.alpha)) * rf_ang.x;
         psi += (p.dt / (p.gammaTheta * p.alpha)) * FA.y + (p.varTheta * sqrtf(p.freeze_temp / p.alpha)) * rf_ang.y;
         theta += (p.dt / p.gammaTheta) * FA.z + p.varTheta * rf_ang.z;
         a.ang[base + i] = make_float4(fi, psi, theta, 0.f);
     }
 }
+
+int tea_partner_segments(int N) { return tea_segments(N); }
 
 // which = 0: epsilon update (snapshot, per-bead statistics, per-trajectory beta); which = 1: prepare + pair step;
 // which = 2: pair step only (the force launch did the prepare part, OP_TEA_PREP)
@@ -471,8 +463,9 @@ cudaError_t launch_tea_kernels(const KArgs &k, int which, long long /*step*/, cu
         tea_beta_kernel<<<k.a.ntr, 256, 0, st>>>(k);
     } else {
         if (which == 1) tea_prepare_kernel<<<eblocks, 256, 0, st>>>(k);
-        if (N >= TEA_SPLIT_NTOT) tea_pair_kernel<4, 2><<<dim3((N + 2 * TEA_IB - 1) / (2 * TEA_IB), k.a.ntr), TEA_THREADS, 0, st>>>(k);
-        else tea_pair_kernel<1, 8><<<dim3((N + 8 * TEA_IB - 1) / (8 * TEA_IB), k.a.ntr), TEA_THREADS, 0, st>>>(k);
+        const dim3 pgrid((N + TEA_BLOCK - 1) / TEA_BLOCK, tea_segments(N), k.a.ntr);
+        if (N >= TEA_SPLIT_NTOT) tea_pair_kernel<4><<<pgrid, 4 * 32, 0, st>>>(k);
+        else tea_pair_kernel<2><<<pgrid, 2 * 32, 0, st>>>(k);
     }
     return cudaGetLastError();
 }
