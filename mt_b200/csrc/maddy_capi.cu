@@ -10,6 +10,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <algorithm>
 #include <thread>
 #include <mutex>
 #include <memory>
@@ -34,6 +35,7 @@ int tea_partner_segments(int N);
 cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
+cudaError_t launch_wide_run(const KArgs &k, int buf, int n_steps, int publish_first, cudaStream_t st);
 cudaError_t launch_analysis(int which, const AnalysisArgs &a, cudaStream_t st);
 cudaError_t launch_ensemble_stats(const double *en_traj, int ntr, double *out, cudaStream_t st);
 cudaError_t launch_ontubule(const float4 *pos, const float4 *ang, int ntr, int N, const OnTubRule &rule, uint8_t *out_flags, uint8_t *live_flags,
@@ -268,8 +270,9 @@ static int sync_and_check(maddy_handle *h)
 }
 
 // Wide path: the same operations as launch sequences over the whole GPU (maddy_wide.cuh).  A step-granular phase is
-// [publish -> phase]; a fused window is [publish, then per step: (rebuild at list-update steps) -> step], one launch per
-// step, the step kernel publishing the next step's stage itself.
+// [publish -> phase]; a fused window is cut at list-update steps and scheduled hydrolysis events into segments of ONE
+// persistent cooperative launch each (wide_run_kernel: per-trajectory barrier per step, near list, state in registers);
+// ensembles whose CTAs cannot all be resident, or MADDY_WIDE_PER_STEP=1, take one launch per step (wide_step_kernel).
 static cudaError_t wide_dispatch(maddy_handle *h, const KArgs &k)
 {
     cudaStream_t st = h->stream;
@@ -288,28 +291,74 @@ static cudaError_t wide_dispatch(maddy_handle *h, const KArgs &k)
     KArgs ks = k, kr = k;
     ks.ops = OP_FORCE;
     kr.ops = rops;
+    const long long end = k.first_step + k.n_steps;
+    const long long freq = p.ljpairsupdatefreq > 0 ? p.ljpairsupdatefreq : 1;
+    auto event_at = [&](long long step) { // scheduled hydrolysis event (maddy_schedule_gtp) at this step: its slot, or -1
+        if (k.sched_slots <= 0 || step < k.sched_first || (step - k.sched_first) % k.sched_period != 0) return -1LL;
+        const long long slot = (step - k.sched_first) / k.sched_period;
+        return slot < k.sched_slots ? slot : -1LL;
+    };
+    auto rebuild_at = [&](long long step) {
+        return rops != 0 && step % freq == 0 && !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
+    };
     int buf = 0;
-    if ((e = launch_wide_publish(ks, buf, st)) != cudaSuccess) return e;
-    for (long long step = k.first_step; step < k.first_step + k.n_steps; step++) {
-        // scheduled hydrolysis event (maddy_schedule_gtp): the flags of this slot become current, the stage is re-published
-        if (k.sched_slots > 0 && step >= k.sched_first && (step - k.sched_first) % k.sched_period == 0) {
-            const long long slot = (step - k.sched_first) / k.sched_period;
-            if (slot < k.sched_slots) {
-                e = cudaMemcpyAsync(h->a.gtp, h->d_sched + (size_t)slot * n, n, cudaMemcpyDeviceToDevice, st);
-                if (e != cudaSuccess) return e;
+    bool staged = false; // stage[buf] holds the current state
+    bool persistent = !getenv("MADDY_WIDE_PER_STEP");
+    long long step = k.first_step;
+    while (step < end) {
+        // scheduled hydrolysis event: the flags of this slot become current (the stage carries them: re-publish)
+        const long long slot = event_at(step);
+        if (slot >= 0) {
+            e = cudaMemcpyAsync(h->a.gtp, h->d_sched + (size_t)slot * n, n, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            staged = false;
+        }
+        if (rebuild_at(step)) {
+            if (!staged) {
                 if ((e = launch_wide_publish(ks, buf, st)) != cudaSuccess) return e;
                 h->launches++;
+                staged = true;
             }
-        }
-        const bool do_rebuild = rops != 0 && step % p.ljpairsupdatefreq == 0 &&
-                                !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
-        if (do_rebuild) {
             if ((e = launch_wide_phase(kr, buf, st)) != cudaSuccess) return e;
             h->launches++;
         }
-        if ((e = launch_wide_step(ks, buf, st)) != cudaSuccess) return e;
-        h->launches++;
-        buf ^= 1;
+        // steps up to the next list-update step / scheduled event: one persistent launch
+        long long seg_end = end;
+        if (rops != 0) seg_end = std::min(seg_end, (step / freq + 1) * freq);
+        if (k.sched_slots > 0) {
+            for (long long q = step + 1; q < seg_end; q++) // (segments are at most one list-update period long)
+                if (event_at(q) >= 0) {
+                    seg_end = q;
+                    break;
+                }
+        }
+        if (rops == 0 && seg_end - step > 4096) seg_end = step + 4096;
+        const int count = (int)(seg_end - step);
+        if (persistent) {
+            e = launch_wide_run(ks, buf, count, staged ? 0 : 1, st);
+            if (e == cudaErrorCooperativeLaunchTooLarge) {
+                persistent = false; // the ensemble does not fit the GPU at once: one launch per step
+                (void)cudaGetLastError();
+            } else if (e != cudaSuccess) {
+                return e;
+            } else {
+                h->launches++;
+                buf ^= count & 1;
+                staged = true;
+                step = seg_end;
+                continue;
+            }
+        }
+        if (!staged) {
+            if ((e = launch_wide_publish(ks, buf, st)) != cudaSuccess) return e;
+            h->launches++;
+            staged = true;
+        }
+        for (; step < seg_end; step++) {
+            if ((e = launch_wide_step(ks, buf, st)) != cudaSuccess) return e;
+            h->launches++;
+            buf ^= 1;
+        }
     }
     return cudaSuccess;
 }
@@ -663,6 +712,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
             pool_req(&a.tea_cnt, (size_t)ntr * ((N + 31) / 32));
         }
         if (wide) pool_req(&a.gstage, 8 * n);
+        if (wide) pool_req(&a.wbar, (size_t)ntr * 4);
         if (wide && !getenv("MADDY_WIDE_ALL_PAIRS")) // WGrid header + count/start/cursor[32768] + members[Npad] per trajectory (maddy_wide.cuh)
             pool_req(reinterpret_cast<char **>(&a.wgrid), (size_t)ntr * (64 + (size_t)3 * 32768 * 4 + (size_t)a.Npad * 2));
         CK(pool_commit(h, reqs));

@@ -62,6 +62,7 @@ struct Near { // shared-memory near list of the fused loop (see MD_NEAR_R2 in ma
     uint8_t *cnt;   // [N]
     float4 *tlo, *thi; // bounding boxes of tiles of MD_TILE consecutive monomers
     int cap, ntiles;
+    int stride;     // row stride of `list` for stages in global memory (the wide path's per-CTA list); N otherwise
     bool ok;        // CTA-uniform: the near list is valid for this step
     bool stale_lj;  // CTA-uniform: the Verlet list in HBM predates the last list-update step (lazy fused loop): a monomer
                     // whose near list overflowed walks its near-candidates instead (same pairs inside the force cut-off,
@@ -241,6 +242,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
             // bit-for-bit unchanged, so the loop body has no branch.  A pair inside the +-1e-6 band around the exact
             // threshold (practically never) is only noted; the sum is then redone with the fp64 tie-break.
             const int n = ncnt;
+            const int nstride = S::kGlobal ? near.stride : a.N; // compile-time choice: the shared-memory stage keeps rows of N
             const int16_t *nl = reinterpret_cast<const int16_t *>(near.list) + i; // bit 15 (LJ-listed) read as the sign
             const float lo = k.cut_force.lo, hi = k.cut_force.hi;
             bool band = false;
@@ -251,7 +253,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
                 const float mid = k.band_mid, hw = k.band_hw;
 #pragma unroll 4
                 for (int kk = 0; kk < n; kk++) {
-                    const float4 Pj = s.P(nu[kk * a.N] & 0x7fffu);
+                    const float4 Pj = s.P(nu[kk * nstride] & 0x7fffu);
                     const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                     const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     band |= fabsf(sf - mid) <= hw;
@@ -264,7 +266,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
                 }
             } else
             for (int kk = 0; kk < n; kk++) {
-                const int e = nl[kk * a.N];
+                const int e = nl[kk * nstride];
                 const float4 Pj = s.P(e & 0x7fff);
                 const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                 const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -280,7 +282,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
             if (band) {
                 fx = fy = fz = 0.f;
                 for (int kk = 0; kk < n; kk++) {
-                    const int e = nl[kk * a.N];
+                    const int e = nl[kk * nstride];
                     const float4 Pj = s.P(e & 0x7fff);
                     const float dx = xi - Pj.x, dy = yi - Pj.y, dz = zi - Pj.z;
                     const float sf = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -1122,6 +1124,7 @@ __device__ __forceinline__ Near carve_near(float4 *smem, const KArgs &k, int N)
     near.ok = false;
     near.stale_lj = false;
     near.topo = nullptr;
+    near.stride = N;
     return near;
 }
 

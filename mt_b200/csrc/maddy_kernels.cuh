@@ -73,6 +73,7 @@ struct DevSys {
     float *tea_eps;
     float *tea_beta;
     float4 *tea_co, *tea_mf, *tea_rf; // per-step snapshots: coordinates (+extra in .w), molecular force, random force
+    unsigned *wbar;    // [ntr][4] wide path, persistent window: barrier tickets + displacement-guard words of each trajectory
     float4 *tea_part;  // [ntr][segments][N] partial sums of the partner segments (long trajectories only)
     unsigned *tea_cnt; // [ntr][bead blocks] tickets of the segment CTAs (self-resetting)
     float4 *gstage; // wide path only (maddy_wide.cuh): [2][4][ntr*N] stage in HBM, or nullptr
