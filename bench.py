@@ -311,7 +311,7 @@ def run_own(args):
         t_warm = region(0, warm, False)
         eng.sync()
         est = max(t_warm / warm * K * 1e-3, 1e-6)  # seconds per repetition
-        reps = int(min(21, max(1, math.ceil(args.min_timed_s / est))))
+        reps = int(min(61, max(1, math.ceil(args.min_timed_s / est))))
         reps += 1 - reps % 2
         launches0 = eng.launches
         if world > 1:
@@ -436,6 +436,17 @@ def run_own(args):
                                      "the binding limit is SM issue/latency (see profiles/)"},
                 "ensemble_energy_sum": [float(x) for x in esum.tolist()], "finite": finite,
             }
+            if system.par.tea_on and win_ms:
+                # TEA: the O(N^2) Rotne-Prager pair work is FP32-pipe bound (~45 flop per ordered pair); the
+                # windows timed above hold force + prepare + pair kernel of every step, so this is a lower bound for the
+                # pair kernel alone (profiles/ has its own duration)
+                flop = 45.0 * (N - 1) * N * ntr_local * md_per_launch
+                tf = flop / (avg_launch_ms * 1e-3) / 1e12
+                fp32_peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+                line["roofline_fp32"] = {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                                         "flop_per_monomer_step": 45.0 * (N - 1), "peak_source": "148 SMs x 128 lanes x 2 flop x SM clock (nominal; "
+                                         "the packed FFMA2 ceiling measured on this GPU is 66 TFLOP/s, profiles/r1_ffma2_microbench.txt)",
+                                         "kernel": "maddy::tea_pair_kernel inside whole TEA steps (force + prepare launch included in the time)"}
             if world > 1:
                 line["shard_parity"] = shard_parity
                 line["e2e_one_host"] = one_host
@@ -627,7 +638,7 @@ def main():
     ap.add_argument("--workload", default="mt40_ensemble")
     ap.add_argument("--ntr", type=int, default=256, help="trajectories per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--min-timed-s", type=float, default=3.0, help="repeat the K-step timed region until this much device time is covered (median reported)")
+    ap.add_argument("--min-timed-s", type=float, default=8.0, help="repeat the K-step timed region until this much device time is covered (median reported)")
     ap.add_argument("--ref-timeout", type=float, default=1500.0)
     ap.add_argument("--ref-sequential-only", action="store_true")
     args = ap.parse_args()

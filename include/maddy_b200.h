@@ -173,6 +173,31 @@ int maddy_run(maddy_handle *h, long long first_step, long long n_steps, unsigned
  * may be issued while the previous window (and its schedule) is still running. */
 int maddy_schedule_gtp(maddy_handle *h, long long first_event, long long period, int n_slots, const int *gtp_slots);
 
+/* ---- hydrolyse() (updater.cpp:229-257) for ALL events of one output stride, on the device.
+ * Inside a stride a dimer's eligibility changes only through hydrolysis itself (on-tubule and reserve flags change at
+ * stride steps), so right after the stride block the events at first_event, first_event + period, ... (n_events of them,
+ * none beyond the next stride step) are evaluated in one go: same draws in the same order as the reference's host loop
+ * (dimer-outer / trajectory-inner, one rand() per eligible dimer, hydrolysis iff rand() / (double)RAND_MAX < 0.02, then
+ * the return of off-tubule GDP dimers to GTP).  rand_window31: the 31 words of the caller's libc-rand()-compatible
+ * generator (glibc TYPE_3), oldest first, such that the next draw is (w[0] + w[28]) >> 1; the device produces the stream
+ * behind it by jump-ahead.  The on-tubule flags are the ones of the last two MADDY_SNAP_ONTUBULE classifications (before
+ * the first: the flags passed to maddy_create).  The result becomes the handle's GTP schedule exactly as if
+ * maddy_schedule_gtp had been called with the n_events states (a following maddy_run may span all of them).
+ * Asynchronous; maddy_hydrolysis_result blocks until the counters have landed: draws_total = rand() calls the events
+ * consumed (the caller advances its generator by that many, e.g. with maddy_rand_discard), event_first_draw[k] = draws
+ * consumed before event k (may be NULL), gtp_slots ([n_events][n_tr_local * n_tot] ints, may be NULL; only available
+ * when the plan was made with MADDY_HYD_KEEP_SLOTS) = GTP state after every event, for the caller's messages.
+ * Requires one handle holding the whole ensemble (n_tr_local == n_tr) and an even n_tot. */
+#define MADDY_HYD_KEEP_SLOTS 1u
+int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *rand_window31, long long first_event, long long period, int n_events, unsigned flags);
+int maddy_hydrolysis_result(maddy_handle *h, unsigned long long *draws_total, unsigned long long *event_first_draw, int *gtp_slots);
+/* The scheduled GTP state of `step` (maddy_schedule_gtp / maddy_hydrolysis_plan), if there is one, becomes current NOW
+ * (the fused loop applies slots at the start of their step; a caller that evaluates energies at that step before it
+ * launches the window - the stride block, compute_cuda.cu:1153-1170 - needs them earlier).  No-op without such a slot. */
+int maddy_apply_scheduled_gtp(maddy_handle *h, long long step);
+/* window31 (oldest word first) of a glibc TYPE_3 generator advanced by n draws, in place.  Needs no GPU. */
+void maddy_rand_discard(unsigned *window31, unsigned long long n);
+
 /* ---- energies: energy_kernel + OutputAllEnergies (compute_cuda.cu:676-911,
  * updater.cpp:3-43).  out_per_traj: [n_tr_local][7] doubles (harm,long,lat,psi,fi,teta,lj);
  * out_per_monomer (may be NULL): [n_tr_local*n_tot][7] doubles in the reference's
@@ -201,6 +226,7 @@ int maddy_rebuild_and_energies(maddy_handle *h, double *out_per_traj, double *ou
  * maddy_snapshot_on_tubule (flags, after maddy_snapshot_end). */
 #define MADDY_SNAP_ONTUBULE 16u
 #define MADDY_SNAP_ONTUBULE_APPLY 32u
+#define MADDY_SNAP_GTP 64u /* the GTP flags as of the snapshot (maddy_snapshot_gtp after maddy_snapshot_end) */
 int maddy_snapshot_begin(maddy_handle *h, unsigned what);
 int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *forces_aos7, double *energies_per_traj);
 /* Per-trajectory on-tubule counts (`sum` of updater.cpp:164-170) of the snapshot in flight: blocks only until the
@@ -213,6 +239,7 @@ int maddy_snapshot_tubule_lengths(maddy_handle *h, int *mt_len, int *undecided);
 int maddy_has_exact_on_tubule(const maddy_handle *h);
 /* on_tubule_cur[n_tr_local * n_tot] / mt_len[n_tr_local] of the snapshot collected last by maddy_snapshot_end. */
 int maddy_snapshot_on_tubule(maddy_handle *h, int *on_tubule_cur, int *mt_len);
+int maddy_snapshot_gtp(maddy_handle *h, int *gtp);
 /* device-resident result of the last maddy_energies call: [n_tr_local][7] doubles */
 void *maddy_energies_device(maddy_handle *h);
 

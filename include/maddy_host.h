@@ -47,6 +47,11 @@ double *mt_system_energies(mt_system *s);         /* [n_tr][7] after a compute w
 const double *mt_system_ensemble_stats(const mt_system *s);
 /* srand(seed) of the reference main (main.cpp:67) for this system's host events (same sequence as libc rand()) */
 int mt_system_srand(mt_system *s, unsigned seed);
+/* the system's rand() stream (glibc TYPE_3, same sequence as libc rand()): its 31-word window (oldest first, what
+ * maddy_hydrolysis_plan takes), a jump over n draws, and one draw */
+int mt_system_rand_window(mt_system *s, unsigned *window31);
+int mt_system_rand_discard(mt_system *s, unsigned long long n);
+int mt_system_rand_next(mt_system *s);
 int mt_system_set_ngpus(mt_system *s, int n_gpus);
 int mt_system_set_steps(mt_system *s, long long steps);
 

@@ -162,6 +162,18 @@ class HostSystem:
         """srand(seed) for this system's host events (hydrolysis, insertion): same sequence as libc rand()"""
         capi.hostlib.mt_system_srand(self._h, int(seed) & 0xffffffff)
 
+    def rand_window(self) -> np.ndarray:
+        """31 words of the host rand() stream, oldest first (what Engine.hydrolysis_plan takes)"""
+        w = np.zeros(31, dtype=np.uint32)
+        capi.hostlib.mt_system_rand_window(self._h, as_ptr(w, C.c_uint))
+        return w
+
+    def rand_discard(self, n: int):
+        capi.hostlib.mt_system_rand_discard(self._h, int(n))
+
+    def rand_next(self) -> int:
+        return int(capi.hostlib.mt_system_rand_next(self._h))
+
     def mt_length(self, step: int) -> np.ndarray:
         out = np.zeros(self.Ntr, dtype=np.int32)
         if capi.hostlib.mt_system_mt_length(self._h, int(step), as_ptr(out, C.c_int)):
@@ -277,11 +289,11 @@ class Engine:
         self._ck(capi.lib.maddy_list_stats(self._h, out, int(reset)))
         return {"near_refresh": out[0], "candidate_rescan": out[1], "all_pairs_fallback": out[2], "near_overflow": out[3]}
 
-    def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False, on_tubule=False, apply_on_tubule=False):
+    def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False, on_tubule=False, apply_on_tubule=False, gtp=False):
         """queue the stride read-back (maddy_snapshot_begin); work queued afterwards overlaps with snapshot_end()"""
         what = (capi.SNAP_COORDS if coords else 0) | (capi.SNAP_FORCES if forces else 0) | (capi.SNAP_ENERGIES if energies else 0) \
             | (capi.SNAP_REBUILD if rebuild else 0) | (capi.SNAP_ONTUBULE if on_tubule or apply_on_tubule else 0) \
-            | (capi.SNAP_ONTUBULE_APPLY if apply_on_tubule else 0)
+            | (capi.SNAP_ONTUBULE_APPLY if apply_on_tubule else 0) | (capi.SNAP_GTP if gtp else 0)
         self._snap = what
         self._ck(capi.lib.maddy_snapshot_begin(self._h, what))
 
@@ -300,7 +312,31 @@ class Engine:
             ln = np.empty(self.ntr, dtype=np.int32)
             self._ck(capi.lib.maddy_snapshot_on_tubule(self._h, as_ptr(on, C.c_int), as_ptr(ln, C.c_int)))
             out["on_tubule"], out["mt_len"] = on, ln
+        if what & capi.SNAP_GTP:
+            g = np.empty((self.ntr, self.N), dtype=np.int32)
+            self._ck(capi.lib.maddy_snapshot_gtp(self._h, as_ptr(g, C.c_int)))
+            out["gtp"] = g
         return out
+
+    # ---- hydrolysis events of a stride on the device (maddy_hydrolysis_plan)
+    def hydrolysis_plan(self, rand_window, first_event: int, period: int, n_events: int, keep_slots: bool = False):
+        w = np.ascontiguousarray(rand_window, dtype=np.uint32)
+        assert w.size == 31
+        self._hyd = (int(n_events), bool(keep_slots))
+        self._ck(capi.lib.maddy_hydrolysis_plan(self._h, as_ptr(w, C.c_uint), int(first_event), int(period), int(n_events),
+                                                capi.HYD_KEEP_SLOTS if keep_slots else 0))
+
+    def hydrolysis_result(self):
+        """-> (draws_total, first draw of every event, slots [n_events, ntr, N] or None)"""
+        ne, keep = self._hyd
+        total = C.c_ulonglong()
+        first = np.zeros(ne, dtype=np.uint64)
+        slots = np.empty((ne, self.ntr, self.N), dtype=np.int32) if keep else None
+        self._ck(capi.lib.maddy_hydrolysis_result(self._h, C.byref(total), as_ptr(first, C.c_ulonglong), as_ptr(slots, C.c_int) if keep else None))
+        return int(total.value), first, slots
+
+    def apply_scheduled_gtp(self, step: int):
+        self._ck(capi.lib.maddy_apply_scheduled_gtp(self._h, int(step)))
 
     def snapshot_tubule_lengths(self):
         """(mt_len [ntr], undecided) of the snapshot in flight: waits for the counts only (maddy_snapshot_tubule_lengths)"""

@@ -53,8 +53,8 @@ def _run(cmd, **kw):
 
 
 def build_kernels(force=False, verbose_ptxas=False):
-    srcs = [CSRC / "maddy_kernels.cu", CSRC / "maddy_tea.cu", CSRC / "maddy_analysis.cu", CSRC / "maddy_capi.cu", CSRC / "maddy_seeds.cpp"]
-    deps = srcs + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "maddy_b200.h"]
+    srcs = [CSRC / "maddy_kernels.cu", CSRC / "maddy_tea.cu", CSRC / "maddy_analysis.cu", CSRC / "maddy_events.cu", CSRC / "maddy_capi.cu", CSRC / "maddy_seeds.cpp"]
+    deps = srcs + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "maddy_b200.h"]
     if not force and not _stale(LIB_KERNELS, deps):
         return LIB_KERNELS
     # -use_fast_math: the reference is built with it (CMakeLists.txt:62) and the MUFU lowering of

@@ -19,7 +19,8 @@ ZERO_SENTINEL = 999999
 LJ_CAPACITY = 256
 RUN_SKIP_FIRST_REBUILD = 1
 SNAP_COORDS, SNAP_FORCES, SNAP_ENERGIES, SNAP_REBUILD = 1, 2, 4, 8
-SNAP_ONTUBULE, SNAP_ONTUBULE_APPLY = 16, 32
+SNAP_ONTUBULE, SNAP_ONTUBULE_APPLY, SNAP_GTP = 16, 32, 64
+HYD_KEEP_SLOTS = 1
 LIST_LONGITUDINAL, LIST_LATERAL, LIST_LJ = 0, 1, 2
 LOAD_QUIET, LOAD_NO_FILES = 1, 2
 
@@ -103,10 +104,12 @@ KERNEL_SYMBOLS = [
     "maddy_list_stats", "maddy_analysis_setup", "maddy_analysis_reference", "maddy_analysis_temperature", "maddy_analysis_project",
     "maddy_analysis_protofilaments", "maddy_ensemble_stats_begin", "maddy_ensemble_stats_end", "maddy_download_tea",
     "maddy_snapshot_tubule_lengths", "maddy_snapshot_on_tubule", "maddy_insert_dimers", "maddy_has_exact_on_tubule",
+    "maddy_hydrolysis_plan", "maddy_hydrolysis_result", "maddy_apply_scheduled_gtp", "maddy_rand_discard", "maddy_snapshot_gtp",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
     "mt_system_gtp", "mt_system_on_tubule", "mt_system_extra", "mt_system_energies", "mt_system_ensemble_stats", "mt_system_set_ngpus", "mt_system_srand",
+    "mt_system_rand_window", "mt_system_rand_discard", "mt_system_rand_next",
     "mt_system_set_steps", "mt_system_compute", "mt_system_mt_length", "mt_system_hydrolyse", "mt_system_change_conc",
     "mt_system_save_pdb", "mt_dcd_read", "mt_pdb_count",
 ]
@@ -153,6 +156,11 @@ _sig(lib.maddy_snapshot_tubule_lengths, _i, [_vp, _pi, _pi])
 _sig(lib.maddy_snapshot_on_tubule, _i, [_vp, _pi, _pi])
 _sig(lib.maddy_insert_dimers, _i, [_vp, _i, _pi, _pf])
 _sig(lib.maddy_has_exact_on_tubule, _i, [_vp])
+_sig(lib.maddy_hydrolysis_plan, _i, [_vp, C.POINTER(C.c_uint), _ll, _ll, _i, _u])
+_sig(lib.maddy_hydrolysis_result, _i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _pi])
+_sig(lib.maddy_apply_scheduled_gtp, _i, [_vp, _ll])
+_sig(lib.maddy_rand_discard, None, [C.POINTER(C.c_uint), C.c_ulonglong])
+_sig(lib.maddy_snapshot_gtp, _i, [_vp, _pi])
 
 _sig(hostlib.mt_host_last_error, C.c_char_p, [])
 _sig(hostlib.mt_system_load, _i, [C.c_char_p, _i, C.POINTER(C.c_char_p), _u, C.POINTER(_vp)])
@@ -167,6 +175,9 @@ _sig(hostlib.mt_system_energies, _pd, [_vp])
 _sig(hostlib.mt_system_ensemble_stats, _pd, [_vp])
 _sig(hostlib.mt_system_set_ngpus, _i, [_vp, _i])
 _sig(hostlib.mt_system_srand, _i, [_vp, _u])
+_sig(hostlib.mt_system_rand_window, _i, [_vp, C.POINTER(C.c_uint)])
+_sig(hostlib.mt_system_rand_discard, _i, [_vp, C.c_ulonglong])
+_sig(hostlib.mt_system_rand_next, _i, [_vp])
 _sig(hostlib.mt_system_set_steps, _i, [_vp, _ll])
 _sig(hostlib.mt_system_compute, _i, [_vp, _i, _pd])
 _sig(hostlib.mt_system_mt_length, _i, [_vp, _ll, _pi])

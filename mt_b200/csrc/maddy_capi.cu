@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 #include "maddy_kernels.cuh"
+#include "maddy_lfib.h"
 
 namespace maddy {
 cudaError_t launch_run_kernel(const KArgs &k, int mpt, int ctas_per_sm, int threads, size_t smem, cudaStream_t st);
@@ -32,6 +33,8 @@ cudaError_t launch_snapshot_kernel(const float4 *pos, const float4 *ang, float *
 cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 int tea_partner_segments(int N);
+cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, cudaStream_t st);
+cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, cudaStream_t st);
 cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
@@ -126,10 +129,28 @@ struct maddy_handle {
     // on-tubule classification with the snapshot (MADDY_SNAP_ONTUBULE): rule, device results, pinned mirrors
     OnTubRule ontub_rule{};
     bool ontub_rule_ok = false;
-    uint8_t *d_cls_flags = nullptr, *h_cls_flags = nullptr;
+    uint8_t *d_cls_pair[2] = {nullptr, nullptr}; // the last two classifications (ping-pong): [cls_cur] newest, [cls_cur ^ 1] the one before
+    int cls_cur = 0;                             // (both start as the flags given to maddy_create: updater.cpp's on_tubule_prev = on_tubule_cur at step 0)
+    uint8_t *h_cls_flags = nullptr;
     int *d_cls_count = nullptr, *h_cls_count = nullptr; // [ntr + 1]: per-trajectory counts, then the undecided word
     unsigned cls_what = 0;                              // classification bits of the snapshot collected last
     cudaEvent_t cls_staged = nullptr, cls_done = nullptr; // counts written on the main stream / landed in h_cls_count
+    // GTP flags with the snapshot (MADDY_SNAP_GTP)
+    uint8_t *d_snap_gtp = nullptr, *h_snap_gtp = nullptr;
+    // hydrolysis events of a stride on the device (maddy_hydrolysis_plan)
+    uint8_t *d_hyd_gt = nullptr, *d_hyd_st = nullptr;
+    unsigned *d_hyd_rowcount = nullptr;
+    unsigned long long *d_hyd_rowstart = nullptr, *d_hyd_counters = nullptr, *h_hyd_counters = nullptr; // [0] draws consumed, [1 + k] first draw of event k
+    int hyd_counters_cap = 0;
+    uint32_t *d_hyd_stream = nullptr, *d_hyd_window = nullptr, *h_hyd_window = nullptr;
+    unsigned long long hyd_stream_cap = 0;
+    void *d_lfib_table = nullptr;
+    int *d_hyd_status = nullptr, *h_hyd_status = nullptr;
+    uint8_t *h_hyd_slots = nullptr;
+    size_t hyd_slots_cap = 0;
+    cudaEvent_t hyd_staged = nullptr, hyd_done = nullptr;
+    int hyd_events = 0;      // events of the plan whose result is pending / was collected last
+    bool hyd_pending = false, hyd_keep = false;
     // sparse insertions (maddy_insert_dimers): pinned + device record buffers {index, then float4 xyzz}, reuse event
     char *h_ins = nullptr, *d_ins = nullptr;
     size_t ins_capacity = 0;
@@ -489,12 +510,19 @@ extern "C" int maddy_destroy(maddy_handle *h)
         if (q) cudaFreeHost(q);
     if (h->snap_done) cudaEventDestroy(h->snap_done);
     if (h->snap_staged) cudaEventDestroy(h->snap_staged);
+    for (void *q : {(void *)h->d_cls_pair[0], (void *)h->d_cls_pair[1], (void *)h->d_snap_gtp, (void *)h->d_hyd_gt, (void *)h->d_hyd_st, (void *)h->d_hyd_rowcount,
+                    (void *)h->d_hyd_rowstart, (void *)h->d_hyd_counters, (void *)h->d_hyd_stream, (void *)h->d_hyd_window, h->d_lfib_table,
+                    (void *)h->d_hyd_status})
+        if (q) cudaFree(q);
+    for (void *q : {(void *)h->h_snap_gtp, (void *)h->h_hyd_counters, (void *)h->h_hyd_window, (void *)h->h_hyd_status, (void *)h->h_hyd_slots})
+        if (q) cudaFreeHost(q);
+    if (h->hyd_staged) cudaEventDestroy(h->hyd_staged);
+    if (h->hyd_done) cudaEventDestroy(h->hyd_done);
     if (h->cls_staged) cudaEventDestroy(h->cls_staged);
     if (h->cls_done) cudaEventDestroy(h->cls_done);
     if (h->ins_done) cudaEventDestroy(h->ins_done);
     if (h->d_ins) cudaFree(h->d_ins);
     if (h->h_ins) cudaFreeHost(h->h_ins);
-    if (h->d_cls_flags) cudaFree(h->d_cls_flags);
     if (h->d_cls_count) cudaFree(h->d_cls_count);
     if (h->h_cls_flags) cudaFreeHost(h->h_cls_flags);
     if (h->h_cls_count) cudaFreeHost(h->h_cls_count);
@@ -515,6 +543,7 @@ extern "C" int maddy_destroy(maddy_handle *h)
 
 extern "C" int maddy_upload_list(maddy_handle *h, int kind, const int *counts, const int *entries);
 static bool make_ontub_rule(OnTubRule &r);
+static int cls_pair_ready(maddy_handle *h);
 
 extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, const float *coords, void *stream,
                             maddy_handle **out)
@@ -761,6 +790,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         CK(maddy_upload_extra(h, top->extra));
         CK(maddy_upload_gtp(h, top->gtp));
         CK(maddy_upload_on_tubule(h, top->on_tubule_cur));
+        CK(cls_pair_ready(h)); // hydrolysis on the device reads the last two classifications: both start as these flags
         if (a.capLong > 0 && top->longitudinal) CK(maddy_upload_list(h, MADDY_LIST_LONGITUDINAL, top->longitudinal_count, top->longitudinal));
         if (a.capLat > 0 && top->lateral) CK(maddy_upload_list(h, MADDY_LIST_LATERAL, top->lateral_count, top->lateral));
 
@@ -1019,10 +1049,195 @@ static bool make_ontub_rule(OnTubRule &r)
     return true;
 }
 
+// the two on-tubule classification buffers; both start as the flags the handle was created with (called by maddy_create)
+static int cls_pair_ready(maddy_handle *h)
+{
+    if (h->d_cls_pair[0]) return MADDY_OK;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    for (int b = 0; b < 2; b++) {
+        CU(h, cudaMalloc(&h->d_cls_pair[b], n));
+        CU(h, cudaMemcpyAsync(h->d_cls_pair[b], h->a.ontub, n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return MADDY_OK;
+}
+
+// ------------------------------------------------------------------ hydrolysis events of a stride on the device
+static const LfibPoly *lfib_host_table()
+{
+    static LfibPoly table[LFIB_POW2];
+    static std::once_flag once;
+    std::call_once(once, [] { lfib_table(table); });
+    return table;
+}
+extern "C" void maddy_rand_discard(unsigned *window31, unsigned long long n)
+{
+    if (!window31 || n == 0) return;
+    uint32_t out[LFIB_DEG];
+    lfib_window(out, window31, lfib_host_table(), n);
+    memcpy(window31, out, sizeof out);
+}
+static int sched_reserve(maddy_handle *h, size_t bytes);
+
+extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, long long first_event, long long period, int n_events, unsigned flags)
+{
+    if (!h || !window31 || n_events < 1 || period <= 0) return MADDY_EINVAL;
+    if (h->p.n_tr_local != h->p.n_tr || (h->a.N & 1))
+        return fail(h, MADDY_EINVAL, "maddy_hydrolysis_plan needs the whole ensemble on one handle and an even n_tot (draw positions are global)");
+    if (h->hyd_pending) return fail(h, MADDY_EINVAL, "maddy_hydrolysis_plan: the previous plan's result has not been collected");
+    CU(h, cudaSetDevice(h->p.device));
+    const int N = h->a.N, ntr = h->a.ntr, nd = N / 2;
+    const size_t n = (size_t)ntr * N, cells = (size_t)nd * ntr;
+    int rc = cls_pair_ready(h);
+    if (rc) return rc;
+    if (!h->d_hyd_gt) {
+        CU(h, cudaMalloc(&h->d_hyd_gt, cells));
+        CU(h, cudaMalloc(&h->d_hyd_st, cells));
+        CU(h, cudaMalloc(&h->d_hyd_rowcount, (size_t)nd * sizeof(unsigned)));
+        CU(h, cudaMalloc(&h->d_hyd_rowstart, (size_t)nd * sizeof(unsigned long long)));
+        CU(h, cudaMalloc(&h->d_hyd_window, LFIB_DEG * sizeof(uint32_t)));
+        CU(h, cudaMallocHost(&h->h_hyd_window, LFIB_DEG * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->d_lfib_table, sizeof(LfibPoly) * LFIB_POW2));
+        CU(h, cudaMemcpyAsync(h->d_lfib_table, lfib_host_table(), sizeof(LfibPoly) * LFIB_POW2, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMalloc(&h->d_hyd_status, sizeof(int)));
+        CU(h, cudaMallocHost(&h->h_hyd_status, sizeof(int)));
+        CU(h, cudaEventCreateWithFlags(&h->hyd_staged, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->hyd_done, cudaEventDisableTiming));
+        if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    }
+    if (n_events + 1 > h->hyd_counters_cap) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (h->d_hyd_counters) cudaFree(h->d_hyd_counters);
+        if (h->h_hyd_counters) cudaFreeHost(h->h_hyd_counters);
+        h->hyd_counters_cap = n_events + 16;
+        CU(h, cudaMalloc(&h->d_hyd_counters, (size_t)h->hyd_counters_cap * sizeof(unsigned long long)));
+        CU(h, cudaMallocHost(&h->h_hyd_counters, (size_t)h->hyd_counters_cap * sizeof(unsigned long long)));
+    }
+    // worst case: every dimer of every trajectory draws at every event
+    const unsigned long long need = (unsigned long long)n_events * cells;
+    if (need > h->hyd_stream_cap) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (h->d_hyd_stream) cudaFree(h->d_hyd_stream);
+        h->d_hyd_stream = nullptr;
+        h->hyd_stream_cap = 0;
+        cudaError_t e = cudaMalloc(&h->d_hyd_stream, need * sizeof(uint32_t));
+        if (e != cudaSuccess) return fail(h, MADDY_ENOMEM, "%llu bytes for the hydrolysis draws: %s", need * 4ull, cudaGetErrorString(e));
+        h->hyd_stream_cap = need;
+    }
+    rc = sched_reserve(h, n * (size_t)n_events);
+    if (rc) return rc;
+    const int b = h->sched_cur ^ 1; // the buffer the last scheduled run was NOT given (same stream: no reader left behind)
+    if (h->sched_copied[b]) CU(h, cudaStreamWaitEvent(h->stream, h->sched_copied[b], 0));
+    // threshold of updater.cpp:236-237 in this process's own double arithmetic
+    static const unsigned threshold = [] {
+        int v = (int)(0.02 * (double)RAND_MAX) + 2;
+        while (!((double)v / (double)RAND_MAX < 0.02)) v--;
+        return (unsigned)v;
+    }();
+    memcpy(h->h_hyd_window, window31, LFIB_DEG * sizeof(uint32_t));
+    CU(h, cudaMemcpyAsync(h->d_hyd_window, h->h_hyd_window, LFIB_DEG * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->d_hyd_counters, 0, sizeof(unsigned long long), h->stream));
+    CU(h, cudaMemsetAsync(h->d_hyd_status, 0, sizeof(int), h->stream));
+    cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_lfib_table, need, h->d_hyd_stream, h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis stream kernel: %s", cudaGetErrorString(e));
+    HydArgs a;
+    a.gtp = h->a.gtp;
+    a.extra = h->a.extra;
+    a.cur = h->d_cls_pair[h->cls_cur];
+    a.prev = h->d_cls_pair[h->cls_cur ^ 1];
+    a.gt = h->d_hyd_gt;
+    a.st = h->d_hyd_st;
+    a.rowcount = h->d_hyd_rowcount;
+    a.rowstart = h->d_hyd_rowstart;
+    a.cursor = h->d_hyd_counters;
+    a.event_start = h->d_hyd_counters + 1;
+    a.stream = h->d_hyd_stream;
+    a.stream_count = need;
+    a.threshold = threshold;
+    a.status = h->d_hyd_status;
+    a.N = N;
+    a.ntr = ntr;
+    a.nd = nd;
+    e = launch_hyd_plan(a, n_events, h->d_sched_buf[b], h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis plan kernels: %s", cudaGetErrorString(e));
+    h->launches += 2 + 3LL * n_events;
+    h->sched_cur = b;
+    h->d_sched = h->d_sched_buf[b];
+    h->sched_first = first_event;
+    h->sched_period = period;
+    h->sched_slots = n_events;
+    // counters (and, on request, the slots) travel beside the windows queued next
+    CU(h, cudaEventRecord(h->hyd_staged, h->stream));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->hyd_staged, 0));
+    CU(h, cudaMemcpyAsync(h->h_hyd_counters, h->d_hyd_counters, (size_t)(n_events + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaMemcpyAsync(h->h_hyd_status, h->d_hyd_status, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
+    h->hyd_keep = (flags & MADDY_HYD_KEEP_SLOTS) != 0;
+    if (h->hyd_keep) {
+        const size_t bytes = n * (size_t)n_events;
+        if (bytes > h->hyd_slots_cap) {
+            if (h->h_hyd_slots) cudaFreeHost(h->h_hyd_slots);
+            h->h_hyd_slots = nullptr;
+            h->hyd_slots_cap = 0;
+            CU(h, cudaMallocHost(&h->h_hyd_slots, bytes));
+            h->hyd_slots_cap = bytes;
+        }
+        CU(h, cudaMemcpyAsync(h->h_hyd_slots, h->d_sched_buf[b], bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    CU(h, cudaEventRecord(h->hyd_done, h->copy_stream));
+    // a later plan must not rewrite this buffer while the copy stream still reads it
+    if (!h->sched_copied[b]) CU(h, cudaEventCreateWithFlags(&h->sched_copied[b], cudaEventDisableTiming));
+    CU(h, cudaEventRecord(h->sched_copied[b], h->copy_stream));
+    h->hyd_events = n_events;
+    h->hyd_pending = true;
+    return MADDY_OK;
+}
+
+extern "C" int maddy_hydrolysis_result(maddy_handle *h, unsigned long long *draws_total, unsigned long long *event_first_draw, int *gtp_slots)
+{
+    if (!h) return MADDY_EINVAL;
+    if (!h->hyd_pending) return fail(h, MADDY_EINVAL, "maddy_hydrolysis_result without maddy_hydrolysis_plan");
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaEventSynchronize(h->hyd_done));
+    h->hyd_pending = false;
+    if (*h->h_hyd_status) return fail(h, MADDY_EOVERFLOW, "hydrolysis plan: the pre-drawn rand() stream was too short");
+    if (draws_total) *draws_total = h->h_hyd_counters[0];
+    if (event_first_draw) memcpy(event_first_draw, h->h_hyd_counters + 1, (size_t)h->hyd_events * sizeof(unsigned long long));
+    if (gtp_slots) {
+        if (!h->hyd_keep) return fail(h, MADDY_EINVAL, "maddy_hydrolysis_result: the plan was made without MADDY_HYD_KEEP_SLOTS");
+        const size_t bytes = (size_t)h->a.ntr * h->a.N * (size_t)h->hyd_events;
+        const uint8_t *v = h->h_hyd_slots;
+        HOST_PARALLEL_FOR(bytes)
+        for (long long q = 0; q < (long long)bytes; q++) gtp_slots[q] = v[q];
+    }
+    return MADDY_OK;
+}
+
+extern "C" int maddy_apply_scheduled_gtp(maddy_handle *h, long long step)
+{
+    if (!h) return MADDY_EINVAL;
+    if (h->sched_slots <= 0 || step < h->sched_first || (step - h->sched_first) % h->sched_period != 0) return MADDY_OK;
+    const long long slot = (step - h->sched_first) / h->sched_period;
+    if (slot >= h->sched_slots) return MADDY_OK;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    CU(h, cudaMemcpyAsync(h->a.gtp, h->d_sched + (size_t)slot * n, n, cudaMemcpyDeviceToDevice, h->stream));
+    return MADDY_OK;
+}
+
+extern "C" int maddy_snapshot_gtp(maddy_handle *h, int *gtp)
+{
+    if (!h || !gtp) return MADDY_EINVAL;
+    if (!(h->cls_what & MADDY_SNAP_GTP)) return fail(h, MADDY_EINVAL, "maddy_snapshot_gtp: the last collected snapshot did not carry the GTP flags");
+    const size_t n = (size_t)h->a.ntr * h->a.N;
+    const uint8_t *v = h->h_snap_gtp;
+    HOST_PARALLEL_FOR(n)
+    for (size_t q = 0; q < n; q++) gtp[q] = v[q];
+    return MADDY_OK;
+}
+
 // ------------------------------------------------------------------ asynchronous stride snapshot
 extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
 {
-    if (!h || !(what & (MADDY_SNAP_COORDS | MADDY_SNAP_FORCES | MADDY_SNAP_ENERGIES | MADDY_SNAP_ONTUBULE))) return MADDY_EINVAL;
+    if (!h || !(what & (MADDY_SNAP_COORDS | MADDY_SNAP_FORCES | MADDY_SNAP_ENERGIES | MADDY_SNAP_ONTUBULE | MADDY_SNAP_GTP))) return MADDY_EINVAL;
     if (h->snap_what) return fail(h, MADDY_EINVAL, "maddy_snapshot_begin: the previous snapshot has not been collected");
     if ((what & MADDY_SNAP_ONTUBULE_APPLY) && !(what & MADDY_SNAP_ONTUBULE))
         return fail(h, MADDY_EINVAL, "maddy_snapshot_begin: MADDY_SNAP_ONTUBULE_APPLY needs MADDY_SNAP_ONTUBULE");
@@ -1066,8 +1281,7 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
         // the previous stride, as in the reference: compute_cuda.cu:1165 precedes :1186-1190).  The counts travel first, on
         // their own event, so a caller that needs them before it may queue the next window waits microseconds, not for the
         // coordinates.
-        if (!h->d_cls_flags) {
-            CU(h, cudaMalloc(&h->d_cls_flags, n));
+        if (!h->d_cls_count) {
             CU(h, cudaMalloc(&h->d_cls_count, ((size_t)h->a.ntr + 1) * sizeof(int)));
             CU(h, cudaMallocHost(&h->h_cls_flags, n));
             CU(h, cudaMallocHost(&h->h_cls_count, ((size_t)h->a.ntr + 1) * sizeof(int)));
@@ -1075,7 +1289,10 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
             CU(h, cudaEventCreateWithFlags(&h->cls_done, cudaEventDisableTiming));
         }
         CU(h, cudaMemsetAsync(h->d_cls_count + h->a.ntr, 0, sizeof(int), h->stream));
-        cudaError_t e = launch_ontubule(h->a.pos, h->a.ang, h->a.ntr, h->a.N, h->ontub_rule, h->d_cls_flags, h->a.ontub,
+        int rcp = cls_pair_ready(h);
+        if (rcp) return rcp;
+        h->cls_cur ^= 1; // the older of the two classifications is overwritten and becomes the current one
+        cudaError_t e = launch_ontubule(h->a.pos, h->a.ang, h->a.ntr, h->a.N, h->ontub_rule, h->d_cls_pair[h->cls_cur], h->a.ontub,
                                         (what & MADDY_SNAP_ONTUBULE_APPLY) ? 1 : 0, h->d_cls_count, h->d_cls_count + h->a.ntr, h->stream);
         if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "ontubule kernel launch: %s", cudaGetErrorString(e));
         h->launches++;
@@ -1102,6 +1319,13 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
         if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "snapshot kernel launch: %s", cudaGetErrorString(e));
         h->launches++;
     }
+    if (what & MADDY_SNAP_GTP) {
+        if (!h->d_snap_gtp) {
+            CU(h, cudaMalloc(&h->d_snap_gtp, n));
+            CU(h, cudaMallocHost(&h->h_snap_gtp, n));
+        }
+        CU(h, cudaMemcpyAsync(h->d_snap_gtp, h->a.gtp, n, cudaMemcpyDeviceToDevice, h->stream)); // the next window may rewrite a.gtp
+    }
     if (h->gpu_prof) cudaEventRecord(c1, h->stream);
     CU(h, cudaMemcpyAsync(h->d_snap_status, h->a.status, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
     CU(h, cudaEventRecord(h->snap_staged, h->stream));
@@ -1110,7 +1334,8 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
     if (what & MADDY_SNAP_FORCES) CU(h, cudaMemcpyAsync(h->snap_f, h->d_snap_f, aos_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
     if (what & MADDY_SNAP_ENERGIES)
         CU(h, cudaMemcpyAsync(h->snap_en, h->d_snap_en, (size_t)h->a.ntr * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
-    if (what & MADDY_SNAP_ONTUBULE) CU(h, cudaMemcpyAsync(h->h_cls_flags, h->d_cls_flags, n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (what & MADDY_SNAP_ONTUBULE) CU(h, cudaMemcpyAsync(h->h_cls_flags, h->d_cls_pair[h->cls_cur], n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (what & MADDY_SNAP_GTP) CU(h, cudaMemcpyAsync(h->h_snap_gtp, h->d_snap_gtp, n, cudaMemcpyDeviceToHost, h->copy_stream));
     CU(h, cudaMemcpyAsync(h->h_status + 1, h->d_snap_status, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
     CU(h, cudaEventRecord(h->snap_done, h->copy_stream));
     if (h->gpu_prof) {
@@ -1148,7 +1373,7 @@ extern "C" int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *fo
     if (!h->snap_what) return fail(h, MADDY_EINVAL, "maddy_snapshot_end without maddy_snapshot_begin");
     const unsigned what = h->snap_what;
     h->snap_what = 0;
-    h->cls_what = what & (MADDY_SNAP_ONTUBULE | MADDY_SNAP_ONTUBULE_APPLY);
+    h->cls_what = what & (MADDY_SNAP_ONTUBULE | MADDY_SNAP_ONTUBULE_APPLY | MADDY_SNAP_GTP);
     CU(h, cudaSetDevice(h->p.device));
     CU(h, cudaEventSynchronize(h->snap_done));
     // the status word copied with the snapshot covers everything queued before it; later launches may already be
@@ -1276,13 +1501,10 @@ static int stage_submit(maddy_handle *h, uint8_t *dst, int slot)
     CU(h, cudaEventRecord(h->stage_done[slot], h->stream));
     return MADDY_OK;
 }
-extern "C" int maddy_schedule_gtp(maddy_handle *h, long long first_event, long long period, int n_slots, const int *gtp_slots)
+// the two device / pinned schedule buffers hold at least `bytes` (a resize waits for everything in flight)
+static int sched_reserve(maddy_handle *h, size_t bytes)
 {
-    if (!h || n_slots < 0 || (n_slots > 0 && (!gtp_slots || period <= 0))) return MADDY_EINVAL;
-    h->sched_slots = 0;
-    if (n_slots == 0) return MADDY_OK;
-    CU(h, cudaSetDevice(h->p.device));
-    const size_t n = (size_t)h->a.ntr * h->a.N, bytes = n * (size_t)n_slots;
+    const size_t n = (size_t)h->a.ntr * h->a.N;
     if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (bytes > h->sched_capacity) {
         CU(h, cudaStreamSynchronize(h->stream)); // a running window may still read the old buffers
@@ -1302,6 +1524,20 @@ extern "C" int maddy_schedule_gtp(maddy_handle *h, long long first_event, long l
             if (!h->sched_copied[b]) CU(h, cudaEventCreateWithFlags(&h->sched_copied[b], cudaEventDisableTiming));
         }
         h->sched_capacity = cap;
+    }
+    return MADDY_OK;
+}
+extern "C" int maddy_schedule_gtp(maddy_handle *h, long long first_event, long long period, int n_slots, const int *gtp_slots)
+{
+    if (!h || n_slots < 0 || (n_slots > 0 && (!gtp_slots || period <= 0))) return MADDY_EINVAL;
+    h->sched_slots = 0;
+    if (n_slots == 0) return MADDY_OK;
+    CU(h, cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->a.ntr * h->a.N, bytes = n * (size_t)n_slots;
+    if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    {
+        int rcr = sched_reserve(h, bytes);
+        if (rcr) return rcr;
     }
     // Fill the buffer the last scheduled run was NOT given (that run may still be executing).  The copy waits for the
     // last run that did read this buffer (sched_reader), the next run for the copy (sched_copied).

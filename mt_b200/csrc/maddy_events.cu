@@ -1,0 +1,174 @@
+/*
+ * maddy_events.cu — hydrolyse() (updater.cpp:229-257) on the device, for ALL events of one output stride at once.
+ *
+ * What the reference does at every hydrostep: a host loop, dimer-outer / trajectory-inner, that draws one libc rand()
+ * per eligible dimer (GTP, not in the reserve, on the tubule now and at the previous stride), hydrolyses it with
+ * probability 0.02, then a second loop that returns GDP dimers off the tubule (now and before) to GTP; followed by an
+ * H2D copy of the whole gtp array (compute_cuda.cu:1153-1160).
+ *
+ * Here: the eligibility of a dimer changes inside a stride only through hydrolysis itself (the on-tubule flags and the
+ * reserve flags change at stride steps), so right after the stride block the device evaluates every event up to the
+ * next stride step in one go and leaves the results where the fused loop already looks for them - the GTP schedule
+ * (KArgs::gtp_sched, one slot per event).  The position of a dimer's draw in the rand() stream is a prefix sum over the
+ * eligibility mask in the reference's order (rows = dimers, columns = trajectories); the stream itself is produced on
+ * the device from the host generator's 31-word window by polynomial jump-ahead (maddy_lfib.h).  The host is left with
+ * advancing its generator by the number of draws the device reports - it issues no per-event work at all, and a fused
+ * window can span the whole stride.  Bit-identical to hydrolyse(): same draws, same order, same threshold.
+ */
+#include "maddy_kernels.cuh"
+#include "maddy_lfib.h"
+
+namespace maddy {
+
+#define HYD_ROUNDS 32                       // rounds of 31 draws per thread of the stream kernel
+#define HYD_PER_THREAD (31 * HYD_ROUNDS)    // 992
+
+// out[v] = draw v of the plan = x[31 + v] >> 1, v < count; W[k] = x[k] is the generator's window (oldest word first)
+__global__ void __launch_bounds__(64) hyd_stream_kernel(const uint32_t *__restrict__ W, const LfibPoly *__restrict__ table, unsigned long long count,
+                                                        uint32_t *__restrict__ out)
+{
+    const unsigned long long first = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * HYD_PER_THREAD;
+    if (first >= count) return;
+    uint32_t base[LFIB_DEG], r[LFIB_DEG];
+    for (int k = 0; k < LFIB_DEG; k++) base[k] = W[k];
+    lfib_window(r, base, table, first); // r[j] = x[first + j]: the 31 words in front of draw `first`
+    for (int round = 0; round < HYD_ROUNDS; round++) {
+        const unsigned long long v0 = first + (unsigned long long)round * 31;
+        if (v0 >= count) break;
+#pragma unroll
+        for (int j = 0; j < 31; j++) {
+            r[j] = r[j] + r[(j + 28) % 31]; // x[n] = x[n-31] + x[n-3]; (j + 28) % 31 < j holds the value made three steps ago
+            if (v0 + j < count) out[v0 + j] = r[j] >> 1;
+        }
+    }
+}
+
+// transposed working set of a plan: rows = dimers, columns = trajectories (the reference's loop order)
+//   gt[d][tr]  GTP state of the dimer's first monomer as the events go by (1 / 0 / other)
+//   st[d][tr]  bit 0: can hydrolyse (not reserve, on the tubule now and before)   bit 1: returns to GTP (not reserve, off both)
+__global__ void __launch_bounds__(256) hyd_prepare_kernel(HydArgs h)
+{
+    const size_t cells = (size_t)h.nd * h.ntr;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)(c / h.ntr), tr = (int)(c % h.ntr);
+        const size_t q = (size_t)tr * h.N + 2 * d;
+        const bool ex = h.extra[q] != 0, cur = h.cur[q] != 0, prev = h.prev[q] != 0;
+        h.gt[c] = h.gtp[q];
+        h.st[c] = (uint8_t)((!ex && cur && prev ? 1 : 0) | (!ex && !cur && !prev ? 2 : 0));
+    }
+}
+
+// draws of one event per dimer row
+__global__ void __launch_bounds__(128) hyd_count_kernel(HydArgs h)
+{
+    __shared__ unsigned wsum[4];
+    const int d = blockIdx.x;
+    const uint8_t *gt = h.gt + (size_t)d * h.ntr, *st = h.st + (size_t)d * h.ntr;
+    unsigned c = 0;
+    for (int tr = threadIdx.x; tr < h.ntr; tr += blockDim.x) c += gt[tr] == 1 && (st[tr] & 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) h.rowcount[d] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+}
+
+// first draw of every row = draws consumed so far + exclusive prefix of the row counts; one CTA
+__global__ void __launch_bounds__(1024) hyd_scan_kernel(HydArgs h, int event)
+{
+    __shared__ unsigned long long wsum[32];
+    const int per = (h.nd + 1023) / 1024;
+    const int d0 = threadIdx.x * per, d1 = min(h.nd, d0 + per);
+    unsigned long long s = 0;
+    for (int d = d0; d < d1; d++) s += h.rowcount[d];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = wsum[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        wsum[lane] = winc - w;
+    }
+    __syncthreads();
+    const unsigned long long base = h.cursor[0];
+    unsigned long long run = base + wsum[warp] + inc - s;
+    for (int d = d0; d < d1; d++) {
+        h.rowstart[d] = run;
+        run += h.rowcount[d];
+    }
+    __syncthreads(); // every thread has read the cursor
+    if (threadIdx.x == 1023) {
+        h.event_start[event] = base;
+        h.cursor[0] = run; // the last thread's running sum is the total
+    }
+}
+
+// one event: a warp per dimer row walks the trajectories in order (ballot prefix = position in the stream)
+__global__ void __launch_bounds__(128) hyd_apply_kernel(HydArgs h, uint8_t *__restrict__ slot)
+{
+    const int lane = threadIdx.x & 31;
+    const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (d >= h.nd) return;
+    uint8_t *gt = h.gt + (size_t)d * h.ntr;
+    const uint8_t *st = h.st + (size_t)d * h.ntr;
+    unsigned long long pos = h.rowstart[d];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int t0 = 0; t0 < h.ntr; t0 += 32) {
+        const int tr = t0 + lane;
+        const bool in = tr < h.ntr;
+        uint8_t g = in ? gt[tr] : (uint8_t)2;
+        const uint8_t s = in ? st[tr] : (uint8_t)0;
+        const bool elig = g == 1 && (s & 1);
+        const unsigned bl = __ballot_sync(0xffffffffu, elig);
+        if (elig) {
+            const unsigned long long v = pos + __popc(bl & lt);
+            if (v < h.stream_count) {
+                if (h.stream[v] <= h.threshold) g = 0; // rand() / (double)RAND_MAX < 0.02  (updater.cpp:236-237)
+            } else {
+                atomicOr(h.status, 1);
+            }
+        }
+        pos += __popc(bl);
+        if (g == 0 && (s & 2)) g = 1; // off the tubule now and before: back to GTP (updater.cpp:246-254), no draw
+        if (in) {
+            gt[tr] = g;
+            // both monomers of the dimer (2 d is even and N is even: the pair is 2-byte aligned)
+            *reinterpret_cast<uint16_t *>(slot + (size_t)tr * h.N + 2 * d) = (uint16_t)(g | (g << 8));
+        }
+    }
+}
+
+cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, cudaStream_t st)
+{
+    const unsigned long long threads = (count + HYD_PER_THREAD - 1) / HYD_PER_THREAD;
+    if (threads == 0) return cudaSuccess;
+    hyd_stream_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(W, reinterpret_cast<const LfibPoly *>(table), count, out);
+    return cudaGetLastError();
+}
+
+// all events of a plan, slot k of `slots` ([n_events][ntr * N] bytes) = GTP state after event k
+cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, cudaStream_t st)
+{
+    const size_t cells = (size_t)h.nd * h.ntr;
+    int pb = (int)((cells + 255) / 256);
+    if (pb > 148 * 8) pb = 148 * 8;
+    hyd_prepare_kernel<<<pb, 256, 0, st>>>(h);
+    for (int k = 0; k < n_events; k++) {
+        hyd_count_kernel<<<h.nd, 128, 0, st>>>(h);
+        hyd_scan_kernel<<<1, 1024, 0, st>>>(h, k);
+        hyd_apply_kernel<<<(h.nd + 3) / 4, 128, 0, st>>>(h, slots + (size_t)k * h.ntr * h.N);
+    }
+    return cudaGetLastError();
+}
+
+} // namespace maddy

@@ -143,6 +143,21 @@ struct OnTubRule {
     float edge[ONTUB_EDGES]; // on iff |theta| in [0, e0) U (e1, e2) U (e3, e4) U (e5, e6)
 };
 
+// hydrolysis events of one stride on the device (maddy_events.cu)
+struct HydArgs {
+    const uint8_t *gtp, *extra, *cur, *prev; // [ntr * N]: GTP state at the stride, reserve flags, on-tubule flags now / previous stride
+    uint8_t *gt, *st;                        // [nd][ntr] transposed working set (see hyd_prepare_kernel)
+    unsigned *rowcount;                      // [nd] draws of the current event per dimer row
+    unsigned long long *rowstart;            // [nd] index of each row's first draw in the plan's stream
+    unsigned long long *cursor;              // [1] draws consumed so far by the plan
+    unsigned long long *event_start;         // [n_events] first draw of every event
+    const uint32_t *stream;                  // the plan's draws (rand() values), stream_count of them
+    unsigned long long stream_count;
+    unsigned threshold;                      // largest rand() value v with v / (double)RAND_MAX < 0.02
+    int *status;                             // bit 0: the stream was too short (cannot happen: sized for the worst case)
+    int N, ntr, nd;
+};
+
 // in-situ analysis (maddy_analysis.cu)
 struct AnalysisArgs {
     const float4 *pos, *ang;   // current state

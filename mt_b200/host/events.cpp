@@ -508,6 +508,53 @@ void compute(System &s, bool fused, ComputeStats *stats)
     const bool feedback = flags_matter || (hp.is_const_conc && hp.tub_length); // host results of a stride change the next forces
     const bool overlap_stride = fused && !par.tea_on && !hp.out_force && (!feedback || dev_classify) && !getenv("MADDY_NO_OVERLAP");
     const bool counts_first = overlap_stride && dev_classify && feedback; // the next window waits for the counts (not the coordinates)
+    // hydrolyse() itself runs on the device when ONE handle holds the ensemble (draw positions are global): right after a
+    // stride block every event up to the next stride step is evaluated in one go (maddy_hydrolysis_plan) from the 31 words
+    // of the host generator and left as the GTP schedule of the fused loop - a window then spans the whole stride and the
+    // host only advances its generator by the number of draws the device reports.  May be switched off mid-run (a
+    // classification the device could not decide): the host then carries on from the synchronised state.
+    bool hyd_dev = overlap_stride && dev_classify && hp.hydrolysis && hp.hydrostep > 0 && G == 1 && N % 2 == 0 && !getenv("MADDY_HOST_HYDROLYSIS");
+    bool plan_pending = false;           // a plan whose draw count has not been folded into s.rng yet
+    long long plan_first = 0;            // step of its first event
+    int plan_events = 0;
+    auto plan_covers = [&](long long at) {
+        return plan_events > 0 && at >= plan_first && (at - plan_first) % hp.hydrostep == 0 && (at - plan_first) / hp.hydrostep < plan_events;
+    };
+    // result of the pending plan: the host generator jumps over its draws, and the events' messages are printed in the
+    // reference's order (the schedule holds the GTP state after every event; s.gtp the state the plan started from)
+    auto collect_plan = [&] {
+        if (!plan_pending) return;
+        plan_pending = false;
+        Shard &d = sh.v[0];
+        unsigned long long total = 0;
+        std::vector<int> slots;
+        if (!s.quiet) slots.resize((size_t)plan_events * n);
+        ck(maddy_hydrolysis_result(d.h, &total, nullptr, s.quiet ? nullptr : slots.data()), d.h, "maddy_hydrolysis_result");
+        s.rng.discard(total);
+        st.d2h_bytes += 8.0 * (plan_events + 1) + (s.quiet ? 0.0 : (double)plan_events * n);
+        if (s.quiet) return;
+        for (int k = 0; k < plan_events; k++) {
+            const int *before = k == 0 ? s.gtp.data() : &slots[(size_t)(k - 1) * n], *after = &slots[(size_t)k * n];
+            for (int dm = 0; dm < N / 2; dm++)
+                for (int tr = 0; tr < Ntr; tr++) {
+                    const size_t q = 2 * dm + (size_t)tr * N;
+                    if (before[q] == 1 && after[q] == 0) printf("*** Hydrolysis occured to dimer # %d trajectory #%d ***\n", dm, tr);
+                }
+            for (int dm = 0; dm < N / 2; dm++)
+                for (int tr = 0; tr < Ntr; tr++) {
+                    const size_t q = 2 * dm + (size_t)tr * N;
+                    if (before[q] == 0 && after[q] == 1) printf("*** Transition to GTP occured to dimer # %d trajectory #%d ***\n", dm, tr);
+                }
+        }
+    };
+    // the GTP flags as they stand on the device (hyd_dev mode keeps s.gtp current only at strides)
+    auto download_gtp = [&] {
+        Shard &d = sh.v[0];
+        ck(maddy_snapshot_begin(d.h, MADDY_SNAP_GTP), d.h, "maddy_snapshot_begin");
+        ck(maddy_snapshot_end(d.h, nullptr, nullptr, nullptr), d.h, "maddy_snapshot_end");
+        ck(maddy_snapshot_gtp(d.h, s.gtp.data()), d.h, "maddy_snapshot_gtp");
+        st.d2h_bytes += (double)n;
+    };
     int pending_output = 0; // an overlapped stride whose update() is still to be written
     long long pending_step = 0;
     std::string pending_log;
@@ -520,6 +567,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
     };
     long long step = 0;
     long long hydrolysed_for = -1; // event step whose hydrolysis has already been evaluated on the host
+    const bool pending_snapshot_open = false; // (a checkpoint is taken at the top of a step: no snapshot is in flight there)
     // Windows that span several hydrolysis events (overlapped mode only).  Every event of a stride depends on the flags
     // classified at that stride alone, so the events of the NEXT window are drawn (same rand() order) while the GPU runs the
     // current one and handed over as a GTP schedule: window lengths grow by one event period per window inside a stride
@@ -540,6 +588,17 @@ void compute(System &s, bool fused, ComputeStats *stats)
     auto write_checkpoint = [&](long long at) {
         if (!sched_gtp.empty()) die("checkpoint at step %lld with a pending GTP schedule (checkpoint_freq must be a multiple of stride)", at);
         if (pending_output) flush_pending();
+        if (hyd_dev) {
+            // the device has evaluated the events up to and including `at` already: fold them in (generator, messages) and
+            // record `at` as done, so that a resumed run continues exactly where the uninterrupted one does
+            if (pending_snapshot_open) die("checkpoint at step %lld with a snapshot in flight", at);
+            collect_plan();
+            if (plan_covers(at)) {
+                ck(maddy_apply_scheduled_gtp(sh.v[0].h, at), sh.v[0].h, "maddy_apply_scheduled_gtp");
+                hydrolysed_for = at;
+            }
+            download_gtp();
+        }
         CheckpointState out;
         out.step = at;
         out.hydrolysed_for = hydrolysed_for;
@@ -644,7 +703,12 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.begin();
         // ---- hydrolysis (compute_cuda.cu:1153-1160)
         long long scheduled_end = -1;
-        if (hp.hydrolysis && step % hp.hydrostep == 0 && step != 0) {
+        if (hyd_dev && hp.hydrolysis && step % hp.hydrostep == 0 && step != 0 && plan_covers(step)) {
+            // evaluated on the device at the last stride; inside a window the fused loop applies the slot itself, at a
+            // stride step it has to be current before the stride block evaluates the energies
+            if (stride_now) ck(maddy_apply_scheduled_gtp(sh.v[0].h, step), sh.v[0].h, "maddy_apply_scheduled_gtp");
+            hydrolysed_for = step;
+        } else if (hp.hydrolysis && step % hp.hydrostep == 0 && step != 0) {
             if (!sched_gtp.empty() && sched_first == step) {
                 // the events of this window were drawn beside the previous one: slot k becomes current at step + k periods
                 const int slots = (int)sched_gtp.size();
@@ -706,14 +770,23 @@ void compute(System &s, bool fused, ComputeStats *stats)
             });
             if (hp.out_energy) ens_end(step);
         };
+        const bool classify0 = overlapped && hyd_dev && step == 0; // the device needs the step-0 classification too (hydrolysis flags only)
         if (overlapped) {
             // The read-back is only QUEUED here; it is collected after the next window has been launched.
+            if (hyd_dev) collect_plan(); // the generator passes the events of the last stride BEFORE this stride's insertion draws
             const unsigned what = MADDY_SNAP_COORDS | (hp.out_energy ? MADDY_SNAP_ENERGIES : 0u) | (fused_stride_energy ? MADDY_SNAP_REBUILD : 0u) |
-                                  (classify ? MADDY_SNAP_ONTUBULE | (par.barrier ? MADDY_SNAP_ONTUBULE_APPLY : 0u) : 0u);
+                                  (classify ? MADDY_SNAP_ONTUBULE | (par.barrier ? MADDY_SNAP_ONTUBULE_APPLY : 0u) : 0u) |
+                                  (classify0 ? MADDY_SNAP_ONTUBULE : 0u) | (hyd_dev ? MADDY_SNAP_GTP : 0u);
             for_each([&](Shard &d) { ck(maddy_snapshot_begin(d.h, what), d.h, "maddy_snapshot_begin"); });
             if (hp.out_energy) ens_begin();
-            st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0) + (classify ? (double)n + 4.0 * Ntr : 0.0);
-            if (classify && counts_first) {
+            st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0) + (classify || classify0 ? (double)n + 4.0 * Ntr : 0.0) +
+                            (hyd_dev ? (double)n : 0.0);
+            if (classify0) { // nothing of it is used by the host (step 0: mt_length() after update(), host flags only): just make sure it was decided
+                int u = 0;
+                ck(maddy_snapshot_tubule_lengths(sh.v[0].h, nullptr, &u), sh.v[0].h, "maddy_snapshot_tubule_lengths");
+                if (u) hyd_dev = false; // s.gtp and the generator are still the host's own
+            }
+            if (classify && (counts_first || hyd_dev)) {
                 // What the host derives from this stride feeds back into the next forces (non-zero barrier: the flags, already
                 // applied on the device; constant concentration: the insertions).  Only the Ntr counts are waited for.
                 std::vector<int> counts(Ntr);
@@ -727,8 +800,13 @@ void compute(System &s, bool fused, ComputeStats *stats)
                 if (undecided) { // some |theta| outside the exact rule's range: this stride takes the reference's serial block
                     collect();
                     collected = true;
+                    if (hyd_dev) { // ... and hydrolysis returns to the host for the rest of the run, from the synchronised state
+                        ck(maddy_snapshot_gtp(sh.v[0].h, s.gtp.data()), sh.v[0].h, "maddy_snapshot_gtp");
+                        hyd_dev = false;
+                        plan_events = 0;
+                    }
                     deferred_output = host_events();
-                } else {
+                } else if (counts_first) {
                     mt_len_prev = mt_len;
                     mt_len = counts;
                     mt_length_output(s, step, mt_len);
@@ -749,6 +827,22 @@ void compute(System &s, bool fused, ComputeStats *stats)
                             st.h2d_bytes += (double)inserted.size() * 20;
                         }
                     }
+                }
+            }
+            if (hyd_dev) {
+                // every hydrolysis event up to (and including) the next stride step, on the device, from the 31 words of
+                // the host generator as they stand after this stride's insertion draws
+                const long long h = hp.hydrostep;
+                const long long first = (step / h + 1) * h, last = std::min((step / hp.stride + 1) * hp.stride, hp.steps - 1);
+                plan_events = first <= last ? (int)((last - first) / h + 1) : 0;
+                plan_first = first;
+                if (plan_events > 0) {
+                    uint32_t w[31];
+                    s.rng.window(w);
+                    ck(maddy_hydrolysis_plan(sh.v[0].h, w, first, h, plan_events, s.quiet ? 0u : MADDY_HYD_KEEP_SLOTS), sh.v[0].h, "maddy_hydrolysis_plan");
+                    plan_pending = true;
+                    st.h2d_bytes += 124.0;
+                    mark("hydrolysis plan queued", step);
                 }
             }
         } else if (stride_now) {
@@ -780,7 +874,9 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // One window per hydrolysis period: hydrolyse() for the NEXT event is evaluated on the host while the GPU runs
         // the current window (see below), so the events cost no GPU idle time.  (maddy_schedule_gtp can fold several
         // events into one launch, but their evaluation would then sit between two windows instead of beside one.)
-        if (hydro) next = std::min(next, scheduled_end > step ? scheduled_end : (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
+        // (events evaluated on the device are applied inside the window: it runs to the next stride step)
+        if (hydro && !(hyd_dev && plan_covers((step / hp.hydrostep + 1) * (long long)hp.hydrostep)))
+            next = std::min(next, scheduled_end > step ? scheduled_end : (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
         const long long count = next - step;
         if (stepwise) {
             for (long long q = step; q < next; q++) {
@@ -814,6 +910,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.begin();
         if (overlapped && !collected) {
             collect();
+            if (hyd_dev) ck(maddy_snapshot_gtp(sh.v[0].h, s.gtp.data()), sh.v[0].h, "maddy_snapshot_gtp"); // state after the event of this step, if any
             prof.end("stride collect (wait + transpose)");
             mark("snapshot collected", step);
             prof.begin();
@@ -856,7 +953,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.end("stride collect");
         prof.begin();
         if (deferred_output) {
-            if (overlapped && deferred_output == 1) {
+            if (overlapped && deferred_output == 1 && !hyd_dev) {
                 // The next hydrolysis event only needs the flags just classified; evaluate it and queue its window
                 // BEFORE the stride's own output is formatted.  Messages are held back so stdout keeps the reference's
                 // order, and the GTP state the output refers to is kept aside.
@@ -871,7 +968,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.end("stride output");
         prof.begin();
         // overlap with the asynchronous window: evaluate the hydrolysis event AT the window end on the host now
-        if (hydro && next < hp.steps && next % hp.hydrostep == 0 && next != 0) {
+        if (hydro && next < hp.steps && next % hp.hydrostep == 0 && next != 0 && !(hyd_dev && plan_covers(next))) {
             if (pending_output) s.event_log = &pending_log;
             hydrolyse(s);
             hydrolysed_for = next;
@@ -902,6 +999,10 @@ void compute(System &s, bool fused, ComputeStats *stats)
         st.steps += count;
     }
     if (pending_output) flush_pending();
+    if (hyd_dev) { // the host copies catch up with the device: generator past the last events, their messages, final GTP flags
+        collect_plan();
+        download_gtp();
+    }
     if (!hp.checkpoint.empty() && hp.steps > start_step) write_checkpoint(hp.steps);
     prof.begin();
     if (s.writer) {

@@ -83,6 +83,17 @@ int mt_system_srand(mt_system *s, unsigned seed)
     s->sys.rng.seed(seed);
     return 0;
 }
+int mt_system_rand_window(mt_system *s, unsigned *w31)
+{
+    s->sys.rng.window(w31);
+    return 0;
+}
+int mt_system_rand_discard(mt_system *s, unsigned long long n)
+{
+    s->sys.rng.discard(n);
+    return 0;
+}
+int mt_system_rand_next(mt_system *s) { return s->sys.rng.next(); }
 int mt_system_set_ngpus(mt_system *s, int n)
 {
     s->sys.hp.n_gpus = n;

@@ -179,6 +179,28 @@ class HostRand {
         f_ = nf;
     }
 
+    // The 31 words of the generator, oldest first: the next draw is (w[0] + w[28]) >> 1.  With discard() this is all the
+    // device needs to produce the stream itself (maddy_hydrolysis_plan) and all the host needs to follow it afterwards.
+    void window(uint32_t w[31]) const
+    {
+        for (int i = 0; i < 31; i++) w[i] = (uint32_t)r_[(f_ + i) % 31];
+    }
+    void set_window(const uint32_t w[31])
+    {
+        for (int i = 0; i < 31; i++) r_[i] = (int32_t)w[i];
+        f_ = 0;
+        b_ = 28;
+    }
+    // advance by n draws without making them (polynomial jump-ahead, maddy_rand_discard)
+    void discard(unsigned long long n)
+    {
+        if (n == 0) return;
+        uint32_t w[31];
+        window(w);
+        maddy_rand_discard(w, n);
+        set_window(w);
+    }
+
     // full generator state, for checkpoints: 31 words + the two cursors
     void get_state(int32_t out[33]) const
     {

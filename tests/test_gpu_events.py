@@ -173,3 +173,64 @@ def _rundir_with(rundir, case, ntr, over, conditions):
     from mt_b200 import workspace
     spec = workspace.BASELINE_CONFIGS[case]
     return rundir(case, structure=spec["structure"], runnum=ntr, conditions=conditions, **over)
+
+
+def test_device_hydrolysis_plan_equals_host_hydrolyse(rundir, load_system):
+    """maddy_hydrolysis_plan (all events of a stride on the device, rand() stream produced there by jump-ahead) == hydrolyse()
+    called event by event on the host with the same generator: GTP state after every event, number of draws, next draw."""
+    ntr, n_events = 37, 6
+    s = load_system(rundir("mt120_disassembly", runnum=ntr))
+    N = s.Ntot
+    e = Engine(s)
+    rng = np.random.default_rng(5)
+    c = np.array(s.coords).copy()
+
+    def classify(frac_off):
+        """a classification with ~frac_off of the monomers off the tubule (radius beyond R_MT + R_THRES), device and host"""
+        cc = c.copy()
+        off = rng.random((ntr, N // 2)) < frac_off
+        cc[..., 0] = np.where(off.repeat(2, axis=1), 100.0, cc[..., 0])
+        e.upload_coords(cc)
+        e.snapshot_begin(coords=False, energies=False, on_tubule=True)
+        e.snapshot_end()
+        s.coords[...] = cc
+        s.on_tubule_prev[...] = s.on_tubule_cur
+        s.mt_length(1000)
+
+    s.on_tubule_prev[...] = s.on_tubule_cur  # as the stride block of step 0 does
+    classify(0.2)
+    classify(0.3)
+    gtp0 = (rng.random((ntr, N // 2)) < 0.7).astype(np.int32).repeat(2, axis=1)  # some dimers start as GDP
+    s.gtp[...] = gtp0
+    e.upload_gtp(gtp0)
+    s.srand(4242)
+    w = s.rand_window()
+    e.hydrolysis_plan(w, 1100, 100, n_events, keep_slots=True)
+    total, first, slots = e.hydrolysis_result()
+    draws = 0
+    for k in range(n_events):
+        before = np.array(s.gtp).copy()
+        elig = int(((before[:, ::2] == 1) & (np.array(s.on_tubule_cur)[:, ::2] * np.array(s.on_tubule_prev)[:, ::2] == 1)).sum())
+        assert int(first[k]) == draws
+        s.hydrolyse()
+        draws += elig
+        assert np.array_equal(slots[k], np.array(s.gtp)), k
+    assert total == draws and 0 < (slots[-1] == 0).sum() and (slots[0] != gtp0).any()
+    # the host generator (which made the draws) and a copy that jumps over them agree on what comes next
+    nxt = [s.rand_next() for _ in range(5)]
+    s.srand(4242)
+    s.rand_discard(total)
+    assert [s.rand_next() for _ in range(5)] == nxt
+    # the schedule is what the fused loop sees: a window over the events ends in the last slot's state
+    e.run(1000, 100 * n_events + 50)
+    e.snapshot_begin(coords=False, energies=False, gtp=True)
+    assert np.array_equal(e.snapshot_end()["gtp"], slots[-1])
+    # ... and a slot can be made current ahead of its window (stride block)
+    f = Engine(s)
+    f.upload_gtp(gtp0)
+    f.snapshot_begin(coords=False, energies=False, on_tubule=True)
+    f.snapshot_end()
+    from mt_b200 import MaddyError
+    g = Engine(s, traj_first=0, n_tr_local=ntr - 1)
+    with pytest.raises(MaddyError):
+        g.hydrolysis_plan(w, 1100, 100, 2)  # a shard: draw positions are global

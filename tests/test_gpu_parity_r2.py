@@ -113,8 +113,21 @@ def _compare_dcd(d_ref, d_own, ntr, frames, n, tol_xyz=1e-3, tol_ang=1e-4):
             a = mt_b200.read_dcd(d_own / "dcd" / f"run_{t}{suffix}")
             b = mt_b200.read_dcd(d_ref / "dcd" / f"run_{t}{suffix}")
             assert a.shape == b.shape == (frames, n, 3), (a.shape, b.shape)
-            worst[k] = max(worst[k], float(np.abs(a - b).max()))
-            assert np.abs(a - b).max() < tol, (t, suffix, np.abs(a - b).max())
+            # absolute tolerance, plus float rounding relative to the distance from the origin: a dimer the reference's
+            # change_conc() drops ON another one (same 2-nm grid point, updater.cpp:118-119) is shot out to ~1e8 nm by the
+            # r^-6 repulsion in both executables, where one ulp is 8 nm
+            # (such a dimer and what it hits on its way out leave the 160 x 80 nm cylinder by orders of magnitude; their
+            # trajectories amplify rounding like any collision at r -> 0 and are compared to 1e-3 relative, everything
+            # that stays in the box to the absolute tolerance;
+            # their angles, driven by forces of 1e7 and more, are not compared at all)
+            dist = np.linalg.norm(mt_b200.read_dcd(d_ref / "dcd" / f"run_{t}.dcd"), axis=-1, keepdims=True)
+            flung = np.broadcast_to(dist > 2000.0, a.shape)
+            err = np.where(flung, 0.0, np.abs(a - b))
+            worst[k] = max(worst[k], float(err.max()))
+            assert err.max() < tol, (t, suffix, err.max())
+            assert flung.mean() < 0.05
+            if suffix == ".dcd":
+                assert (np.abs(a - b) <= 1e-3 * np.maximum(dist, 1.0))[flung].all()
     return worst
 
 
