@@ -13,8 +13,8 @@ the 13-protofilament seed (520 monomers) x 256 trajectories PER GPU (weak scalin
 trajectories is sharded in contiguous blocks, every shard uses the GLOBAL RNG stream ids).
 
 value   device-timed whole job, state resident in HBM: K strides issued exactly as the drop-in loop issues them
-        (snapshot_begin[rebuild + energies + coordinates -> pinned host] , fused maddy_run windows of 100/100/200/300/300
-        steps with their GTP uploads / schedules, snapshot_end), ONE CUDA event pair on the launching stream around the K
+        (snapshot_begin[rebuild + energies + on-tubule classification + coordinates -> pinned host], the hydrolysis events of
+        the stride planned on the device, ONE fused maddy_run window per stride, snapshot_end), ONE CUDA event pair on the launching stream around the K
         strides, a 256 MiB L2 flush write between bench steps (inside the pair), max over ranks; repeated R times, median.
 e2e     the drop-in compute() call of the C++ host (mt_system_compute) over K strides with HOST buffers: device
         allocation + upload of coordinates / topology / seeds, hydrolysis draws + uploads, energies + coordinate download
@@ -199,7 +199,14 @@ class StrideIssuer:
         self.tea = bool(system.par.tea_on)
         first = eng.par.traj_first
         self.gtp = np.ascontiguousarray(system.gtp[first:first + eng.ntr], dtype=np.int32)
-        self.windows = self._pattern(single_event)
+        # hydrolysis on the device (the drop-in loop's default when one handle holds the ensemble): the events of a stride
+        # are planned right after its stride block and applied inside ONE window that spans the stride
+        self.system = system
+        self.dev_hyd = bool(self.period) and not self.tea and system.Ntot % 2 == 0 and bool(system.host.tub_length) \
+            and eng.ntr == system.Ntr and not os.environ.get("MADDY_HOST_HYDROLYSIS") and not os.environ.get("MADDY_HOST_EVENTS")
+        self.apply_flags = bool(system.par.barrier)
+        self.plan_pending = False
+        self.windows = [(0, self.stride, self.stride // self.period)] if self.dev_hyd else self._pattern(single_event)
         self.window_events = []  # (start, end) torch events around every maddy_run since the last reset
         self.md_in_windows = 0
 
@@ -225,6 +232,31 @@ class StrideIssuer:
         import numpy as np
         import torch
         eng = self.eng
+        if self.dev_hyd:
+            # exactly the calls of mt::compute() in its device-events mode (mt_b200/host/events.cpp)
+            h = self.period
+            if s0 != 0 and s0 % h == 0:
+                eng.apply_scheduled_gtp(s0)  # the event AT a stride step precedes that stride's energies
+            if self.plan_pending:
+                total, _, _ = eng.hydrolysis_result()
+                self.system.rand_discard(total)
+                self.plan_pending = False
+            eng.snapshot_begin(coords=True, energies=True, rebuild=True, on_tubule=True, apply_on_tubule=(s0 != 0 and self.apply_flags), gtp=True,
+                               guard=True)
+            eng.hydrolysis_plan(self.system.rand_window(), s0 + h, h, self.stride // h)
+            self.plan_pending = True
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(self.stream)
+            eng.run(s0, self.stride, skip_first_rebuild=True)
+            if timed:
+                b.record(self.stream)
+                self.window_events.append((a, b))
+                self.md_in_windows += self.stride
+            eng.snapshot_end()  # the host collects while the window runs
+            if eng.snapshot_tubule_lengths()[1]:
+                raise RuntimeError("bench: the on-tubule classification was undecided (the drop-in loop would redo the stride on the host)")
+            return
         for off, n, n_ev in self.windows:
             if off == 0:
                 if self.period and s0 != 0:

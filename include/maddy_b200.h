@@ -227,6 +227,12 @@ int maddy_rebuild_and_energies(maddy_handle *h, double *out_per_traj, double *ou
 #define MADDY_SNAP_ONTUBULE 16u
 #define MADDY_SNAP_ONTUBULE_APPLY 32u
 #define MADDY_SNAP_GTP 64u /* the GTP flags as of the snapshot (maddy_snapshot_gtp after maddy_snapshot_end) */
+/* With MADDY_SNAP_ONTUBULE: a caller that does not want to wait for the verdict may queue its hydrolysis plan and its next
+ * window right behind the snapshot.  Should the classification turn out undecided (see maddy_snapshot_tubule_lengths),
+ * every maddy_run window and maddy_hydrolysis_plan queued behind it on this handle returns at once WITHOUT touching the
+ * state, until maddy_clear_guard(): the caller then classifies on the host, uploads, and queues the window again.
+ * Nothing ever runs on a guessed flag. */
+#define MADDY_SNAP_ONTUBULE_GUARD 128u
 int maddy_snapshot_begin(maddy_handle *h, unsigned what);
 int maddy_snapshot_end(maddy_handle *h, float *coords_aos7, float *forces_aos7, double *energies_per_traj);
 /* Per-trajectory on-tubule counts (`sum` of updater.cpp:164-170) of the snapshot in flight: blocks only until the
@@ -240,6 +246,7 @@ int maddy_has_exact_on_tubule(const maddy_handle *h);
 /* on_tubule_cur[n_tr_local * n_tot] / mt_len[n_tr_local] of the snapshot collected last by maddy_snapshot_end. */
 int maddy_snapshot_on_tubule(maddy_handle *h, int *on_tubule_cur, int *mt_len);
 int maddy_snapshot_gtp(maddy_handle *h, int *gtp);
+int maddy_clear_guard(maddy_handle *h);
 /* device-resident result of the last maddy_energies call: [n_tr_local][7] doubles */
 void *maddy_energies_device(maddy_handle *h);
 

@@ -289,11 +289,12 @@ class Engine:
         self._ck(capi.lib.maddy_list_stats(self._h, out, int(reset)))
         return {"near_refresh": out[0], "candidate_rescan": out[1], "all_pairs_fallback": out[2], "near_overflow": out[3]}
 
-    def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False, on_tubule=False, apply_on_tubule=False, gtp=False):
+    def snapshot_begin(self, coords=True, forces=False, energies=True, rebuild=False, on_tubule=False, apply_on_tubule=False, gtp=False, guard=False):
         """queue the stride read-back (maddy_snapshot_begin); work queued afterwards overlaps with snapshot_end()"""
         what = (capi.SNAP_COORDS if coords else 0) | (capi.SNAP_FORCES if forces else 0) | (capi.SNAP_ENERGIES if energies else 0) \
             | (capi.SNAP_REBUILD if rebuild else 0) | (capi.SNAP_ONTUBULE if on_tubule or apply_on_tubule else 0) \
-            | (capi.SNAP_ONTUBULE_APPLY if apply_on_tubule else 0) | (capi.SNAP_GTP if gtp else 0)
+            | (capi.SNAP_ONTUBULE_APPLY if apply_on_tubule else 0) | (capi.SNAP_GTP if gtp else 0) \
+            | (capi.SNAP_ONTUBULE_GUARD if guard else 0)
         self._snap = what
         self._ck(capi.lib.maddy_snapshot_begin(self._h, what))
 
@@ -334,6 +335,9 @@ class Engine:
         slots = np.empty((ne, self.ntr, self.N), dtype=np.int32) if keep else None
         self._ck(capi.lib.maddy_hydrolysis_result(self._h, C.byref(total), as_ptr(first, C.c_ulonglong), as_ptr(slots, C.c_int) if keep else None))
         return int(total.value), first, slots
+
+    def clear_guard(self):
+        self._ck(capi.lib.maddy_clear_guard(self._h))
 
     def apply_scheduled_gtp(self, step: int):
         self._ck(capi.lib.maddy_apply_scheduled_gtp(self._h, int(step)))

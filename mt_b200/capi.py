@@ -19,7 +19,7 @@ ZERO_SENTINEL = 999999
 LJ_CAPACITY = 256
 RUN_SKIP_FIRST_REBUILD = 1
 SNAP_COORDS, SNAP_FORCES, SNAP_ENERGIES, SNAP_REBUILD = 1, 2, 4, 8
-SNAP_ONTUBULE, SNAP_ONTUBULE_APPLY, SNAP_GTP = 16, 32, 64
+SNAP_ONTUBULE, SNAP_ONTUBULE_APPLY, SNAP_GTP, SNAP_ONTUBULE_GUARD = 16, 32, 64, 128
 HYD_KEEP_SLOTS = 1
 LIST_LONGITUDINAL, LIST_LATERAL, LIST_LJ = 0, 1, 2
 LOAD_QUIET, LOAD_NO_FILES = 1, 2
@@ -104,7 +104,7 @@ KERNEL_SYMBOLS = [
     "maddy_list_stats", "maddy_analysis_setup", "maddy_analysis_reference", "maddy_analysis_temperature", "maddy_analysis_project",
     "maddy_analysis_protofilaments", "maddy_ensemble_stats_begin", "maddy_ensemble_stats_end", "maddy_download_tea",
     "maddy_snapshot_tubule_lengths", "maddy_snapshot_on_tubule", "maddy_insert_dimers", "maddy_has_exact_on_tubule",
-    "maddy_hydrolysis_plan", "maddy_hydrolysis_result", "maddy_apply_scheduled_gtp", "maddy_rand_discard", "maddy_snapshot_gtp",
+    "maddy_hydrolysis_plan", "maddy_hydrolysis_result", "maddy_apply_scheduled_gtp", "maddy_rand_discard", "maddy_snapshot_gtp", "maddy_clear_guard",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
@@ -161,6 +161,7 @@ _sig(lib.maddy_hydrolysis_result, _i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(
 _sig(lib.maddy_apply_scheduled_gtp, _i, [_vp, _ll])
 _sig(lib.maddy_rand_discard, None, [C.POINTER(C.c_uint), C.c_ulonglong])
 _sig(lib.maddy_snapshot_gtp, _i, [_vp, _pi])
+_sig(lib.maddy_clear_guard, _i, [_vp])
 
 _sig(hostlib.mt_host_last_error, C.c_char_p, [])
 _sig(hostlib.mt_system_load, _i, [C.c_char_p, _i, C.POINTER(C.c_char_p), _u, C.POINTER(_vp)])

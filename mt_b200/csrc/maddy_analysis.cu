@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(AN_THREADS) ensemble_stats_kernel(const double
 // per-trajectory count to out_count.
 __global__ void __launch_bounds__(AN_THREADS) ontubule_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ ang, int N, OnTubRule rule,
                                                               uint8_t *__restrict__ out_flags, uint8_t *__restrict__ live_flags, int apply,
-                                                              int *__restrict__ out_count, int *__restrict__ status)
+                                                              int *__restrict__ out_count, int *__restrict__ status, int *__restrict__ guard)
 {
     __shared__ int wsum[AN_THREADS / 32];
     const int traj = blockIdx.x;
@@ -202,13 +202,16 @@ __global__ void __launch_bounds__(AN_THREADS) ontubule_kernel(const float4 *__re
         for (int w = 0; w < AN_THREADS / 32; w++) t += wsum[w];
         out_count[traj] = t;
     }
-    if (undecided) atomicOr(status, 1); // the word behind the counts: some |theta| was beyond the rule's range
+    if (undecided) {
+        atomicOr(status, 1); // the word behind the counts: some |theta| was beyond the rule's range
+        if (guard) atomicOr(guard, 1); // ... and what the caller queued behind this classification must not run on a guess
+    }
 }
 
 cudaError_t launch_ontubule(const float4 *pos, const float4 *ang, int ntr, int N, const OnTubRule &rule, uint8_t *out_flags, uint8_t *live_flags,
-                            int apply, int *out_count, int *status, cudaStream_t st)
+                            int apply, int *out_count, int *status, int *guard, cudaStream_t st)
 {
-    ontubule_kernel<<<ntr, AN_THREADS, 0, st>>>(pos, ang, N, rule, out_flags, live_flags, apply, out_count, status);
+    ontubule_kernel<<<ntr, AN_THREADS, 0, st>>>(pos, ang, N, rule, out_flags, live_flags, apply, out_count, status, guard);
     return cudaGetLastError();
 }
 

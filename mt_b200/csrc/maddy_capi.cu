@@ -33,7 +33,7 @@ cudaError_t launch_snapshot_kernel(const float4 *pos, const float4 *ang, float *
 cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 int tea_partner_segments(int N);
-cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, cudaStream_t st);
+cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, const int *guard, cudaStream_t st);
 cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, cudaStream_t st);
 cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
@@ -42,7 +42,7 @@ cudaError_t launch_wide_run(const KArgs &k, int buf, int n_steps, int publish_fi
 cudaError_t launch_analysis(int which, const AnalysisArgs &a, cudaStream_t st);
 cudaError_t launch_ensemble_stats(const double *en_traj, int ntr, double *out, cudaStream_t st);
 cudaError_t launch_ontubule(const float4 *pos, const float4 *ang, int ntr, int N, const OnTubRule &rule, uint8_t *out_flags, uint8_t *live_flags,
-                            int apply, int *out_count, int *status, cudaStream_t st);
+                            int apply, int *out_count, int *status, int *guard, cudaStream_t st);
 cudaError_t launch_insert_dimers(float4 *pos, float4 *rpos, uint8_t *extra, int *cand_valid, int N, int n_insert, const int *index,
                                  const float4 *xyzz, cudaStream_t st);
 } // namespace maddy
@@ -729,6 +729,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         pool_req(&a.en_mono, n * 7);
         pool_req(&a.en_traj, (size_t)ntr * 7);
         pool_req(&a.status, 1);
+        pool_req(&a.guard, 1);
         pool_req(&a.stats, 4);
         if (par->tea_on) {
             pool_req(&a.tea_ci, n);
@@ -749,6 +750,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         CUK(cudaMemsetAsync(a.cand_valid, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.lj_stale, 0, (size_t)ntr * sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.status, 0, sizeof(int), h->stream));
+        CUK(cudaMemsetAsync(a.guard, 0, sizeof(int), h->stream));
         CUK(cudaMemsetAsync(a.stats, 0, 4 * sizeof(unsigned long long), h->stream));
         CUK(cudaMemsetAsync(a.fpos, 0, n * sizeof(float4), h->stream));
         CUK(cudaMemsetAsync(a.fang, 0, n * sizeof(float4), h->stream));
@@ -839,6 +841,10 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
         std::call_once(once, [] { rule_ok = make_ontub_rule(rule); });
         h->ontub_rule = rule;
         h->ontub_rule_ok = rule_ok;
+        if (const char *e = getenv("MADDY_ONTUB_AMAX")) { // (the cached rule was made once per process: the hook is per handle)
+            const float v = (float)atof(e);
+            if (v > 0.f && v < h->ontub_rule.a_max) h->ontub_rule.a_max = v;
+        }
     }
     *out = h;
     return MADDY_OK;
@@ -1046,6 +1052,10 @@ static bool make_ontub_rule(OnTubRule &r)
         r.edge[k] = on_at_lo ? flt(hi) : flt(lo);
     }
     r.a_max = (float)(ONTUB_EDGES * pi); // the end of the last branch that was bisected
+    if (const char *e = getenv("MADDY_ONTUB_AMAX")) { // test hook: a small range makes "undecided" (and the host's take-over) easy to reach
+        const float v = (float)atof(e);
+        if (v > 0.f && v < r.a_max) r.a_max = v;
+    }
     return true;
 }
 
@@ -1137,7 +1147,7 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
     CU(h, cudaMemcpyAsync(h->d_hyd_window, h->h_hyd_window, LFIB_DEG * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->d_hyd_counters, 0, sizeof(unsigned long long), h->stream));
     CU(h, cudaMemsetAsync(h->d_hyd_status, 0, sizeof(int), h->stream));
-    cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_lfib_table, need, h->d_hyd_stream, h->stream);
+    cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_lfib_table, need, h->d_hyd_stream, h->a.guard, h->stream);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis stream kernel: %s", cudaGetErrorString(e));
     HydArgs a;
     a.gtp = h->a.gtp;
@@ -1154,6 +1164,7 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
     a.stream_count = need;
     a.threshold = threshold;
     a.status = h->d_hyd_status;
+    a.guard = h->a.guard;
     a.N = N;
     a.ntr = ntr;
     a.nd = nd;
@@ -1220,6 +1231,14 @@ extern "C" int maddy_apply_scheduled_gtp(maddy_handle *h, long long step)
     CU(h, cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->a.ntr * h->a.N;
     CU(h, cudaMemcpyAsync(h->a.gtp, h->d_sched + (size_t)slot * n, n, cudaMemcpyDeviceToDevice, h->stream));
+    return MADDY_OK;
+}
+
+extern "C" int maddy_clear_guard(maddy_handle *h)
+{
+    if (!h) return MADDY_EINVAL;
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaMemsetAsync(h->a.guard, 0, sizeof(int), h->stream));
     return MADDY_OK;
 }
 
@@ -1293,7 +1312,8 @@ extern "C" int maddy_snapshot_begin(maddy_handle *h, unsigned what)
         if (rcp) return rcp;
         h->cls_cur ^= 1; // the older of the two classifications is overwritten and becomes the current one
         cudaError_t e = launch_ontubule(h->a.pos, h->a.ang, h->a.ntr, h->a.N, h->ontub_rule, h->d_cls_pair[h->cls_cur], h->a.ontub,
-                                        (what & MADDY_SNAP_ONTUBULE_APPLY) ? 1 : 0, h->d_cls_count, h->d_cls_count + h->a.ntr, h->stream);
+                                        (what & MADDY_SNAP_ONTUBULE_APPLY) ? 1 : 0, h->d_cls_count, h->d_cls_count + h->a.ntr,
+                                        (what & MADDY_SNAP_ONTUBULE_GUARD) ? h->a.guard : nullptr, h->stream);
         if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "ontubule kernel launch: %s", cudaGetErrorString(e));
         h->launches++;
         CU(h, cudaEventRecord(h->cls_staged, h->stream));

@@ -17,16 +17,18 @@
  */
 #include "maddy_kernels.cuh"
 #include "maddy_lfib.h"
+#include <stdlib.h>
 
 namespace maddy {
 
-#define HYD_ROUNDS 32                       // rounds of 31 draws per thread of the stream kernel
-#define HYD_PER_THREAD (31 * HYD_ROUNDS)    // 992
+#define HYD_ROUNDS 4                        // rounds of 31 draws per thread of the stream kernel
+#define HYD_PER_THREAD (31 * HYD_ROUNDS)    // 124
 
 // out[v] = draw v of the plan = x[31 + v] >> 1, v < count; W[k] = x[k] is the generator's window (oldest word first)
 __global__ void __launch_bounds__(64) hyd_stream_kernel(const uint32_t *__restrict__ W, const LfibPoly *__restrict__ table, unsigned long long count,
-                                                        uint32_t *__restrict__ out)
+                                                        uint32_t *__restrict__ out, const int *__restrict__ guard)
 {
+    if (*guard) return;
     const unsigned long long first = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * HYD_PER_THREAD;
     if (first >= count) return;
     uint32_t base[LFIB_DEG], r[LFIB_DEG];
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(64) hyd_stream_kernel(const uint32_t *__restri
 //   st[d][tr]  bit 0: can hydrolyse (not reserve, on the tubule now and before)   bit 1: returns to GTP (not reserve, off both)
 __global__ void __launch_bounds__(256) hyd_prepare_kernel(HydArgs h)
 {
+    if (*h.guard) return;
     const size_t cells = (size_t)h.nd * h.ntr;
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
         const int d = (int)(c / h.ntr), tr = (int)(c % h.ntr);
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(256) hyd_prepare_kernel(HydArgs h)
 __global__ void __launch_bounds__(128) hyd_count_kernel(HydArgs h)
 {
     __shared__ unsigned wsum[4];
+    if (*h.guard) return;
     const int d = blockIdx.x;
     const uint8_t *gt = h.gt + (size_t)d * h.ntr, *st = h.st + (size_t)d * h.ntr;
     unsigned c = 0;
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(128) hyd_count_kernel(HydArgs h)
 __global__ void __launch_bounds__(1024) hyd_scan_kernel(HydArgs h, int event)
 {
     __shared__ unsigned long long wsum[32];
+    if (*h.guard) return;
     const int per = (h.nd + 1023) / 1024;
     const int d0 = threadIdx.x * per, d1 = min(h.nd, d0 + per);
     unsigned long long s = 0;
@@ -113,15 +118,11 @@ __global__ void __launch_bounds__(1024) hyd_scan_kernel(HydArgs h, int event)
     }
 }
 
-// one event: a warp per dimer row walks the trajectories in order (ballot prefix = position in the stream)
-__global__ void __launch_bounds__(128) hyd_apply_kernel(HydArgs h, uint8_t *__restrict__ slot)
+// one event, one dimer row, one warp: the trajectories in order (ballot prefix = position in the stream)
+__device__ __forceinline__ void hyd_apply_row(const HydArgs &h, int d, unsigned long long pos, uint8_t *__restrict__ slot, int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (d >= h.nd) return;
     uint8_t *gt = h.gt + (size_t)d * h.ntr;
     const uint8_t *st = h.st + (size_t)d * h.ntr;
-    unsigned long long pos = h.rowstart[d];
     const unsigned lt = (1u << lane) - 1u;
     for (int t0 = 0; t0 < h.ntr; t0 += 32) {
         const int tr = t0 + lane;
@@ -147,12 +148,91 @@ __global__ void __launch_bounds__(128) hyd_apply_kernel(HydArgs h, uint8_t *__re
         }
     }
 }
+__global__ void __launch_bounds__(128) hyd_apply_kernel(HydArgs h, uint8_t *__restrict__ slot)
+{
+    if (*h.guard) return;
+    const int lane = threadIdx.x & 31;
+    const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (d >= h.nd) return;
+    hyd_apply_row(h, d, h.rowstart[d], slot, lane);
+}
 
-cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, cudaStream_t st)
+// The whole plan in ONE launch of ONE CTA (ensembles up to ~1 M dimer-trajectory cells: the per-event kernels above are
+// three launches per event, and a stride has ten events): prepare, then per event count -> scan -> apply with CTA
+// barriers in between; the row offsets live in shared memory.
+__global__ void __launch_bounds__(1024) hyd_plan_fused_kernel(HydArgs h, int n_events, uint8_t *__restrict__ slots)
+{
+    extern __shared__ unsigned s_row[]; // [nd]: draws per row, then exclusive prefix
+    __shared__ unsigned s_wsum[32];
+    __shared__ unsigned s_total;
+    if (*h.guard) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t cells = (size_t)h.nd * h.ntr;
+    for (size_t c = tid; c < cells; c += 1024) {
+        const int d = (int)(c / h.ntr), tr = (int)(c % h.ntr);
+        const size_t q = (size_t)tr * h.N + 2 * d;
+        const bool ex = h.extra[q] != 0, cur = h.cur[q] != 0, prev = h.prev[q] != 0;
+        h.gt[c] = h.gtp[q];
+        h.st[c] = (uint8_t)((!ex && cur && prev ? 1 : 0) | (!ex && !cur && !prev ? 2 : 0));
+    }
+    __syncthreads();
+    unsigned long long cursor = 0;
+    const int per = (h.nd + 1023) / 1024;
+    for (int k = 0; k < n_events; k++) {
+        for (int d = warp; d < h.nd; d += 32) { // draws of this event per row
+            const uint8_t *gt = h.gt + (size_t)d * h.ntr, *st = h.st + (size_t)d * h.ntr;
+            unsigned c = 0;
+            for (int tr = lane; tr < h.ntr; tr += 32) c += gt[tr] == 1 && (st[tr] & 1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) s_row[d] = c;
+        }
+        __syncthreads();
+        { // exclusive prefix over the rows
+            const int d0 = tid * per, d1 = min(h.nd, d0 + per);
+            unsigned sum = 0;
+            for (int d = d0; d < d1; d++) sum += s_row[d];
+            unsigned inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                const unsigned w = s_wsum[lane];
+                unsigned winc = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+                    if (lane >= o) winc += t;
+                }
+                s_wsum[lane] = winc - w;
+                if (lane == 31) s_total = winc;
+            }
+            __syncthreads();
+            unsigned run = s_wsum[warp] + inc - sum;
+            for (int d = d0; d < d1; d++) {
+                const unsigned c = s_row[d];
+                s_row[d] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        for (int d = warp; d < h.nd; d += 32) hyd_apply_row(h, d, cursor + s_row[d], slots + (size_t)k * h.ntr * h.N, lane);
+        if (tid == 0) h.event_start[k] = cursor;
+        cursor += s_total;
+        __syncthreads();
+    }
+    if (tid == 0) h.cursor[0] = cursor;
+}
+
+cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, const int *guard, cudaStream_t st)
 {
     const unsigned long long threads = (count + HYD_PER_THREAD - 1) / HYD_PER_THREAD;
     if (threads == 0) return cudaSuccess;
-    hyd_stream_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(W, reinterpret_cast<const LfibPoly *>(table), count, out);
+    hyd_stream_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(W, reinterpret_cast<const LfibPoly *>(table), count, out, guard);
     return cudaGetLastError();
 }
 
@@ -160,6 +240,10 @@ cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned lon
 cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, cudaStream_t st)
 {
     const size_t cells = (size_t)h.nd * h.ntr;
+    if (cells <= (1u << 20) && h.nd <= 8192 && !getenv("MADDY_HYD_PER_EVENT_KERNELS")) {
+        hyd_plan_fused_kernel<<<1, 1024, (size_t)h.nd * sizeof(unsigned), st>>>(h, n_events, slots);
+        return cudaGetLastError();
+    }
     int pb = (int)((cells + 255) / 256);
     if (pb > 148 * 8) pb = 148 * 8;
     hyd_prepare_kernel<<<pb, 256, 0, st>>>(h);

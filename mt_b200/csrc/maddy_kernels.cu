@@ -1152,6 +1152,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
     float4 *const smem = g_smem;
     const maddy_params &p = k.p;
     const DevSys &a = k.a;
+    if (*a.guard) return; // an on-tubule classification queued before this window could not be decided: the host redoes the stride
     const int N = a.N;
     const int traj = blockIdx.x;
     const size_t base = (size_t)traj * N;

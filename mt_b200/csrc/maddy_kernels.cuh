@@ -59,6 +59,7 @@ struct DevSys {
     double *en_mono; // [n][7]
     double *en_traj; // [ntr][7]
     int *status;
+    int *guard; // non-zero: fused windows and hydrolysis plans queued behind return at once (MADDY_SNAP_ONTUBULE_GUARD)
     unsigned long long *stats; // [4] list-maintenance events: near refresh on guard trip, candidate re-scan, all-pairs fallback, near overflow
     uint16_t *cand;    // [ntr][MD_CAND_CAPACITY][Npad] candidate list, k-major
     uint16_t *candcnt; // [ntr][Npad]
@@ -155,6 +156,7 @@ struct HydArgs {
     unsigned long long stream_count;
     unsigned threshold;                      // largest rand() value v with v / (double)RAND_MAX < 0.02
     int *status;                             // bit 0: the stream was too short (cannot happen: sized for the worst case)
+    const int *guard;                        // see DevSys::guard
     int N, ntr, nd;
 };
 

@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const __grid_constant_
 __global__ void __launch_bounds__(WIDE_THREADS) wide_step_kernel(const __grid_constant__ KArgs k, int buf)
 {
     const DevSys &a = k.a;
+    if (*a.guard) return;
     const int N = a.N;
     const int traj = blockIdx.y;
     const size_t base = (size_t)traj * N;
@@ -629,6 +630,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 5) wide_run_kernel(const __grid_
     __shared__ uint8_t s_cnt[WIDE_THREADS];
     __shared__ uint4 s_topo[WIDE_THREADS];
     const DevSys &a = k.a;
+    if (*a.guard) return; // see run_kernel (every CTA reads the same word: nobody is left waiting at a barrier)
     const int N = a.N;
     const int traj = blockIdx.y, tid = threadIdx.x;
     const size_t base = (size_t)traj * N;

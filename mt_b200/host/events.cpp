@@ -507,13 +507,19 @@ void compute(System &s, bool fused, ComputeStats *stats)
     for (Shard &d : sh.v) dev_classify = dev_classify && maddy_has_exact_on_tubule(d.h);
     const bool feedback = flags_matter || (hp.is_const_conc && hp.tub_length); // host results of a stride change the next forces
     const bool overlap_stride = fused && !par.tea_on && !hp.out_force && (!feedback || dev_classify) && !getenv("MADDY_NO_OVERLAP");
-    const bool counts_first = overlap_stride && dev_classify && feedback; // the next window waits for the counts (not the coordinates)
+    // The next window waits for the Ntr counts (not the coordinates) where the host needs them first: for the insertions of
+    // constant concentration, and with several shards whose flags feed back into the forces (a shard cannot run ahead on a
+    // classification another shard could not decide).
+    const bool counts_first = overlap_stride && dev_classify && ((hp.is_const_conc && hp.tub_length) || (feedback && G > 1));
     // hydrolyse() itself runs on the device when ONE handle holds the ensemble (draw positions are global): right after a
     // stride block every event up to the next stride step is evaluated in one go (maddy_hydrolysis_plan) from the 31 words
     // of the host generator and left as the GTP schedule of the fused loop - a window then spans the whole stride and the
     // host only advances its generator by the number of draws the device reports.  May be switched off mid-run (a
     // classification the device could not decide): the host then carries on from the synchronised state.
     bool hyd_dev = overlap_stride && dev_classify && hp.hydrolysis && hp.hydrostep > 0 && G == 1 && N % 2 == 0 && !getenv("MADDY_HOST_HYDROLYSIS");
+    // Everywhere else nothing is waited for: plan and window are queued right behind the snapshot, GUARDED - should the device
+    // be unable to decide a classification, they return without touching the state and the host redoes the stride itself.
+    const bool guarded = overlap_stride && dev_classify && !counts_first && G == 1 && (feedback || hyd_dev);
     bool plan_pending = false;           // a plan whose draw count has not been folded into s.rng yet
     long long plan_first = 0;            // step of its first event
     int plan_events = 0;
@@ -776,17 +782,13 @@ void compute(System &s, bool fused, ComputeStats *stats)
             if (hyd_dev) collect_plan(); // the generator passes the events of the last stride BEFORE this stride's insertion draws
             const unsigned what = MADDY_SNAP_COORDS | (hp.out_energy ? MADDY_SNAP_ENERGIES : 0u) | (fused_stride_energy ? MADDY_SNAP_REBUILD : 0u) |
                                   (classify ? MADDY_SNAP_ONTUBULE | (par.barrier ? MADDY_SNAP_ONTUBULE_APPLY : 0u) : 0u) |
-                                  (classify0 ? MADDY_SNAP_ONTUBULE : 0u) | (hyd_dev ? MADDY_SNAP_GTP : 0u);
+                                  (classify0 ? MADDY_SNAP_ONTUBULE : 0u) | (hyd_dev ? MADDY_SNAP_GTP : 0u) |
+                                  (guarded && (classify || classify0) ? MADDY_SNAP_ONTUBULE_GUARD : 0u);
             for_each([&](Shard &d) { ck(maddy_snapshot_begin(d.h, what), d.h, "maddy_snapshot_begin"); });
             if (hp.out_energy) ens_begin();
             st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0) + (classify || classify0 ? (double)n + 4.0 * Ntr : 0.0) +
                             (hyd_dev ? (double)n : 0.0);
-            if (classify0) { // nothing of it is used by the host (step 0: mt_length() after update(), host flags only): just make sure it was decided
-                int u = 0;
-                ck(maddy_snapshot_tubule_lengths(sh.v[0].h, nullptr, &u), sh.v[0].h, "maddy_snapshot_tubule_lengths");
-                if (u) hyd_dev = false; // s.gtp and the generator are still the host's own
-            }
-            if (classify && (counts_first || hyd_dev)) {
+            if (classify && counts_first) {
                 // What the host derives from this stride feeds back into the next forces (non-zero barrier: the flags, already
                 // applied on the device; constant concentration: the insertions).  Only the Ntr counts are waited for.
                 std::vector<int> counts(Ntr);
@@ -806,7 +808,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
                         plan_events = 0;
                     }
                     deferred_output = host_events();
-                } else if (counts_first) {
+                } else {
                     mt_len_prev = mt_len;
                     mt_len = counts;
                     mt_length_output(s, step, mt_len);
@@ -867,17 +869,20 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.end("stride block");
         prof.begin();
         // ---- steps up to the next host event
-        long long next = hp.steps;
-        next = std::min(next, (step / hp.stride + 1) * hp.stride);
+        long long next = hp.steps, count = 0;
         const bool stepwise = !fused; // TEA windows are queued by maddy_run as well (force + prepare in one launch)
         const bool hydro = hp.hydrolysis && hp.hydrostep > 0;
+        auto window_end = [&] {
+        next = std::min(hp.steps, (step / hp.stride + 1) * hp.stride);
         // One window per hydrolysis period: hydrolyse() for the NEXT event is evaluated on the host while the GPU runs
         // the current window (see below), so the events cost no GPU idle time.  (maddy_schedule_gtp can fold several
         // events into one launch, but their evaluation would then sit between two windows instead of beside one.)
         // (events evaluated on the device are applied inside the window: it runs to the next stride step)
         if (hydro && !(hyd_dev && plan_covers((step / hp.hydrostep + 1) * (long long)hp.hydrostep)))
             next = std::min(next, scheduled_end > step ? scheduled_end : (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
-        const long long count = next - step;
+        count = next - step;
+        };
+        window_end();
         if (stepwise) {
             for (long long q = step; q < next; q++) {
                 for_each([&](Shard &d) {
@@ -914,20 +919,33 @@ void compute(System &s, bool fused, ComputeStats *stats)
             prof.end("stride collect (wait + transpose)");
             mark("snapshot collected", step);
             prof.begin();
+            // A guarded classification the device could not decide: plan and window returned without touching the state.  The
+            // host takes the stride over - guard cleared, hydrolysis back on the host for good (from the synchronised state:
+            // s.gtp was just read back, the generator has not moved), host classification, and the window queued again.
+            int undecided = 0;
+            if ((classify && !counts_first) || classify0)
+                for_each([&](Shard &d) {
+                    int u = 0;
+                    ck(maddy_snapshot_tubule_lengths(d.h, nullptr, &u), d.h, "maddy_snapshot_tubule_lengths");
+                    undecided |= u;
+                });
+            const bool redo = undecided && guarded;
+            if (redo) {
+                for_each([&](Shard &d) { ck(maddy_clear_guard(d.h), d.h, "maddy_clear_guard"); });
+                if (hyd_dev) {
+                    if (plan_pending) ck(maddy_hydrolysis_result(sh.v[0].h, nullptr, nullptr, nullptr), sh.v[0].h, "maddy_hydrolysis_result");
+                    ck(maddy_schedule_gtp(sh.v[0].h, 0, 1, 0, nullptr), sh.v[0].h, "maddy_schedule_gtp");
+                    plan_pending = false;
+                    plan_events = 0;
+                    hyd_dev = false;
+                }
+            }
             if (!classify) {
                 deferred_output = host_events(); // flags cannot change a force here: the upload only keeps the device copy current
             } else {
                 s.on_tubule_prev = s.on_tubule_cur;
-                int undecided = 0;
-                if (!counts_first) { // nobody needed the counts before the launch: look at the undecided word now
-                    for_each([&](Shard &d) {
-                        int u = 0;
-                        ck(maddy_snapshot_tubule_lengths(d.h, nullptr, &u), d.h, "maddy_snapshot_tubule_lengths");
-                        undecided |= u;
-                    });
-                    mt_len_prev = mt_len;
-                }
-                if (undecided) { // classify this stride on the host (no force depends on it in this mode)
+                if (!counts_first) mt_len_prev = mt_len;
+                if (undecided) { // classify this stride on the host
                     mt_length(s, step, mt_len);
                     if (par.barrier) {
                         for_each([&](Shard &d) { ck(maddy_upload_on_tubule(d.h, &s.on_tubule_cur[(size_t)d.first * N]), d.h, "maddy_upload_on_tubule"); });
@@ -948,6 +966,11 @@ void compute(System &s, bool fused, ComputeStats *stats)
                     a1[2] = e.z2;
                 }
                 deferred_output = 1;
+            }
+            if (redo) { // the window of this stride, again, now in host mode (it ends at the next host event)
+                window_end();
+                for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, explicit_rebuild ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u), d.h, "maddy_run"); });
+                mark("window launched again (host events)", step);
             }
         }
         prof.end("stride collect");

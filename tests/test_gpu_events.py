@@ -234,3 +234,67 @@ def test_device_hydrolysis_plan_equals_host_hydrolyse(rundir, load_system):
     g = Engine(s, traj_first=0, n_tr_local=ntr - 1)
     with pytest.raises(MaddyError):
         g.hydrolysis_plan(w, 1100, 100, 2)  # a shard: draw positions are global
+
+
+def test_guarded_classification_poisons_what_is_queued_behind_it(rundir, load_system):
+    """MADDY_SNAP_ONTUBULE_GUARD: an undecided classification turns the plan and the window queued behind it into no-ops
+    (state, RNG streams, lists untouched) until maddy_clear_guard; a decided one changes nothing."""
+    s = load_system(rundir("mt120_disassembly", runnum=3))
+    e, ref = Engine(s), Engine(s)
+    for eng in (e, ref):
+        eng.run(0, 40)
+    c = e.coords()
+    bad = c.copy()
+    bad[1, 7, 4] = 40.0  # several turns away: the device does not guess
+    e.upload_coords(bad)
+    ref.upload_coords(bad)
+    e.snapshot_begin(coords=False, energies=False, apply_on_tubule=True, guard=True)
+    e.hydrolysis_plan(s.rand_window(), 100, 100, 2)
+    e.run(40, 60)            # no-op
+    _, und = e.snapshot_tubule_lengths()
+    assert und != 0
+    from mt_b200 import MaddyError
+    with pytest.raises(MaddyError):
+        e.snapshot_end()
+    total, _, _ = e.hydrolysis_result()
+    assert total == 0
+    assert np.array_equal(e.coords(), bad) and np.array_equal(e.rng_state(), ref.rng_state())
+    e.clear_guard()
+    e.schedule_gtp(0, 1, [])
+    # the host's verdict, then the same window on both engines
+    s.coords[...] = bad
+    s.mt_length(40)
+    for eng in (e, ref):
+        eng.upload_on_tubule(np.array(s.on_tubule_cur))
+        eng.run(40, 60)
+    assert np.array_equal(e.coords(), ref.coords()) and not np.array_equal(e.coords(), bad)
+
+
+@pytest.mark.parametrize("case", ["mt120_disassembly", "mt40_ensemble"])
+def test_loop_takes_over_on_the_host_when_the_device_cannot_decide(case, rundir, monkeypatch):
+    """compute() with a crippled device rule (MADDY_ONTUB_AMAX, test hook: |theta| >= 0.05 counts as undecided) == the
+    host-events loop: the guarded windows are redone, hydrolysis returns to the host, nothing is guessed."""
+    import mt_b200
+    from mt_b200 import HostSystem, workspace
+    out = {}
+    for mode in ("crippled", "host"):
+        d = rundir(case, runnum=3, steps=650, stride=200)
+        if mode == "crippled":
+            monkeypatch.setenv("MADDY_ONTUB_AMAX", "0.05")
+        else:
+            monkeypatch.delenv("MADDY_ONTUB_AMAX")
+            monkeypatch.setenv("MADDY_HOST_EVENTS", "1")
+            monkeypatch.setenv("MADDY_NO_OVERLAP", "1")
+        with workspace.chdir(d):
+            s = HostSystem("config.conf", [], write_files=True)
+            s.srand(s.par.rseed)
+            s.compute()
+            out[mode] = (np.array(s.coords).copy(), np.array(s.gtp).copy(), np.array(s.on_tubule_cur).copy(), np.array(s.energies).copy(),
+                         [mt_b200.read_dcd(d / "dcd" / f"run_{t}.dcd") for t in range(3)], (d / "mt_len.dat").read_text(), s.rand_next())
+            s.close()
+    monkeypatch.delenv("MADDY_HOST_EVENTS")
+    monkeypatch.delenv("MADDY_NO_OVERLAP")
+    a, b = out["crippled"], out["host"]
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    assert all(np.array_equal(x, y) and x.shape[0] == 4 for x, y in zip(a[4], b[4])) and a[5] == b[5] and a[6] == b[6]
