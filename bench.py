@@ -206,7 +206,8 @@ class StrideIssuer:
             and eng.ntr == system.Ntr and not os.environ.get("MADDY_HOST_HYDROLYSIS") and not os.environ.get("MADDY_HOST_EVENTS")
         self.apply_flags = bool(system.par.barrier)
         self.plan_pending = False
-        self.windows = [(0, self.stride, self.stride // self.period)] if self.dev_hyd else self._pattern(single_event)
+        self.windows = [(0, self.period, 0), (self.period, self.stride - self.period, self.stride // self.period)] if self.dev_hyd \
+            else self._pattern(single_event)
         self.window_events = []  # (start, end) torch events around every maddy_run since the last reset
         self.md_in_windows = 0
 
@@ -245,15 +246,18 @@ class StrideIssuer:
                                guard=True)
             eng.hydrolysis_plan(self.system.rand_window(), s0 + h, h, self.stride // h)
             self.plan_pending = True
-            if timed:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(self.stream)
-            eng.run(s0, self.stride, skip_first_rebuild=True)
-            if timed:
-                b.record(self.stream)
-                self.window_events.append((a, b))
-                self.md_in_windows += self.stride
-            eng.snapshot_end()  # the host collects while the window runs
+            # the plan is evaluated beside the window up to its first event; the window to the next stride step waits for it
+            for first, n in ((s0, h), (s0 + h, self.stride - h)):
+                if timed:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(self.stream)
+                eng.run(first, n, skip_first_rebuild=(first == s0))
+                if timed:
+                    b.record(self.stream)
+                    self.window_events.append((a, b))
+                    self.md_in_windows += n
+                if first == s0:
+                    eng.snapshot_end()  # the host collects while the first window runs
             if eng.snapshot_tubule_lengths()[1]:
                 raise RuntimeError("bench: the on-tubule classification was undecided (the drop-in loop would redo the stride on the host)")
             return

@@ -148,7 +148,9 @@ struct maddy_handle {
     int *d_hyd_status = nullptr, *h_hyd_status = nullptr;
     uint8_t *h_hyd_slots = nullptr;
     size_t hyd_slots_cap = 0;
-    cudaEvent_t hyd_staged = nullptr, hyd_done = nullptr;
+    cudaEvent_t hyd_staged = nullptr, hyd_done = nullptr, hyd_in = nullptr;
+    cudaStream_t aux_stream = nullptr; // the plan's kernels run beside the window that precedes its first event
+    bool plan_wait = false;            // the main stream has not yet been made to wait for the plan
     int hyd_events = 0;      // events of the plan whose result is pending / was collected last
     bool hyd_pending = false, hyd_keep = false;
     // sparse insertions (maddy_insert_dimers): pinned + device record buffers {index, then float4 xyzz}, reuse event
@@ -517,6 +519,8 @@ extern "C" int maddy_destroy(maddy_handle *h)
     for (void *q : {(void *)h->h_snap_gtp, (void *)h->h_hyd_counters, (void *)h->h_hyd_window, (void *)h->h_hyd_status, (void *)h->h_hyd_slots})
         if (q) cudaFreeHost(q);
     if (h->hyd_staged) cudaEventDestroy(h->hyd_staged);
+    if (h->hyd_in) cudaEventDestroy(h->hyd_in);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->hyd_done) cudaEventDestroy(h->hyd_done);
     if (h->cls_staged) cudaEventDestroy(h->cls_staged);
     if (h->cls_done) cudaEventDestroy(h->cls_done);
@@ -933,6 +937,10 @@ extern "C" int maddy_run(maddy_handle *h, long long first_step, long long n_step
     k.first_step = first_step;
     k.n_steps = n_steps;
     k.run_flags = flags;
+    if (h->plan_wait && k.sched_slots > 0 && first_step + n_steps > k.sched_first) { // the window reaches an event planned on the aux stream
+        CU(h, cudaStreamWaitEvent(h->stream, h->hyd_staged, 0));
+        h->plan_wait = false;
+    }
     if (k.lazy && rebuilds) { // does the window contain a list-update step?
         long long m = (first_step + freq - 1) / freq * freq;
         if (m == first_step && skip_first) m += freq;
@@ -1112,6 +1120,8 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
         CU(h, cudaMallocHost(&h->h_hyd_status, sizeof(int)));
         CU(h, cudaEventCreateWithFlags(&h->hyd_staged, cudaEventDisableTiming));
         CU(h, cudaEventCreateWithFlags(&h->hyd_done, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->hyd_in, cudaEventDisableTiming));
+        CU(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
         if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     }
     if (n_events + 1 > h->hyd_counters_cap) {
@@ -1136,18 +1146,24 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
     rc = sched_reserve(h, n * (size_t)n_events);
     if (rc) return rc;
     const int b = h->sched_cur ^ 1; // the buffer the last scheduled run was NOT given (same stream: no reader left behind)
-    if (h->sched_copied[b]) CU(h, cudaStreamWaitEvent(h->stream, h->sched_copied[b], 0));
+    if (h->sched_copied[b]) CU(h, cudaStreamWaitEvent(h->aux_stream, h->sched_copied[b], 0));
     // threshold of updater.cpp:236-237 in this process's own double arithmetic
     static const unsigned threshold = [] {
         int v = (int)(0.02 * (double)RAND_MAX) + 2;
         while (!((double)v / (double)RAND_MAX < 0.02)) v--;
         return (unsigned)v;
     }();
+    // The kernels run on a stream of their own, behind everything queued so far (classification, GTP state) and beside what
+    // is queued next - the window up to the first event, which needs none of it (the small CTAs fit on the SMs the fused
+    // loop leaves half empty).  The first maddy_run that reaches an event of the plan waits for it.
+    cudaStream_t ax = h->aux_stream;
+    CU(h, cudaEventRecord(h->hyd_in, h->stream));
+    CU(h, cudaStreamWaitEvent(ax, h->hyd_in, 0));
     memcpy(h->h_hyd_window, window31, LFIB_DEG * sizeof(uint32_t));
-    CU(h, cudaMemcpyAsync(h->d_hyd_window, h->h_hyd_window, LFIB_DEG * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemsetAsync(h->d_hyd_counters, 0, sizeof(unsigned long long), h->stream));
-    CU(h, cudaMemsetAsync(h->d_hyd_status, 0, sizeof(int), h->stream));
-    cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_lfib_table, need, h->d_hyd_stream, h->a.guard, h->stream);
+    CU(h, cudaMemcpyAsync(h->d_hyd_window, h->h_hyd_window, LFIB_DEG * sizeof(uint32_t), cudaMemcpyHostToDevice, ax));
+    CU(h, cudaMemsetAsync(h->d_hyd_counters, 0, sizeof(unsigned long long), ax));
+    CU(h, cudaMemsetAsync(h->d_hyd_status, 0, sizeof(int), ax));
+    cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_lfib_table, need, h->d_hyd_stream, h->a.guard, ax);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis stream kernel: %s", cudaGetErrorString(e));
     HydArgs a;
     a.gtp = h->a.gtp;
@@ -1168,16 +1184,17 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
     a.N = N;
     a.ntr = ntr;
     a.nd = nd;
-    e = launch_hyd_plan(a, n_events, h->d_sched_buf[b], h->stream);
+    e = launch_hyd_plan(a, n_events, h->d_sched_buf[b], ax);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis plan kernels: %s", cudaGetErrorString(e));
-    h->launches += 2 + 3LL * n_events;
+    h->launches += 2 + 3LL * n_events; // stream + prepare + (count, scan, apply) per event
     h->sched_cur = b;
     h->d_sched = h->d_sched_buf[b];
     h->sched_first = first_event;
     h->sched_period = period;
     h->sched_slots = n_events;
     // counters (and, on request, the slots) travel beside the windows queued next
-    CU(h, cudaEventRecord(h->hyd_staged, h->stream));
+    CU(h, cudaEventRecord(h->hyd_staged, ax));
+    h->plan_wait = true;
     CU(h, cudaStreamWaitEvent(h->copy_stream, h->hyd_staged, 0));
     CU(h, cudaMemcpyAsync(h->h_hyd_counters, h->d_hyd_counters, (size_t)(n_events + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->copy_stream));
     CU(h, cudaMemcpyAsync(h->h_hyd_status, h->d_hyd_status, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
@@ -1229,6 +1246,10 @@ extern "C" int maddy_apply_scheduled_gtp(maddy_handle *h, long long step)
     const long long slot = (step - h->sched_first) / h->sched_period;
     if (slot >= h->sched_slots) return MADDY_OK;
     CU(h, cudaSetDevice(h->p.device));
+    if (h->plan_wait) {
+        CU(h, cudaStreamWaitEvent(h->stream, h->hyd_staged, 0));
+        h->plan_wait = false;
+    }
     const size_t n = (size_t)h->a.ntr * h->a.N;
     CU(h, cudaMemcpyAsync(h->a.gtp, h->d_sched + (size_t)slot * n, n, cudaMemcpyDeviceToDevice, h->stream));
     return MADDY_OK;

@@ -240,7 +240,9 @@ cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned lon
 cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, cudaStream_t st)
 {
     const size_t cells = (size_t)h.nd * h.ntr;
-    if (cells <= (1u << 20) && h.nd <= 8192 && !getenv("MADDY_HYD_PER_EVENT_KERNELS")) {
+    // (one CTA is latency-bound on its dependent loads: 1.3 ms per plan at 260 x 256 against 0.18 ms for the per-event
+    // launches below; kept for very small ensembles, where the launches dominate)
+    if (cells <= 4096 && h.nd <= 8192 && !getenv("MADDY_HYD_PER_EVENT_KERNELS")) {
         hyd_plan_fused_kernel<<<1, 1024, (size_t)h.nd * sizeof(unsigned), st>>>(h, n_events, slots);
         return cudaGetLastError();
     }

@@ -877,9 +877,15 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // One window per hydrolysis period: hydrolyse() for the NEXT event is evaluated on the host while the GPU runs
         // the current window (see below), so the events cost no GPU idle time.  (maddy_schedule_gtp can fold several
         // events into one launch, but their evaluation would then sit between two windows instead of beside one.)
-        // (events evaluated on the device are applied inside the window: it runs to the next stride step)
-        if (hydro && !(hyd_dev && plan_covers((step / hp.hydrostep + 1) * (long long)hp.hydrostep)))
-            next = std::min(next, scheduled_end > step ? scheduled_end : (step / hp.hydrostep + 1) * (long long)hp.hydrostep);
+        // Events evaluated on the device are applied inside the window.  The window that follows a stride block stops at the
+        // first of them: the plan queued with the stride block is evaluated on a stream of its own BESIDE that window, and
+        // the next one - which runs to the next stride step - waits for it.
+        const long long first_event = (step / hp.hydrostep + 1) * (long long)hp.hydrostep;
+        if (hydro && hyd_dev && plan_covers(first_event)) {
+            if (stride_now) next = std::min(next, first_event);
+        } else if (hydro) {
+            next = std::min(next, scheduled_end > step ? scheduled_end : first_event);
+        }
         count = next - step;
         };
         window_end();
