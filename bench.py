@@ -18,7 +18,7 @@ value   device-timed whole job, state resident in HBM: K strides issued exactly 
         strides, a 256 MiB L2 flush write between bench steps (inside the pair), max over ranks; repeated R times, median.
 e2e     the drop-in compute() call of the C++ host (mt_system_compute) over K strides with HOST buffers: device
         allocation + upload of coordinates / topology / seeds, hydrolysis draws + uploads, energies + coordinate download
-        every stride, DCD / PDB / mt_len output, all inside the timed region (wall clock); median of 5 runs.
+        every stride, DCD / PDB / mt_len output, all inside the timed region (wall clock); median of 9 runs after 2 untimed ones.
 roofline  algorithmic bytes of the step-granular contract (352 B per monomer-step on the intact lattice)
         per fused-window launch / average launch duration (event pairs around every maddy_run inside the timed region),
         against the measured HBM copy bandwidth.  The fused kernel keeps the state on-chip, so `traffic` (ncu dram
@@ -184,6 +184,13 @@ def cpu_baseline(workload: str, budget_s: float = 10.0):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+class _DevicePtr:
+    """a raw device buffer of the C-ABI as something torch can wrap (no copy)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
 class StrideIssuer:
     """Issues strides on one Engine the way mt_b200/host/events.cpp::compute does in its overlapped mode: at a stride step
     the read-back (list rebuild + energies + coordinates) is queued, the first window launched, the snapshot collected;
@@ -202,8 +209,10 @@ class StrideIssuer:
         # hydrolysis on the device (the drop-in loop's default when one handle holds the ensemble): the events of a stride
         # are planned right after its stride block and applied inside ONE window that spans the stride
         self.system = system
+        self.shards = system.Ntr // eng.ntr if system.Ntr % eng.ntr == 0 else 0  # equal contiguous blocks, one per rank
         self.dev_hyd = bool(self.period) and not self.tea and system.Ntot % 2 == 0 and bool(system.host.tub_length) \
-            and eng.ntr == system.Ntr and not os.environ.get("MADDY_HOST_HYDROLYSIS") and not os.environ.get("MADDY_HOST_EVENTS")
+            and self.shards >= 1 and not os.environ.get("MADDY_HOST_HYDROLYSIS") and not os.environ.get("MADDY_HOST_EVENTS")
+        self.gathered = None  # sharded ensemble: every rank's plan inputs, all-gathered once per stride (NCCL over NVLink)
         self.apply_flags = bool(system.par.barrier)
         self.plan_pending = False
         self.windows = [(0, self.period, 0), (self.period, self.stride - self.period, self.stride // self.period)] if self.dev_hyd \
@@ -244,7 +253,17 @@ class StrideIssuer:
                 self.plan_pending = False
             eng.snapshot_begin(coords=True, energies=True, rebuild=True, on_tubule=True, apply_on_tubule=(s0 != 0 and self.apply_flags), gtp=True,
                                guard=True)
-            eng.hydrolysis_plan(self.system.rand_window(), s0 + h, h, self.stride // h)
+            if self.shards == 1:
+                eng.hydrolysis_plan(self.system.rand_window(), s0 + h, h, self.stride // h)
+            else:
+                # the draw positions are global: each rank evaluates the ensemble's plan from the gathered inputs
+                import torch.distributed as dist
+                ptr, nb = eng.hydrolysis_inputs()
+                own = torch.as_tensor(_DevicePtr(ptr, nb), device="cuda")
+                if self.gathered is None:
+                    self.gathered = torch.empty(self.shards * nb, dtype=torch.uint8, device="cuda")
+                dist.all_gather_into_tensor(self.gathered, own)
+                eng.hydrolysis_plan_sharded(self.gathered.data_ptr(), self.shards, self.system.rand_window(), s0 + h, h, self.stride // h)
             self.plan_pending = True
             # the plan is evaluated beside the window up to its first event; the window to the next stride step waits for it
             for first, n in ((s0, h), (s0 + h, self.stride - h)):
@@ -256,8 +275,7 @@ class StrideIssuer:
                     b.record(self.stream)
                     self.window_events.append((a, b))
                     self.md_in_windows += n
-                if first == s0:
-                    eng.snapshot_end()  # the host collects while the first window runs
+            eng.snapshot_end()  # the host collects while the windows run
             if eng.snapshot_tubule_lengths()[1]:
                 raise RuntimeError("bench: the on-tubule classification was undecided (the drop-in loop would redo the stride on the host)")
             return
@@ -387,7 +405,7 @@ def run_own(args):
         # and tmpfs pages (single runs of 0.4 s and 2.6 s were seen before the 0.20 s steady state), like the W warm-up steps
         # of the device-timed leg.
         walls = []
-        for rep in range(-2, 5):
+        for rep in range(-2, 9):
             e2e_sys = make_system(args.workload, ntr_local, tmp / f"e2e_{rep}", [f"device={local}"], write_files=True, steps=K * stride)
             e2e_sys.srand(e2e_sys.par.rseed)
             if world > 1:
@@ -407,7 +425,7 @@ def run_own(args):
         e2e = {"value": N * ntr_global * stride * K / wall, "unit": UNIT,
                "h2d_bytes_per_step": st["h2d_bytes"] / K, "d2h_bytes_per_step": st["d2h_bytes"] / K,
                "call": "mt_system_compute (drop-in compute(): create + upload, fused windows, hydrolysis draws + uploads, asynchronous stride read-back, DCD output)",
-               "md_steps": K * stride, "wall_s": wall, "wall_s_runs": [round(w, 4) for w in tw.tolist()], "statistic": "median of 5 runs (each the max over ranks) after 2 untimed runs of the same length",
+               "md_steps": K * stride, "wall_s": wall, "wall_s_runs": [round(w, 4) for w in tw.tolist()], "statistic": "median of 9 runs (each the max over ranks) after 2 untimed runs of the same length",
                "scratch": str(tmp.parent)}
 
         # ---- N > 1: the product's own multi-GPU path, one host thread driving N handles

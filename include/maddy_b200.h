@@ -187,9 +187,23 @@ int maddy_schedule_gtp(maddy_handle *h, long long first_event, long long period,
  * consumed (the caller advances its generator by that many, e.g. with maddy_rand_discard), event_first_draw[k] = draws
  * consumed before event k (may be NULL), gtp_slots ([n_events][n_tr_local * n_tot] ints, may be NULL; only available
  * when the plan was made with MADDY_HYD_KEEP_SLOTS) = GTP state after every event, for the caller's messages.
- * Requires one handle holding the whole ensemble (n_tr_local == n_tr) and an even n_tot. */
+ * Requires one handle holding the whole ensemble (n_tr_local == n_tr) and an even n_tot.
+ *
+ * SHARDED ensembles (equal contiguous blocks, one handle each): the draw positions are global, so every shard evaluates
+ * the plan of the WHOLE ensemble and keeps the slots of its own trajectories.  maddy_hydrolysis_inputs queues the
+ * preparation of this shard's inputs (its GTP state and eligibility masks, transposed: [2][n_tot / 2][n_tr_local] bytes)
+ * and returns the device buffer; the caller gathers the buffers of all shards in shard order into one device array on
+ * every GPU (ncclAllGather, torch.distributed.all_gather_into_tensor, ... in stream order with the handle's stream) and
+ * passes it to maddy_hydrolysis_plan_sharded.  maddy_hydrolysis_plan_all does all of that for handles living in this
+ * process (NCCL).  draws_total of maddy_hydrolysis_result is the ensemble's, identical on every shard; gtp_slots holds
+ * this shard's trajectories. */
 #define MADDY_HYD_KEEP_SLOTS 1u
 int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *rand_window31, long long first_event, long long period, int n_events, unsigned flags);
+int maddy_hydrolysis_inputs(maddy_handle *h, void **device_buffer, unsigned long *bytes);
+int maddy_hydrolysis_plan_sharded(maddy_handle *h, const void *gathered_device, int n_shards, const unsigned *rand_window31, long long first_event,
+                                  long long period, int n_events, unsigned flags);
+int maddy_hydrolysis_plan_all(maddy_handle **handles, int n, const unsigned *rand_window31, long long first_event, long long period, int n_events,
+                              unsigned flags);
 int maddy_hydrolysis_result(maddy_handle *h, unsigned long long *draws_total, unsigned long long *event_first_draw, int *gtp_slots);
 /* The scheduled GTP state of `step` (maddy_schedule_gtp / maddy_hydrolysis_plan), if there is one, becomes current NOW
  * (the fused loop applies slots at the start of their step; a caller that evaluates energies at that step before it

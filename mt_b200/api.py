@@ -327,6 +327,18 @@ class Engine:
         self._ck(capi.lib.maddy_hydrolysis_plan(self._h, as_ptr(w, C.c_uint), int(first_event), int(period), int(n_events),
                                                 capi.HYD_KEEP_SLOTS if keep_slots else 0))
 
+    def hydrolysis_inputs(self):
+        """(device pointer, bytes) of this shard's transposed plan inputs, prepared in stream order (maddy_hydrolysis_inputs)"""
+        ptr, nb = C.c_void_p(), C.c_ulong()
+        self._ck(capi.lib.maddy_hydrolysis_inputs(self._h, C.byref(ptr), C.byref(nb)))
+        return int(ptr.value), int(nb.value)
+
+    def hydrolysis_plan_sharded(self, gathered_ptr: int, n_shards: int, rand_window, first_event: int, period: int, n_events: int, keep_slots=False):
+        w = np.ascontiguousarray(rand_window, dtype=np.uint32)
+        self._hyd = (int(n_events), bool(keep_slots))
+        self._ck(capi.lib.maddy_hydrolysis_plan_sharded(self._h, C.c_void_p(gathered_ptr), int(n_shards), as_ptr(w, C.c_uint), int(first_event),
+                                                        int(period), int(n_events), capi.HYD_KEEP_SLOTS if keep_slots else 0))
+
     def hydrolysis_result(self):
         """-> (draws_total, first draw of every event, slots [n_events, ntr, N] or None)"""
         ne, keep = self._hyd

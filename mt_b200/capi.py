@@ -105,6 +105,7 @@ KERNEL_SYMBOLS = [
     "maddy_analysis_protofilaments", "maddy_ensemble_stats_begin", "maddy_ensemble_stats_end", "maddy_download_tea",
     "maddy_snapshot_tubule_lengths", "maddy_snapshot_on_tubule", "maddy_insert_dimers", "maddy_has_exact_on_tubule",
     "maddy_hydrolysis_plan", "maddy_hydrolysis_result", "maddy_apply_scheduled_gtp", "maddy_rand_discard", "maddy_snapshot_gtp", "maddy_clear_guard",
+    "maddy_hydrolysis_inputs", "maddy_hydrolysis_plan_sharded", "maddy_hydrolysis_plan_all",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
@@ -162,6 +163,9 @@ _sig(lib.maddy_apply_scheduled_gtp, _i, [_vp, _ll])
 _sig(lib.maddy_rand_discard, None, [C.POINTER(C.c_uint), C.c_ulonglong])
 _sig(lib.maddy_snapshot_gtp, _i, [_vp, _pi])
 _sig(lib.maddy_clear_guard, _i, [_vp])
+_sig(lib.maddy_hydrolysis_inputs, _i, [_vp, C.POINTER(_vp), C.POINTER(C.c_ulong)])
+_sig(lib.maddy_hydrolysis_plan_sharded, _i, [_vp, _vp, _i, C.POINTER(C.c_uint), _ll, _ll, _i, _u])
+_sig(lib.maddy_hydrolysis_plan_all, _i, [C.POINTER(_vp), _i, C.POINTER(C.c_uint), _ll, _ll, _i, _u])
 
 _sig(hostlib.mt_host_last_error, C.c_char_p, [])
 _sig(hostlib.mt_system_load, _i, [C.c_char_p, _i, C.POINTER(C.c_char_p), _u, C.POINTER(_vp)])

@@ -34,7 +34,8 @@ cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaS
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 int tea_partner_segments(int N);
 cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, const int *guard, cudaStream_t st);
-cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, cudaStream_t st);
+cudaError_t launch_hyd_prepare(const HydArgs &h, cudaStream_t st);
+cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, bool prepared, cudaStream_t st);
 cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_phase(const KArgs &k, int buf, cudaStream_t st);
 cudaError_t launch_wide_step(const KArgs &k, int buf, cudaStream_t st);
@@ -138,7 +139,8 @@ struct maddy_handle {
     // GTP flags with the snapshot (MADDY_SNAP_GTP)
     uint8_t *d_snap_gtp = nullptr, *h_snap_gtp = nullptr;
     // hydrolysis events of a stride on the device (maddy_hydrolysis_plan)
-    uint8_t *d_hyd_gt = nullptr, *d_hyd_st = nullptr;
+    uint8_t *d_hyd_own = nullptr, *d_hyd_all = nullptr; // this shard's transposed inputs / the working copy of every shard's (== own for one shard)
+    size_t hyd_all_cap = 0;
     unsigned *d_hyd_rowcount = nullptr;
     unsigned long long *d_hyd_rowstart = nullptr, *d_hyd_counters = nullptr, *h_hyd_counters = nullptr; // [0] draws consumed, [1 + k] first draw of event k
     int hyd_counters_cap = 0;
@@ -512,7 +514,7 @@ extern "C" int maddy_destroy(maddy_handle *h)
         if (q) cudaFreeHost(q);
     if (h->snap_done) cudaEventDestroy(h->snap_done);
     if (h->snap_staged) cudaEventDestroy(h->snap_staged);
-    for (void *q : {(void *)h->d_cls_pair[0], (void *)h->d_cls_pair[1], (void *)h->d_snap_gtp, (void *)h->d_hyd_gt, (void *)h->d_hyd_st, (void *)h->d_hyd_rowcount,
+    for (void *q : {(void *)h->d_cls_pair[0], (void *)h->d_cls_pair[1], (void *)h->d_snap_gtp, (void *)h->d_hyd_own, (void *)(h->d_hyd_all != h->d_hyd_own ? h->d_hyd_all : nullptr), (void *)h->d_hyd_rowcount,
                     (void *)h->d_hyd_rowstart, (void *)h->d_hyd_counters, (void *)h->d_hyd_stream, (void *)h->d_hyd_window, h->d_lfib_table,
                     (void *)h->d_hyd_status})
         if (q) cudaFree(q);
@@ -1096,46 +1098,110 @@ extern "C" void maddy_rand_discard(unsigned *window31, unsigned long long n)
 }
 static int sched_reserve(maddy_handle *h, size_t bytes);
 
-extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, long long first_event, long long period, int n_events, unsigned flags)
+// buffers every hydrolysis call needs (first use)
+static int hyd_ready(maddy_handle *h)
 {
-    if (!h || !window31 || n_events < 1 || period <= 0) return MADDY_EINVAL;
-    if (h->p.n_tr_local != h->p.n_tr || (h->a.N & 1))
-        return fail(h, MADDY_EINVAL, "maddy_hydrolysis_plan needs the whole ensemble on one handle and an even n_tot (draw positions are global)");
+    if (h->d_hyd_own) return MADDY_OK;
+    const int nd = h->a.N / 2;
+    const size_t cells = (size_t)nd * h->a.ntr;
+    CU(h, cudaMalloc(&h->d_hyd_own, 2 * cells));
+    CU(h, cudaMalloc(&h->d_hyd_rowcount, (size_t)nd * sizeof(unsigned)));
+    CU(h, cudaMalloc(&h->d_hyd_rowstart, (size_t)nd * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&h->d_hyd_window, LFIB_DEG * sizeof(uint32_t)));
+    CU(h, cudaMallocHost(&h->h_hyd_window, LFIB_DEG * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&h->d_lfib_table, sizeof(LfibPoly) * LFIB_POW2));
+    CU(h, cudaMemcpyAsync(h->d_lfib_table, lfib_host_table(), sizeof(LfibPoly) * LFIB_POW2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMalloc(&h->d_hyd_status, sizeof(int)));
+    CU(h, cudaMallocHost(&h->h_hyd_status, sizeof(int)));
+    CU(h, cudaEventCreateWithFlags(&h->hyd_staged, cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->hyd_done, cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->hyd_in, cudaEventDisableTiming));
+    CU(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    return MADDY_OK;
+}
+static HydArgs hyd_args(maddy_handle *h, int shards, int shard)
+{
+    HydArgs a;
+    memset(&a, 0, sizeof a);
+    a.gtp = h->a.gtp;
+    a.extra = h->a.extra;
+    a.cur = h->d_cls_pair[h->cls_cur];
+    a.prev = h->d_cls_pair[h->cls_cur ^ 1];
+    a.own = h->d_hyd_own;
+    a.all = shards > 1 ? h->d_hyd_all : h->d_hyd_own;
+    a.rowcount = h->d_hyd_rowcount;
+    a.rowstart = h->d_hyd_rowstart;
+    a.cursor = h->d_hyd_counters;
+    a.event_start = h->d_hyd_counters + 1;
+    a.stream = h->d_hyd_stream;
+    a.status = h->d_hyd_status;
+    a.guard = h->a.guard;
+    a.N = h->a.N;
+    a.nd = h->a.N / 2;
+    a.ntr_l = h->a.ntr;
+    a.shards = shards;
+    a.shard = shard;
+    a.ntr = shards * h->a.ntr;
+    return a;
+}
+
+extern "C" int maddy_hydrolysis_inputs(maddy_handle *h, void **device_buffer, unsigned long *bytes)
+{
+    if (!h || !device_buffer) return MADDY_EINVAL;
+    if (h->a.N & 1) return fail(h, MADDY_EINVAL, "hydrolysis on the device needs an even n_tot");
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = cls_pair_ready(h);
+    if (!rc) rc = hyd_ready(h);
+    if (rc) return rc;
+    cudaError_t e = launch_hyd_prepare(hyd_args(h, 1, 0), h->stream);
+    if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis prepare kernel: %s", cudaGetErrorString(e));
+    h->launches++;
+    *device_buffer = h->d_hyd_own;
+    if (bytes) *bytes = (unsigned long)((size_t)h->a.N * h->a.ntr); // 2 x (N / 2) x n_tr_local
+    return MADDY_OK;
+}
+
+// gathered == nullptr: one shard, the plan prepares its inputs itself
+static int hyd_plan_impl(maddy_handle *h, const void *gathered, int shards, const unsigned *window31, long long first_event, long long period, int n_events,
+                         unsigned flags)
+{
+    if (!h || !window31 || n_events < 1 || period <= 0 || shards < 1) return MADDY_EINVAL;
+    if (h->a.N & 1) return fail(h, MADDY_EINVAL, "hydrolysis on the device needs an even n_tot");
+    if ((long long)shards * h->p.n_tr_local != h->p.n_tr || h->p.traj_first % h->p.n_tr_local != 0)
+        return fail(h, MADDY_EINVAL, "hydrolysis plan: %d shard(s) of %d trajectories do not make the ensemble of %d (draw positions are global: "
+                                     "every shard must take part, in equal contiguous blocks)", shards, h->p.n_tr_local, h->p.n_tr);
     if (h->hyd_pending) return fail(h, MADDY_EINVAL, "maddy_hydrolysis_plan: the previous plan's result has not been collected");
+    const int shard = h->p.traj_first / h->p.n_tr_local;
     CU(h, cudaSetDevice(h->p.device));
     const int N = h->a.N, ntr = h->a.ntr, nd = N / 2;
-    const size_t n = (size_t)ntr * N, cells = (size_t)nd * ntr;
+    const size_t n = (size_t)ntr * N, cells_l = (size_t)nd * ntr, cells = cells_l * shards;
     int rc = cls_pair_ready(h);
+    if (!rc) rc = hyd_ready(h);
     if (rc) return rc;
-    if (!h->d_hyd_gt) {
-        CU(h, cudaMalloc(&h->d_hyd_gt, cells));
-        CU(h, cudaMalloc(&h->d_hyd_st, cells));
-        CU(h, cudaMalloc(&h->d_hyd_rowcount, (size_t)nd * sizeof(unsigned)));
-        CU(h, cudaMalloc(&h->d_hyd_rowstart, (size_t)nd * sizeof(unsigned long long)));
-        CU(h, cudaMalloc(&h->d_hyd_window, LFIB_DEG * sizeof(uint32_t)));
-        CU(h, cudaMallocHost(&h->h_hyd_window, LFIB_DEG * sizeof(uint32_t)));
-        CU(h, cudaMalloc(&h->d_lfib_table, sizeof(LfibPoly) * LFIB_POW2));
-        CU(h, cudaMemcpyAsync(h->d_lfib_table, lfib_host_table(), sizeof(LfibPoly) * LFIB_POW2, cudaMemcpyHostToDevice, h->stream));
-        CU(h, cudaMalloc(&h->d_hyd_status, sizeof(int)));
-        CU(h, cudaMallocHost(&h->h_hyd_status, sizeof(int)));
-        CU(h, cudaEventCreateWithFlags(&h->hyd_staged, cudaEventDisableTiming));
-        CU(h, cudaEventCreateWithFlags(&h->hyd_done, cudaEventDisableTiming));
-        CU(h, cudaEventCreateWithFlags(&h->hyd_in, cudaEventDisableTiming));
-        CU(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-        if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (shards > 1 && 2 * cells > h->hyd_all_cap) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaStreamSynchronize(h->aux_stream));
+        if (h->d_hyd_all && h->d_hyd_all != h->d_hyd_own) cudaFree(h->d_hyd_all);
+        h->d_hyd_all = nullptr;
+        h->hyd_all_cap = 0;
+        CU(h, cudaMalloc(&h->d_hyd_all, 2 * cells));
+        h->hyd_all_cap = 2 * cells;
     }
     if (n_events + 1 > h->hyd_counters_cap) {
         CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaStreamSynchronize(h->aux_stream));
         if (h->d_hyd_counters) cudaFree(h->d_hyd_counters);
         if (h->h_hyd_counters) cudaFreeHost(h->h_hyd_counters);
         h->hyd_counters_cap = n_events + 16;
         CU(h, cudaMalloc(&h->d_hyd_counters, (size_t)h->hyd_counters_cap * sizeof(unsigned long long)));
         CU(h, cudaMallocHost(&h->h_hyd_counters, (size_t)h->hyd_counters_cap * sizeof(unsigned long long)));
     }
-    // worst case: every dimer of every trajectory draws at every event
+    // worst case: every dimer of every trajectory of the ENSEMBLE draws at every event
     const unsigned long long need = (unsigned long long)n_events * cells;
     if (need > h->hyd_stream_cap) {
         CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaStreamSynchronize(h->aux_stream));
         if (h->d_hyd_stream) cudaFree(h->d_hyd_stream);
         h->d_hyd_stream = nullptr;
         h->hyd_stream_cap = 0;
@@ -1153,9 +1219,9 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
         while (!((double)v / (double)RAND_MAX < 0.02)) v--;
         return (unsigned)v;
     }();
-    // The kernels run on a stream of their own, behind everything queued so far (classification, GTP state) and beside what
-    // is queued next - the window up to the first event, which needs none of it (the small CTAs fit on the SMs the fused
-    // loop leaves half empty).  The first maddy_run that reaches an event of the plan waits for it.
+    // The kernels run on a stream of their own, behind everything queued so far (classification, GTP state, the gather) and
+    // beside what is queued next - the window up to the first event, which needs none of it (the small CTAs fit on the SMs
+    // the fused loop leaves half empty).  The first maddy_run that reaches an event of the plan waits for it.
     cudaStream_t ax = h->aux_stream;
     CU(h, cudaEventRecord(h->hyd_in, h->stream));
     CU(h, cudaStreamWaitEvent(ax, h->hyd_in, 0));
@@ -1163,28 +1229,15 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
     CU(h, cudaMemcpyAsync(h->d_hyd_window, h->h_hyd_window, LFIB_DEG * sizeof(uint32_t), cudaMemcpyHostToDevice, ax));
     CU(h, cudaMemsetAsync(h->d_hyd_counters, 0, sizeof(unsigned long long), ax));
     CU(h, cudaMemsetAsync(h->d_hyd_status, 0, sizeof(int), ax));
+    uint8_t *work = shards > 1 ? h->d_hyd_all : h->d_hyd_own;
+    if (gathered && gathered != work) CU(h, cudaMemcpyAsync(work, gathered, 2 * cells, cudaMemcpyDeviceToDevice, ax)); // the plan rewrites its copy
     cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_lfib_table, need, h->d_hyd_stream, h->a.guard, ax);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis stream kernel: %s", cudaGetErrorString(e));
-    HydArgs a;
-    a.gtp = h->a.gtp;
-    a.extra = h->a.extra;
-    a.cur = h->d_cls_pair[h->cls_cur];
-    a.prev = h->d_cls_pair[h->cls_cur ^ 1];
-    a.gt = h->d_hyd_gt;
-    a.st = h->d_hyd_st;
-    a.rowcount = h->d_hyd_rowcount;
-    a.rowstart = h->d_hyd_rowstart;
-    a.cursor = h->d_hyd_counters;
-    a.event_start = h->d_hyd_counters + 1;
-    a.stream = h->d_hyd_stream;
+    HydArgs a = hyd_args(h, shards, shard);
+    a.all = work;
     a.stream_count = need;
     a.threshold = threshold;
-    a.status = h->d_hyd_status;
-    a.guard = h->a.guard;
-    a.N = N;
-    a.ntr = ntr;
-    a.nd = nd;
-    e = launch_hyd_plan(a, n_events, h->d_sched_buf[b], ax);
+    e = launch_hyd_plan(a, n_events, h->d_sched_buf[b], gathered != nullptr, ax);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis plan kernels: %s", cudaGetErrorString(e));
     h->launches += 2 + 3LL * n_events; // stream + prepare + (count, scan, apply) per event
     h->sched_cur = b;
@@ -1217,6 +1270,19 @@ extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, 
     h->hyd_events = n_events;
     h->hyd_pending = true;
     return MADDY_OK;
+}
+
+extern "C" int maddy_hydrolysis_plan(maddy_handle *h, const unsigned *window31, long long first_event, long long period, int n_events, unsigned flags)
+{
+    if (h && h->p.n_tr_local != h->p.n_tr)
+        return fail(h, MADDY_EINVAL, "maddy_hydrolysis_plan needs the whole ensemble on one handle (a shard: maddy_hydrolysis_plan_sharded / _all)");
+    return hyd_plan_impl(h, nullptr, 1, window31, first_event, period, n_events, flags);
+}
+extern "C" int maddy_hydrolysis_plan_sharded(maddy_handle *h, const void *gathered_device, int n_shards, const unsigned *window31, long long first_event,
+                                             long long period, int n_events, unsigned flags)
+{
+    if (!gathered_device) return MADDY_EINVAL;
+    return hyd_plan_impl(h, gathered_device, n_shards, window31, first_event, period, n_events, flags);
 }
 
 extern "C" int maddy_hydrolysis_result(maddy_handle *h, unsigned long long *draws_total, unsigned long long *event_first_draw, int *gtp_slots)
@@ -1941,6 +2007,7 @@ struct Nccl {
     int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -1956,6 +2023,7 @@ struct Nccl {
         CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
         GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
@@ -2083,5 +2151,74 @@ extern "C" int maddy_ensemble_stats_end(maddy_handle **hs, int n, double *out16)
         h->ens_pending = false;
     }
     memcpy(out16, hs[0]->h_ens, 16 * sizeof(double)); // every handle holds the same all-reduced record
+    return MADDY_OK;
+}
+
+// communicators for these handles' devices (created once per device set)
+static int nccl_comms_for(maddy_handle **hs, int n)
+{
+    maddy_handle *h0 = hs[0];
+    if (!g_nccl.load() || !g_nccl.AllGather) return fail(h0, MADDY_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+    std::vector<int> devs(n);
+    for (int g = 0; g < n; g++) devs[g] = hs[g]->p.device;
+    if (g_comm_devs != devs) {
+        for (ncclComm_t c : g_comms) g_nccl.CommDestroy(c);
+        g_comms.assign(n, nullptr);
+        int r = g_nccl.CommInitAll(g_comms.data(), n, devs.data());
+        if (r != 0) {
+            g_comms.clear();
+            g_comm_devs.clear();
+            return fail(h0, MADDY_ENCCL, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        }
+        g_comm_devs = devs;
+    }
+    return MADDY_OK;
+}
+
+// The plan of a SHARDED ensemble, all handles in this process (one per GPU, shard order): every shard prepares its transposed
+// inputs, one ncclAllGather (a byte per dimer-trajectory cell and array, once per stride - not per event) hands every GPU the
+// whole ensemble's, and each evaluates the global plan on its own copy, keeping the slots of its own trajectories.  The draws
+// and their order are those of the single-GPU plan and of the reference's host loop.
+extern "C" int maddy_hydrolysis_plan_all(maddy_handle **hs, int n, const unsigned *window31, long long first_event, long long period, int n_events,
+                                         unsigned flags)
+{
+    if (!hs || n <= 0 || !window31) return MADDY_EINVAL;
+    for (int g = 0; g < n; g++)
+        if (!hs[g]) return MADDY_EINVAL;
+    if (n == 1) return maddy_hydrolysis_plan(hs[0], window31, first_event, period, n_events, flags);
+    maddy_handle *h0 = hs[0];
+    int rc = nccl_comms_for(hs, n);
+    if (rc) return rc;
+    const size_t bytes = (size_t)h0->a.N * h0->a.ntr; // per shard: 2 x (N / 2) x n_tr_local
+    for (int g = 0; g < n; g++) {
+        maddy_handle *h = hs[g];
+        if (h->a.ntr != h0->a.ntr || h->a.N != h0->a.N) return fail(h0, MADDY_EINVAL, "maddy_hydrolysis_plan_all: the shards must be equal blocks");
+        void *own = nullptr;
+        rc = maddy_hydrolysis_inputs(h, &own, nullptr);
+        if (rc) return rc;
+        CU(h, cudaSetDevice(h->p.device));
+        if ((size_t)n * bytes > h->hyd_all_cap) {
+            CU(h, cudaStreamSynchronize(h->stream));
+            CU(h, cudaStreamSynchronize(h->aux_stream));
+            if (h->d_hyd_all) cudaFree(h->d_hyd_all);
+            h->d_hyd_all = nullptr;
+            h->hyd_all_cap = 0;
+            CU(h, cudaMalloc(&h->d_hyd_all, (size_t)n * bytes));
+            h->hyd_all_cap = (size_t)n * bytes;
+        }
+    }
+    g_nccl.GroupStart();
+    int rr = 0;
+    for (int g = 0; g < n; g++) {
+        cudaSetDevice(hs[g]->p.device);
+        int r = g_nccl.AllGather(hs[g]->d_hyd_own, hs[g]->d_hyd_all, bytes, /*ncclUint8*/ 1, g_comms[g], hs[g]->stream);
+        if (r) rr = r;
+    }
+    int r2 = g_nccl.GroupEnd();
+    if (rr || r2) return fail(h0, MADDY_ENCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rr ? rr : r2) : "error");
+    for (int g = 0; g < n; g++) {
+        rc = hyd_plan_impl(hs[g], hs[g]->d_hyd_all, n, window31, first_event, period, n_events, flags);
+        if (rc) return rc;
+    }
     return MADDY_OK;
 }

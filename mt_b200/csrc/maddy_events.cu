@@ -45,19 +45,28 @@ __global__ void __launch_bounds__(64) hyd_stream_kernel(const uint32_t *__restri
     }
 }
 
-// transposed working set of a plan: rows = dimers, columns = trajectories (the reference's loop order)
+// The plan's working set: rows = dimers, columns = trajectories in GLOBAL order (the reference's loop order).  A sharded
+// ensemble gathers every shard's block (contiguous trajectories) and each shard evaluates the whole plan on its own copy:
+// the draw positions are global, the slots it writes are those of its own trajectories.
+__device__ __forceinline__ size_t hyd_cell(const HydArgs &h, int which, int d, int tr)
+{
+    const int g = tr / h.ntr_l, tl = tr - g * h.ntr_l;
+    return (((size_t)g * 2 + which) * h.nd + d) * h.ntr_l + tl;
+}
+
+// transposed inputs of this shard: rows = dimers, columns = its trajectories
 //   gt[d][tr]  GTP state of the dimer's first monomer as the events go by (1 / 0 / other)
 //   st[d][tr]  bit 0: can hydrolyse (not reserve, on the tubule now and before)   bit 1: returns to GTP (not reserve, off both)
 __global__ void __launch_bounds__(256) hyd_prepare_kernel(HydArgs h)
 {
     if (*h.guard) return;
-    const size_t cells = (size_t)h.nd * h.ntr;
+    const size_t cells = (size_t)h.nd * h.ntr_l;
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
-        const int d = (int)(c / h.ntr), tr = (int)(c % h.ntr);
+        const int d = (int)(c / h.ntr_l), tr = (int)(c % h.ntr_l);
         const size_t q = (size_t)tr * h.N + 2 * d;
         const bool ex = h.extra[q] != 0, cur = h.cur[q] != 0, prev = h.prev[q] != 0;
-        h.gt[c] = h.gtp[q];
-        h.st[c] = (uint8_t)((!ex && cur && prev ? 1 : 0) | (!ex && !cur && !prev ? 2 : 0));
+        h.own[c] = h.gtp[q];
+        h.own[cells + c] = (uint8_t)((!ex && cur && prev ? 1 : 0) | (!ex && !cur && !prev ? 2 : 0));
     }
 }
 
@@ -67,9 +76,8 @@ __global__ void __launch_bounds__(128) hyd_count_kernel(HydArgs h)
     __shared__ unsigned wsum[4];
     if (*h.guard) return;
     const int d = blockIdx.x;
-    const uint8_t *gt = h.gt + (size_t)d * h.ntr, *st = h.st + (size_t)d * h.ntr;
     unsigned c = 0;
-    for (int tr = threadIdx.x; tr < h.ntr; tr += blockDim.x) c += gt[tr] == 1 && (st[tr] & 1);
+    for (int tr = threadIdx.x; tr < h.ntr; tr += blockDim.x) c += h.all[hyd_cell(h, 0, d, tr)] == 1 && (h.all[hyd_cell(h, 1, d, tr)] & 1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
@@ -121,14 +129,14 @@ __global__ void __launch_bounds__(1024) hyd_scan_kernel(HydArgs h, int event)
 // one event, one dimer row, one warp: the trajectories in order (ballot prefix = position in the stream)
 __device__ __forceinline__ void hyd_apply_row(const HydArgs &h, int d, unsigned long long pos, uint8_t *__restrict__ slot, int lane)
 {
-    uint8_t *gt = h.gt + (size_t)d * h.ntr;
-    const uint8_t *st = h.st + (size_t)d * h.ntr;
     const unsigned lt = (1u << lane) - 1u;
+    const int own_lo = h.shard * h.ntr_l;
     for (int t0 = 0; t0 < h.ntr; t0 += 32) {
         const int tr = t0 + lane;
         const bool in = tr < h.ntr;
-        uint8_t g = in ? gt[tr] : (uint8_t)2;
-        const uint8_t s = in ? st[tr] : (uint8_t)0;
+        const size_t cg = in ? hyd_cell(h, 0, d, tr) : 0;
+        uint8_t g = in ? h.all[cg] : (uint8_t)2;
+        const uint8_t s = in ? h.all[hyd_cell(h, 1, d, tr)] : (uint8_t)0;
         const bool elig = g == 1 && (s & 1);
         const unsigned bl = __ballot_sync(0xffffffffu, elig);
         if (elig) {
@@ -142,9 +150,10 @@ __device__ __forceinline__ void hyd_apply_row(const HydArgs &h, int d, unsigned 
         pos += __popc(bl);
         if (g == 0 && (s & 2)) g = 1; // off the tubule now and before: back to GTP (updater.cpp:246-254), no draw
         if (in) {
-            gt[tr] = g;
-            // both monomers of the dimer (2 d is even and N is even: the pair is 2-byte aligned)
-            *reinterpret_cast<uint16_t *>(slot + (size_t)tr * h.N + 2 * d) = (uint16_t)(g | (g << 8));
+            h.all[cg] = g;
+            // this shard's trajectories: both monomers of the dimer (2 d is even and N is even: the pair is 2-byte aligned)
+            const int tl = tr - own_lo;
+            if (tl >= 0 && tl < h.ntr_l) *reinterpret_cast<uint16_t *>(slot + (size_t)tl * h.N + 2 * d) = (uint16_t)(g | (g << 8));
         }
     }
 }
@@ -167,22 +176,22 @@ __global__ void __launch_bounds__(1024) hyd_plan_fused_kernel(HydArgs h, int n_e
     __shared__ unsigned s_total;
     if (*h.guard) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t cells = (size_t)h.nd * h.ntr;
+    // (one shard only: the inputs were not gathered, this kernel prepares them itself)
+    const size_t cells = (size_t)h.nd * h.ntr_l;
     for (size_t c = tid; c < cells; c += 1024) {
-        const int d = (int)(c / h.ntr), tr = (int)(c % h.ntr);
+        const int d = (int)(c / h.ntr_l), tr = (int)(c % h.ntr_l);
         const size_t q = (size_t)tr * h.N + 2 * d;
         const bool ex = h.extra[q] != 0, cur = h.cur[q] != 0, prev = h.prev[q] != 0;
-        h.gt[c] = h.gtp[q];
-        h.st[c] = (uint8_t)((!ex && cur && prev ? 1 : 0) | (!ex && !cur && !prev ? 2 : 0));
+        h.own[c] = h.gtp[q];
+        h.own[cells + c] = (uint8_t)((!ex && cur && prev ? 1 : 0) | (!ex && !cur && !prev ? 2 : 0));
     }
     __syncthreads();
     unsigned long long cursor = 0;
     const int per = (h.nd + 1023) / 1024;
     for (int k = 0; k < n_events; k++) {
         for (int d = warp; d < h.nd; d += 32) { // draws of this event per row
-            const uint8_t *gt = h.gt + (size_t)d * h.ntr, *st = h.st + (size_t)d * h.ntr;
             unsigned c = 0;
-            for (int tr = lane; tr < h.ntr; tr += 32) c += gt[tr] == 1 && (st[tr] & 1);
+            for (int tr = lane; tr < h.ntr; tr += 32) c += h.all[hyd_cell(h, 0, d, tr)] == 1 && (h.all[hyd_cell(h, 1, d, tr)] & 1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
             if (lane == 0) s_row[d] = c;
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(1024) hyd_plan_fused_kernel(HydArgs h, int n_e
             }
         }
         __syncthreads();
-        for (int d = warp; d < h.nd; d += 32) hyd_apply_row(h, d, cursor + s_row[d], slots + (size_t)k * h.ntr * h.N, lane);
+        for (int d = warp; d < h.nd; d += 32) hyd_apply_row(h, d, cursor + s_row[d], slots + (size_t)k * h.ntr_l * h.N, lane);
         if (tid == 0) h.event_start[k] = cursor;
         cursor += s_total;
         __syncthreads();
@@ -236,23 +245,35 @@ cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned lon
     return cudaGetLastError();
 }
 
-// all events of a plan, slot k of `slots` ([n_events][ntr * N] bytes) = GTP state after event k
-cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, cudaStream_t st)
+// this shard's transposed inputs (h.own), for the gather of a sharded ensemble
+cudaError_t launch_hyd_prepare(const HydArgs &h, cudaStream_t st)
+{
+    const size_t cells = (size_t)h.nd * h.ntr_l;
+    int pb = (int)((cells + 255) / 256);
+    if (pb > 148 * 8) pb = 148 * 8;
+    hyd_prepare_kernel<<<pb, 256, 0, st>>>(h);
+    return cudaGetLastError();
+}
+
+// all events of a plan on h.all (prepared / gathered by the caller when `prepared`), slot k of `slots` ([n_events][ntr_l * N]
+// bytes) = GTP state of THIS shard's trajectories after event k
+cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, bool prepared, cudaStream_t st)
 {
     const size_t cells = (size_t)h.nd * h.ntr;
     // (one CTA is latency-bound on its dependent loads: 1.3 ms per plan at 260 x 256 against 0.18 ms for the per-event
     // launches below; kept for very small ensembles, where the launches dominate)
-    if (cells <= 4096 && h.nd <= 8192 && !getenv("MADDY_HYD_PER_EVENT_KERNELS")) {
+    if (!prepared && h.shards == 1 && cells <= 4096 && h.nd <= 8192 && !getenv("MADDY_HYD_PER_EVENT_KERNELS")) {
         hyd_plan_fused_kernel<<<1, 1024, (size_t)h.nd * sizeof(unsigned), st>>>(h, n_events, slots);
         return cudaGetLastError();
     }
-    int pb = (int)((cells + 255) / 256);
-    if (pb > 148 * 8) pb = 148 * 8;
-    hyd_prepare_kernel<<<pb, 256, 0, st>>>(h);
+    if (!prepared) {
+        cudaError_t e = launch_hyd_prepare(h, st);
+        if (e != cudaSuccess) return e;
+    }
     for (int k = 0; k < n_events; k++) {
         hyd_count_kernel<<<h.nd, 128, 0, st>>>(h);
         hyd_scan_kernel<<<1, 1024, 0, st>>>(h, k);
-        hyd_apply_kernel<<<(h.nd + 3) / 4, 128, 0, st>>>(h, slots + (size_t)k * h.ntr * h.N);
+        hyd_apply_kernel<<<(h.nd + 3) / 4, 128, 0, st>>>(h, slots + (size_t)k * h.ntr_l * h.N);
     }
     return cudaGetLastError();
 }

@@ -147,7 +147,9 @@ struct OnTubRule {
 // hydrolysis events of one stride on the device (maddy_events.cu)
 struct HydArgs {
     const uint8_t *gtp, *extra, *cur, *prev; // [ntr * N]: GTP state at the stride, reserve flags, on-tubule flags now / previous stride
-    uint8_t *gt, *st;                        // [nd][ntr] transposed working set (see hyd_prepare_kernel)
+    uint8_t *own;                            // [2][nd][ntr_l] this shard's transposed inputs: GTP state, then static mask (hyd_prepare_kernel)
+    uint8_t *all;                            // [shards][2][nd][ntr_l] the inputs of EVERY shard (== own for one shard); the plan works on this copy
+    int ntr_l, shards, shard;                // trajectories per shard, number of shards, this shard: ntr = shards * ntr_l is the GLOBAL count
     unsigned *rowcount;                      // [nd] draws of the current event per dimer row
     unsigned long long *rowstart;            // [nd] index of each row's first draw in the plan's stream
     unsigned long long *cursor;              // [1] draws consumed so far by the plan

@@ -510,13 +510,16 @@ void compute(System &s, bool fused, ComputeStats *stats)
     // The next window waits for the Ntr counts (not the coordinates) where the host needs them first: for the insertions of
     // constant concentration, and with several shards whose flags feed back into the forces (a shard cannot run ahead on a
     // classification another shard could not decide).
-    const bool counts_first = overlap_stride && dev_classify && ((hp.is_const_conc && hp.tub_length) || (feedback && G > 1));
+    const bool hyd_possible = overlap_stride && dev_classify && hp.hydrolysis && hp.hydrostep > 0 && Ntr % G == 0 && N % 2 == 0 &&
+                              !getenv("MADDY_HOST_HYDROLYSIS");
+    const bool counts_first = overlap_stride && dev_classify && ((hp.is_const_conc && hp.tub_length) || ((feedback || hyd_possible) && G > 1));
     // hydrolyse() itself runs on the device when ONE handle holds the ensemble (draw positions are global): right after a
     // stride block every event up to the next stride step is evaluated in one go (maddy_hydrolysis_plan) from the 31 words
     // of the host generator and left as the GTP schedule of the fused loop - a window then spans the whole stride and the
     // host only advances its generator by the number of draws the device reports.  May be switched off mid-run (a
     // classification the device could not decide): the host then carries on from the synchronised state.
-    bool hyd_dev = overlap_stride && dev_classify && hp.hydrolysis && hp.hydrostep > 0 && G == 1 && N % 2 == 0 && !getenv("MADDY_HOST_HYDROLYSIS");
+    // With several shards every GPU evaluates the ensemble's plan from the gathered inputs (maddy_hydrolysis_plan_all).
+    bool hyd_dev = hyd_possible;
     // Everywhere else nothing is waited for: plan and window are queued right behind the snapshot, GUARDED - should the device
     // be unable to decide a classification, they return without touching the state and the host redoes the stride itself.
     const bool guarded = overlap_stride && dev_classify && !counts_first && G == 1 && (feedback || hyd_dev);
@@ -531,11 +534,18 @@ void compute(System &s, bool fused, ComputeStats *stats)
     auto collect_plan = [&] {
         if (!plan_pending) return;
         plan_pending = false;
-        Shard &d = sh.v[0];
         unsigned long long total = 0;
-        std::vector<int> slots;
+        std::vector<int> slots; // [event][global monomer]
         if (!s.quiet) slots.resize((size_t)plan_events * n);
-        ck(maddy_hydrolysis_result(d.h, &total, nullptr, s.quiet ? nullptr : slots.data()), d.h, "maddy_hydrolysis_result");
+        for_each([&](Shard &d) {
+            const size_t cnt = (size_t)d.count * N, off = (size_t)d.first * N;
+            std::vector<int> part;
+            if (!s.quiet) part.resize((size_t)plan_events * cnt);
+            unsigned long long t = 0;
+            ck(maddy_hydrolysis_result(d.h, &t, nullptr, s.quiet ? nullptr : part.data()), d.h, "maddy_hydrolysis_result");
+            total = t; // the ensemble's, identical on every shard
+            for (int k = 0; k < plan_events && !s.quiet; k++) memcpy(&slots[(size_t)k * n + off], &part[(size_t)k * cnt], cnt * sizeof(int));
+        });
         s.rng.discard(total);
         st.d2h_bytes += 8.0 * (plan_events + 1) + (s.quiet ? 0.0 : (double)plan_events * n);
         if (s.quiet) return;
@@ -555,10 +565,11 @@ void compute(System &s, bool fused, ComputeStats *stats)
     };
     // the GTP flags as they stand on the device (hyd_dev mode keeps s.gtp current only at strides)
     auto download_gtp = [&] {
-        Shard &d = sh.v[0];
-        ck(maddy_snapshot_begin(d.h, MADDY_SNAP_GTP), d.h, "maddy_snapshot_begin");
-        ck(maddy_snapshot_end(d.h, nullptr, nullptr, nullptr), d.h, "maddy_snapshot_end");
-        ck(maddy_snapshot_gtp(d.h, s.gtp.data()), d.h, "maddy_snapshot_gtp");
+        for_each([&](Shard &d) {
+            ck(maddy_snapshot_begin(d.h, MADDY_SNAP_GTP), d.h, "maddy_snapshot_begin");
+            ck(maddy_snapshot_end(d.h, nullptr, nullptr, nullptr), d.h, "maddy_snapshot_end");
+            ck(maddy_snapshot_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_snapshot_gtp");
+        });
         st.d2h_bytes += (double)n;
     };
     int pending_output = 0; // an overlapped stride whose update() is still to be written
@@ -600,7 +611,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
             if (pending_snapshot_open) die("checkpoint at step %lld with a snapshot in flight", at);
             collect_plan();
             if (plan_covers(at)) {
-                ck(maddy_apply_scheduled_gtp(sh.v[0].h, at), sh.v[0].h, "maddy_apply_scheduled_gtp");
+                for_each([&](Shard &d) { ck(maddy_apply_scheduled_gtp(d.h, at), d.h, "maddy_apply_scheduled_gtp"); });
                 hydrolysed_for = at;
             }
             download_gtp();
@@ -712,7 +723,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         if (hyd_dev && hp.hydrolysis && step % hp.hydrostep == 0 && step != 0 && plan_covers(step)) {
             // evaluated on the device at the last stride; inside a window the fused loop applies the slot itself, at a
             // stride step it has to be current before the stride block evaluates the energies
-            if (stride_now) ck(maddy_apply_scheduled_gtp(sh.v[0].h, step), sh.v[0].h, "maddy_apply_scheduled_gtp");
+            if (stride_now) for_each([&](Shard &d) { ck(maddy_apply_scheduled_gtp(d.h, step), d.h, "maddy_apply_scheduled_gtp"); });
             hydrolysed_for = step;
         } else if (hp.hydrolysis && step % hp.hydrostep == 0 && step != 0) {
             if (!sched_gtp.empty() && sched_first == step) {
@@ -788,6 +799,15 @@ void compute(System &s, bool fused, ComputeStats *stats)
             if (hp.out_energy) ens_begin();
             st.d2h_bytes += (double)n * 32 + (hp.out_energy ? (double)Ntr * 7 * 8 : 0.0) + (classify || classify0 ? (double)n + 4.0 * Ntr : 0.0) +
                             (hyd_dev ? (double)n : 0.0);
+            if (classify0 && !guarded) { // several shards: nobody runs ahead of a classification that may be undecided
+                int undecided = 0;
+                for_each([&](Shard &d) {
+                    int u = 0;
+                    ck(maddy_snapshot_tubule_lengths(d.h, nullptr, &u), d.h, "maddy_snapshot_tubule_lengths");
+                    undecided |= u;
+                });
+                if (undecided) hyd_dev = false; // s.gtp and the generator are still the host's own
+            }
             if (classify && counts_first) {
                 // What the host derives from this stride feeds back into the next forces (non-zero barrier: the flags, already
                 // applied on the device; constant concentration: the insertions).  Only the Ntr counts are waited for.
@@ -803,7 +823,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
                     collect();
                     collected = true;
                     if (hyd_dev) { // ... and hydrolysis returns to the host for the rest of the run, from the synchronised state
-                        ck(maddy_snapshot_gtp(sh.v[0].h, s.gtp.data()), sh.v[0].h, "maddy_snapshot_gtp");
+                        for_each([&](Shard &d) { ck(maddy_snapshot_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_snapshot_gtp"); });
                         hyd_dev = false;
                         plan_events = 0;
                     }
@@ -841,7 +861,8 @@ void compute(System &s, bool fused, ComputeStats *stats)
                 if (plan_events > 0) {
                     uint32_t w[31];
                     s.rng.window(w);
-                    ck(maddy_hydrolysis_plan(sh.v[0].h, w, first, h, plan_events, s.quiet ? 0u : MADDY_HYD_KEEP_SLOTS), sh.v[0].h, "maddy_hydrolysis_plan");
+                    int rcp = maddy_hydrolysis_plan_all(ens_handles.data(), G, w, first, h, plan_events, s.quiet ? 0u : MADDY_HYD_KEEP_SLOTS);
+                    if (rcp != MADDY_OK) die("maddy_hydrolysis_plan_all failed (%d): %s", rcp, maddy_last_error(ens_handles[0]));
                     plan_pending = true;
                     st.h2d_bytes += 124.0;
                     mark("hydrolysis plan queued", step);
@@ -869,7 +890,7 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.end("stride block");
         prof.begin();
         // ---- steps up to the next host event
-        long long next = hp.steps, count = 0;
+        long long next = hp.steps, count = 0, split_at = 0;
         const bool stepwise = !fused; // TEA windows are queued by maddy_run as well (force + prepare in one launch)
         const bool hydro = hp.hydrolysis && hp.hydrostep > 0;
         auto window_end = [&] {
@@ -881,8 +902,9 @@ void compute(System &s, bool fused, ComputeStats *stats)
         // first of them: the plan queued with the stride block is evaluated on a stream of its own BESIDE that window, and
         // the next one - which runs to the next stride step - waits for it.
         const long long first_event = (step / hp.hydrostep + 1) * (long long)hp.hydrostep;
+        split_at = 0;
         if (hydro && hyd_dev && plan_covers(first_event)) {
-            if (stride_now) next = std::min(next, first_event);
+            if (stride_now && first_event < next) split_at = first_event; // both windows are queued now: the host's stride output must not delay the second
         } else if (hydro) {
             next = std::min(next, scheduled_end > step ? scheduled_end : first_event);
         }
@@ -906,7 +928,16 @@ void compute(System &s, bool fused, ComputeStats *stats)
                 });
             }
         } else {
-            for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, explicit_rebuild ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u), d.h, "maddy_run"); });
+            auto launch_windows = [&] {
+                const unsigned fl = explicit_rebuild ? MADDY_RUN_SKIP_FIRST_REBUILD : 0u;
+                if (split_at > step) {
+                    for_each([&](Shard &d) { ck(maddy_run(d.h, step, split_at - step, fl), d.h, "maddy_run"); });
+                    for_each([&](Shard &d) { ck(maddy_run(d.h, split_at, next - split_at, 0u), d.h, "maddy_run"); });
+                } else {
+                    for_each([&](Shard &d) { ck(maddy_run(d.h, step, count, fl), d.h, "maddy_run"); });
+                }
+            };
+            launch_windows();
             mark("window launched", step);
         }
         prof.end("launch window");
@@ -921,7 +952,8 @@ void compute(System &s, bool fused, ComputeStats *stats)
         prof.begin();
         if (overlapped && !collected) {
             collect();
-            if (hyd_dev) ck(maddy_snapshot_gtp(sh.v[0].h, s.gtp.data()), sh.v[0].h, "maddy_snapshot_gtp"); // state after the event of this step, if any
+            if (hyd_dev) // state after the event of this step, if any
+                for_each([&](Shard &d) { ck(maddy_snapshot_gtp(d.h, &s.gtp[(size_t)d.first * N]), d.h, "maddy_snapshot_gtp"); });
             prof.end("stride collect (wait + transpose)");
             mark("snapshot collected", step);
             prof.begin();

@@ -58,3 +58,20 @@ def test_ensemble_stats_two_gpus_equal_host_statistics(rundir, load_system):
     assert st is not None and st[14] == 6
     assert np.allclose(st[:7], e.sum(axis=0), rtol=1e-13, atol=1e-9)
     assert np.allclose(st[7:14], (e * e).sum(axis=0), rtol=1e-13, atol=1e-9)
+
+
+def test_sharded_device_hydrolysis_equals_single_gpu(rundir, load_system):
+    """Equal shards: every GPU evaluates the ensemble's hydrolysis plan from the all-gathered inputs (maddy_hydrolysis_plan_all)
+    - same draws in the same global order as the single-GPU plan: state, GTP flags, energies and the host generator agree."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = rundir("mt40_ensemble", runnum=6, steps=450, stride=200)
+    out = []
+    for g in (1, 2):
+        s = load_system(d)
+        s.srand(1234567)
+        s.compute(n_gpus=g)
+        out.append((np.array(s.coords).copy(), np.array(s.gtp).copy(), np.array(s.energies).copy(), np.array(s.on_tubule_cur).copy(), s.rand_next()))
+    a, b = out
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and a[4] == b[4]
+    assert (a[1] == 0).any()  # some dimers were hydrolysed
