@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <thread>
 #include <mutex>
+#include <future>
 #include <memory>
 #include <dlfcn.h>
 #include <math.h>
@@ -551,6 +552,23 @@ extern "C" int maddy_upload_list(maddy_handle *h, int kind, const int *counts, c
 static bool make_ontub_rule(OnTubRule &r);
 static int cls_pair_ready(maddy_handle *h);
 
+// The HybridTaus seed table of an ensemble (HybridTaus.cu:21-48): ran2 is sequential (9 ns per draw, 10 ms at 520 x 256), so
+// the table is generated once per process and ensemble - not once per shard - and on a thread of its own while
+// maddy_create allocates and uploads.
+static std::shared_ptr<std::vector<unsigned>> seed_table(int rseed, long long np)
+{
+    static std::mutex seed_mutex;
+    static std::shared_ptr<std::vector<unsigned>> seed_cache;
+    static int seed_cache_rseed = 0;
+    std::lock_guard<std::mutex> lock(seed_mutex);
+    if (!seed_cache || seed_cache_rseed != rseed || (long long)seed_cache->size() != np * 4) {
+        seed_cache = std::make_shared<std::vector<unsigned>>((size_t)np * 4);
+        maddy_generate_seeds(seed_cache->data(), rseed, np);
+        seed_cache_rseed = rseed;
+    }
+    return seed_cache;
+}
+
 extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, const float *coords, void *stream,
                             maddy_handle **out)
 {
@@ -580,6 +598,8 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (par->device < 0 || par->device >= ndev) return fail(nullptr, MADDY_EINVAL, "maddy_create: device %d of %d", par->device, ndev);
 
+    std::future<std::shared_ptr<std::vector<unsigned>>> seed_future =
+        std::async(std::launch::async, seed_table, par->rseed, 2LL * N * par->n_tr);
     maddy_handle *h = new maddy_handle;
     h->p = *par;
     int rc = MADDY_OK;
@@ -816,21 +836,8 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
 
         // RNG: the GLOBAL table of 2*Ntot*Ntr states, sliced (HybridTaus.cu:21-31, compute_cuda.cu:1097)
         {
-            // (ran2 is sequential: the table is generated once per process and ensemble, not once per shard)
-            const long long np = 2LL * N * par->n_tr;
-            static std::mutex seed_mutex;
-            static std::shared_ptr<std::vector<unsigned>> seed_cache;
-            static int seed_cache_rseed = 0;
-            std::shared_ptr<std::vector<unsigned>> table;
-            {
-                std::lock_guard<std::mutex> lock(seed_mutex);
-                if (!seed_cache || seed_cache_rseed != par->rseed || (long long)seed_cache->size() != np * 4) {
-                    seed_cache = std::make_shared<std::vector<unsigned>>((size_t)np * 4);
-                    maddy_generate_seeds(seed_cache->data(), par->rseed, np);
-                    seed_cache_rseed = par->rseed;
-                }
-                table = seed_cache;
-            }
+            // (generated beside the allocations and uploads above: seed_future, started at the top of maddy_create)
+            std::shared_ptr<std::vector<unsigned>> table = seed_future.get();
             const std::vector<unsigned> &seeds = *table;
             const size_t off_xyz = (size_t)par->traj_first * N;
             const size_t off_ang = (size_t)N * par->n_tr + off_xyz;
