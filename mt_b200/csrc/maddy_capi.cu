@@ -34,7 +34,10 @@ cudaError_t launch_snapshot_kernel(const float4 *pos, const float4 *ang, float *
 cudaError_t launch_consts_kernel(const maddy_params &p, StepConsts *d_out, cudaStream_t st);
 cudaError_t launch_tea_kernels(const KArgs &k, int which, long long step, cudaStream_t st);
 int tea_partner_segments(int N);
-cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, const int *guard, cudaStream_t st);
+cudaError_t launch_hyd_stream(const uint32_t *W, const void *mats, unsigned long long count, uint32_t *out, const int *guard, cudaStream_t st);
+cudaError_t launch_hyd_matrices(const void *table, void *mats, cudaStream_t st);
+size_t hyd_matrices_bytes();
+unsigned long long hyd_stream_capacity();
 cudaError_t launch_hyd_prepare(const HydArgs &h, cudaStream_t st);
 cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, bool prepared, cudaStream_t st);
 cudaError_t launch_wide_publish(const KArgs &k, int buf, cudaStream_t st);
@@ -147,7 +150,8 @@ struct maddy_handle {
     int hyd_counters_cap = 0;
     uint32_t *d_hyd_stream = nullptr, *d_hyd_window = nullptr, *h_hyd_window = nullptr;
     unsigned long long hyd_stream_cap = 0;
-    void *d_lfib_table = nullptr;
+    void *d_lfib_table = nullptr, *d_hyd_mats = nullptr;
+    int hyd_rows_cap = 0;
     int *d_hyd_status = nullptr, *h_hyd_status = nullptr;
     uint8_t *h_hyd_slots = nullptr;
     size_t hyd_slots_cap = 0;
@@ -516,7 +520,7 @@ extern "C" int maddy_destroy(maddy_handle *h)
     if (h->snap_done) cudaEventDestroy(h->snap_done);
     if (h->snap_staged) cudaEventDestroy(h->snap_staged);
     for (void *q : {(void *)h->d_cls_pair[0], (void *)h->d_cls_pair[1], (void *)h->d_snap_gtp, (void *)h->d_hyd_own, (void *)(h->d_hyd_all != h->d_hyd_own ? h->d_hyd_all : nullptr), (void *)h->d_hyd_rowcount,
-                    (void *)h->d_hyd_rowstart, (void *)h->d_hyd_counters, (void *)h->d_hyd_stream, (void *)h->d_hyd_window, h->d_lfib_table,
+                    (void *)h->d_hyd_rowstart, (void *)h->d_hyd_counters, (void *)h->d_hyd_stream, (void *)h->d_hyd_window, h->d_lfib_table, h->d_hyd_mats,
                     (void *)h->d_hyd_status})
         if (q) cudaFree(q);
     for (void *q : {(void *)h->h_snap_gtp, (void *)h->h_hyd_counters, (void *)h->h_hyd_window, (void *)h->h_hyd_status, (void *)h->h_hyd_slots})
@@ -1112,12 +1116,15 @@ static int hyd_ready(maddy_handle *h)
     const int nd = h->a.N / 2;
     const size_t cells = (size_t)nd * h->a.ntr;
     CU(h, cudaMalloc(&h->d_hyd_own, 2 * cells));
-    CU(h, cudaMalloc(&h->d_hyd_rowcount, (size_t)nd * sizeof(unsigned)));
-    CU(h, cudaMalloc(&h->d_hyd_rowstart, (size_t)nd * sizeof(unsigned long long)));
     CU(h, cudaMalloc(&h->d_hyd_window, LFIB_DEG * sizeof(uint32_t)));
     CU(h, cudaMallocHost(&h->h_hyd_window, LFIB_DEG * sizeof(uint32_t)));
     CU(h, cudaMalloc(&h->d_lfib_table, sizeof(LfibPoly) * LFIB_POW2));
     CU(h, cudaMemcpyAsync(h->d_lfib_table, lfib_host_table(), sizeof(LfibPoly) * LFIB_POW2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMalloc(&h->d_hyd_mats, hyd_matrices_bytes()));
+    {
+        cudaError_t e = launch_hyd_matrices(h->d_lfib_table, h->d_hyd_mats, h->stream); // once per handle
+        if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis jump matrices: %s", cudaGetErrorString(e));
+    }
     CU(h, cudaMalloc(&h->d_hyd_status, sizeof(int)));
     CU(h, cudaMallocHost(&h->h_hyd_status, sizeof(int)));
     CU(h, cudaEventCreateWithFlags(&h->hyd_staged, cudaEventDisableTiming));
@@ -1150,6 +1157,9 @@ static HydArgs hyd_args(maddy_handle *h, int shards, int shard)
     a.shards = shards;
     a.shard = shard;
     a.ntr = shards * h->a.ntr;
+    a.seg = a.ntr < 256 ? a.ntr : 256; // a warp takes 256 trajectories of a dimer row (8 rounds), whatever the ensemble's size
+    a.nseg = (a.ntr + a.seg - 1) / a.seg;
+    a.nrows = a.nd * a.nseg;
     return a;
 }
 
@@ -1204,8 +1214,24 @@ static int hyd_plan_impl(maddy_handle *h, const void *gathered, int shards, cons
         CU(h, cudaMalloc(&h->d_hyd_counters, (size_t)h->hyd_counters_cap * sizeof(unsigned long long)));
         CU(h, cudaMallocHost(&h->h_hyd_counters, (size_t)h->hyd_counters_cap * sizeof(unsigned long long)));
     }
+    {
+        const HydArgs probe = hyd_args(h, shards, shard);
+        if (probe.nrows > h->hyd_rows_cap) {
+            CU(h, cudaStreamSynchronize(h->stream));
+            CU(h, cudaStreamSynchronize(h->aux_stream));
+            if (h->d_hyd_rowcount) cudaFree(h->d_hyd_rowcount);
+            if (h->d_hyd_rowstart) cudaFree(h->d_hyd_rowstart);
+            h->d_hyd_rowcount = nullptr;
+            h->d_hyd_rowstart = nullptr;
+            h->hyd_rows_cap = 0;
+            CU(h, cudaMalloc(&h->d_hyd_rowcount, (size_t)probe.nrows * sizeof(unsigned)));
+            CU(h, cudaMalloc(&h->d_hyd_rowstart, (size_t)probe.nrows * sizeof(unsigned long long)));
+            h->hyd_rows_cap = probe.nrows;
+        }
+    }
     // worst case: every dimer of every trajectory of the ENSEMBLE draws at every event
     const unsigned long long need = (unsigned long long)n_events * cells;
+    if (need > hyd_stream_capacity()) return fail(h, MADDY_EINVAL, "hydrolysis plan: %llu draws exceed the stream kernel's range", need);
     if (need > h->hyd_stream_cap) {
         CU(h, cudaStreamSynchronize(h->stream));
         CU(h, cudaStreamSynchronize(h->aux_stream));
@@ -1238,7 +1264,7 @@ static int hyd_plan_impl(maddy_handle *h, const void *gathered, int shards, cons
     CU(h, cudaMemsetAsync(h->d_hyd_status, 0, sizeof(int), ax));
     uint8_t *work = shards > 1 ? h->d_hyd_all : h->d_hyd_own;
     if (gathered && gathered != work) CU(h, cudaMemcpyAsync(work, gathered, 2 * cells, cudaMemcpyDeviceToDevice, ax)); // the plan rewrites its copy
-    cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_lfib_table, need, h->d_hyd_stream, h->a.guard, ax);
+    cudaError_t e = launch_hyd_stream(h->d_hyd_window, h->d_hyd_mats, need, h->d_hyd_stream, h->a.guard, ax);
     if (e != cudaSuccess) return fail(h, MADDY_ECUDA, "hydrolysis stream kernel: %s", cudaGetErrorString(e));
     HydArgs a = hyd_args(h, shards, shard);
     a.all = work;

@@ -21,19 +21,58 @@
 
 namespace maddy {
 
-#define HYD_ROUNDS 4                        // rounds of 31 draws per thread of the stream kernel
-#define HYD_PER_THREAD (31 * HYD_ROUNDS)    // 124
+#define HYD_ROUNDS 8                        // rounds of 31 draws per thread of the stream kernel
+#define HYD_PER_THREAD (31 * HYD_ROUNDS)    // 248
+#define HYD_RADIX 32                        // thread t = (a * 32 + b) * 32 + c starts at draw t * HYD_PER_THREAD
+#define HYD_TOP 256                         // values of a: streams of up to 256 * 1024 * 248 = 65 M draws per plan
+
+// Jump matrices, made once per handle: level 0 holds the offsets c * B, level 1 b * 32 B, level 2 a * 1024 B (B =
+// HYD_PER_THREAD); row i of a matrix = coefficients of z^(offset + i) mod p, so that (M w)[i] = x[offset + i] for the
+// window w.  A thread of the stream kernel then reaches ITS window with three 31 x 31 matrix-vector products instead
+// of ~20 polynomial products (the jump was 8/9 of the stream kernel's instructions).
+__global__ void __launch_bounds__(32) hyd_matrices_kernel(const LfibPoly *__restrict__ table, uint32_t *__restrict__ mats)
+{
+    const int m = blockIdx.x, i = threadIdx.x; // matrix, row
+    if (i >= LFIB_DEG) return;
+    const int level = m < HYD_RADIX ? 0 : (m < 2 * HYD_RADIX ? 1 : 2);
+    const unsigned long long j = level == 0 ? m : (level == 1 ? m - HYD_RADIX : m - 2 * HYD_RADIX);
+    const unsigned long long unit = level == 0 ? HYD_PER_THREAD : (level == 1 ? (unsigned long long)HYD_RADIX * HYD_PER_THREAD
+                                                                               : (unsigned long long)HYD_RADIX * HYD_RADIX * HYD_PER_THREAD);
+    LfibPoly q;
+    lfib_power(q, table, j * unit + i);
+    for (int k = 0; k < LFIB_DEG; k++) mats[((size_t)m * LFIB_DEG + i) * LFIB_DEG + k] = q.c[k];
+}
+
+__device__ __forceinline__ void hyd_matvec(uint32_t (&w)[LFIB_DEG], const uint32_t *__restrict__ M)
+{
+    uint32_t out[LFIB_DEG];
+#pragma unroll
+    for (int i = 0; i < LFIB_DEG; i++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < LFIB_DEG; k++) v += M[i * LFIB_DEG + k] * w[k];
+        out[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < LFIB_DEG; i++) w[i] = out[i];
+}
 
 // out[v] = draw v of the plan = x[31 + v] >> 1, v < count; W[k] = x[k] is the generator's window (oldest word first)
-__global__ void __launch_bounds__(64) hyd_stream_kernel(const uint32_t *__restrict__ W, const LfibPoly *__restrict__ table, unsigned long long count,
+__global__ void __launch_bounds__(64) hyd_stream_kernel(const uint32_t *__restrict__ W, const uint32_t *__restrict__ mats, unsigned long long count,
                                                         uint32_t *__restrict__ out, const int *__restrict__ guard)
 {
     if (*guard) return;
-    const unsigned long long first = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * HYD_PER_THREAD;
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long first = t * HYD_PER_THREAD;
     if (first >= count) return;
-    uint32_t base[LFIB_DEG], r[LFIB_DEG];
-    for (int k = 0; k < LFIB_DEG; k++) base[k] = W[k];
-    lfib_window(r, base, table, first); // r[j] = x[first + j]: the 31 words in front of draw `first`
+    uint32_t r[LFIB_DEG];
+#pragma unroll
+    for (int k = 0; k < LFIB_DEG; k++) r[k] = W[k];
+    const unsigned c = (unsigned)(t % HYD_RADIX), b = (unsigned)(t / HYD_RADIX % HYD_RADIX), a = (unsigned)(t / (HYD_RADIX * HYD_RADIX));
+    if (a) hyd_matvec(r, mats + (size_t)(2 * HYD_RADIX + a) * LFIB_DEG * LFIB_DEG);
+    if (b) hyd_matvec(r, mats + (size_t)(HYD_RADIX + b) * LFIB_DEG * LFIB_DEG);
+    if (c) hyd_matvec(r, mats + (size_t)c * LFIB_DEG * LFIB_DEG);
+    // r[j] = x[first + j]: the 31 words in front of draw `first`
     for (int round = 0; round < HYD_ROUNDS; round++) {
         const unsigned long long v0 = first + (unsigned long long)round * 31;
         if (v0 >= count) break;
@@ -75,14 +114,14 @@ __global__ void __launch_bounds__(128) hyd_count_kernel(HydArgs h)
 {
     __shared__ unsigned wsum[4];
     if (*h.guard) return;
-    const int d = blockIdx.x;
+    const int r = blockIdx.x, d = r / h.nseg, t0 = (r % h.nseg) * h.seg, t1 = min(h.ntr, t0 + h.seg);
     unsigned c = 0;
-    for (int tr = threadIdx.x; tr < h.ntr; tr += blockDim.x) c += h.all[hyd_cell(h, 0, d, tr)] == 1 && (h.all[hyd_cell(h, 1, d, tr)] & 1);
+    for (int tr = t0 + threadIdx.x; tr < t1; tr += blockDim.x) c += h.all[hyd_cell(h, 0, d, tr)] == 1 && (h.all[hyd_cell(h, 1, d, tr)] & 1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
     __syncthreads();
-    if (threadIdx.x == 0) h.rowcount[d] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+    if (threadIdx.x == 0) h.rowcount[r] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
 }
 
 // first draw of every row = draws consumed so far + exclusive prefix of the row counts; one CTA
@@ -90,8 +129,8 @@ __global__ void __launch_bounds__(1024) hyd_scan_kernel(HydArgs h, int event)
 {
     __shared__ unsigned long long wsum[32];
     if (*h.guard) return;
-    const int per = (h.nd + 1023) / 1024;
-    const int d0 = threadIdx.x * per, d1 = min(h.nd, d0 + per);
+    const int per = (h.nrows + 1023) / 1024;
+    const int d0 = threadIdx.x * per, d1 = min(h.nrows, d0 + per);
     unsigned long long s = 0;
     for (int d = d0; d < d1; d++) s += h.rowcount[d];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,13 +166,14 @@ __global__ void __launch_bounds__(1024) hyd_scan_kernel(HydArgs h, int event)
 }
 
 // one event, one dimer row, one warp: the trajectories in order (ballot prefix = position in the stream)
-__device__ __forceinline__ void hyd_apply_row(const HydArgs &h, int d, unsigned long long pos, uint8_t *__restrict__ slot, int lane)
+__device__ __forceinline__ void hyd_apply_row(const HydArgs &h, int r, unsigned long long pos, uint8_t *__restrict__ slot, int lane)
 {
     const unsigned lt = (1u << lane) - 1u;
     const int own_lo = h.shard * h.ntr_l;
-    for (int t0 = 0; t0 < h.ntr; t0 += 32) {
+    const int d = r / h.nseg, s0 = (r % h.nseg) * h.seg, s1 = min(h.ntr, s0 + h.seg);
+    for (int t0 = s0; t0 < s1; t0 += 32) {
         const int tr = t0 + lane;
-        const bool in = tr < h.ntr;
+        const bool in = tr < s1;
         const size_t cg = in ? hyd_cell(h, 0, d, tr) : 0;
         uint8_t g = in ? h.all[cg] : (uint8_t)2;
         const uint8_t s = in ? h.all[hyd_cell(h, 1, d, tr)] : (uint8_t)0;
@@ -161,9 +201,9 @@ __global__ void __launch_bounds__(128) hyd_apply_kernel(HydArgs h, uint8_t *__re
 {
     if (*h.guard) return;
     const int lane = threadIdx.x & 31;
-    const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (d >= h.nd) return;
-    hyd_apply_row(h, d, h.rowstart[d], slot, lane);
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= h.nrows) return;
+    hyd_apply_row(h, r, h.rowstart[r], slot, lane);
 }
 
 // The whole plan in ONE launch of ONE CTA (ensembles up to ~1 M dimer-trajectory cells: the per-event kernels above are
@@ -187,18 +227,19 @@ __global__ void __launch_bounds__(1024) hyd_plan_fused_kernel(HydArgs h, int n_e
     }
     __syncthreads();
     unsigned long long cursor = 0;
-    const int per = (h.nd + 1023) / 1024;
+    const int per = (h.nrows + 1023) / 1024;
     for (int k = 0; k < n_events; k++) {
-        for (int d = warp; d < h.nd; d += 32) { // draws of this event per row
+        for (int r = warp; r < h.nrows; r += 32) { // draws of this event per row segment
+            const int d = r / h.nseg, t0 = (r % h.nseg) * h.seg, t1 = min(h.ntr, t0 + h.seg);
             unsigned c = 0;
-            for (int tr = lane; tr < h.ntr; tr += 32) c += h.all[hyd_cell(h, 0, d, tr)] == 1 && (h.all[hyd_cell(h, 1, d, tr)] & 1);
+            for (int tr = t0 + lane; tr < t1; tr += 32) c += h.all[hyd_cell(h, 0, d, tr)] == 1 && (h.all[hyd_cell(h, 1, d, tr)] & 1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) s_row[d] = c;
+            if (lane == 0) s_row[r] = c;
         }
         __syncthreads();
         { // exclusive prefix over the rows
-            const int d0 = tid * per, d1 = min(h.nd, d0 + per);
+            const int d0 = tid * per, d1 = min(h.nrows, d0 + per);
             unsigned sum = 0;
             for (int d = d0; d < d1; d++) sum += s_row[d];
             unsigned inc = sum;
@@ -229,7 +270,7 @@ __global__ void __launch_bounds__(1024) hyd_plan_fused_kernel(HydArgs h, int n_e
             }
         }
         __syncthreads();
-        for (int d = warp; d < h.nd; d += 32) hyd_apply_row(h, d, cursor + s_row[d], slots + (size_t)k * h.ntr_l * h.N, lane);
+        for (int r = warp; r < h.nrows; r += 32) hyd_apply_row(h, r, cursor + s_row[r], slots + (size_t)k * h.ntr_l * h.N, lane);
         if (tid == 0) h.event_start[k] = cursor;
         cursor += s_total;
         __syncthreads();
@@ -237,11 +278,19 @@ __global__ void __launch_bounds__(1024) hyd_plan_fused_kernel(HydArgs h, int n_e
     if (tid == 0) h.cursor[0] = cursor;
 }
 
-cudaError_t launch_hyd_stream(const uint32_t *W, const void *table, unsigned long long count, uint32_t *out, const int *guard, cudaStream_t st)
+// jump matrices of the stream kernel: (2 * HYD_RADIX + HYD_TOP) x 31 x 31 words, computed on the device
+size_t hyd_matrices_bytes() { return (size_t)(2 * HYD_RADIX + HYD_TOP) * LFIB_DEG * LFIB_DEG * sizeof(uint32_t); }
+unsigned long long hyd_stream_capacity() { return (unsigned long long)HYD_TOP * HYD_RADIX * HYD_RADIX * HYD_PER_THREAD; }
+cudaError_t launch_hyd_matrices(const void *table, void *mats, cudaStream_t st)
+{
+    hyd_matrices_kernel<<<2 * HYD_RADIX + HYD_TOP, 32, 0, st>>>(reinterpret_cast<const LfibPoly *>(table), reinterpret_cast<uint32_t *>(mats));
+    return cudaGetLastError();
+}
+cudaError_t launch_hyd_stream(const uint32_t *W, const void *mats, unsigned long long count, uint32_t *out, const int *guard, cudaStream_t st)
 {
     const unsigned long long threads = (count + HYD_PER_THREAD - 1) / HYD_PER_THREAD;
     if (threads == 0) return cudaSuccess;
-    hyd_stream_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(W, reinterpret_cast<const LfibPoly *>(table), count, out, guard);
+    hyd_stream_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(W, reinterpret_cast<const uint32_t *>(mats), count, out, guard);
     return cudaGetLastError();
 }
 
@@ -262,8 +311,8 @@ cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, bool
     const size_t cells = (size_t)h.nd * h.ntr;
     // (one CTA is latency-bound on its dependent loads: 1.3 ms per plan at 260 x 256 against 0.18 ms for the per-event
     // launches below; kept for very small ensembles, where the launches dominate)
-    if (!prepared && h.shards == 1 && cells <= 4096 && h.nd <= 8192 && !getenv("MADDY_HYD_PER_EVENT_KERNELS")) {
-        hyd_plan_fused_kernel<<<1, 1024, (size_t)h.nd * sizeof(unsigned), st>>>(h, n_events, slots);
+    if (!prepared && h.shards == 1 && cells <= 4096 && h.nrows <= 8192 && !getenv("MADDY_HYD_PER_EVENT_KERNELS")) {
+        hyd_plan_fused_kernel<<<1, 1024, (size_t)h.nrows * sizeof(unsigned), st>>>(h, n_events, slots);
         return cudaGetLastError();
     }
     if (!prepared) {
@@ -271,9 +320,9 @@ cudaError_t launch_hyd_plan(const HydArgs &h, int n_events, uint8_t *slots, bool
         if (e != cudaSuccess) return e;
     }
     for (int k = 0; k < n_events; k++) {
-        hyd_count_kernel<<<h.nd, 128, 0, st>>>(h);
+        hyd_count_kernel<<<h.nrows, 128, 0, st>>>(h);
         hyd_scan_kernel<<<1, 1024, 0, st>>>(h, k);
-        hyd_apply_kernel<<<(h.nd + 3) / 4, 128, 0, st>>>(h, slots + (size_t)k * h.ntr_l * h.N);
+        hyd_apply_kernel<<<(h.nrows + 3) / 4, 128, 0, st>>>(h, slots + (size_t)k * h.ntr_l * h.N);
     }
     return cudaGetLastError();
 }

@@ -236,7 +236,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
         const float amp = p.ljscale * p.ljsigma6;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         const int ncnt = near.ok ? (int)near.cnt[i] : MD_NEAR_FULL;
-        if (ncnt != MD_NEAR_FULL) {
+        if (ncnt < MD_NEAR_FULL_EXACT) {
             // shared-memory near list: the listed pairs that can be inside the 6-nm cut-off (see MD_NEAR_R2)
             // An entry outside the force cut-off (or not LJ-listed) gets the coefficient 0, which leaves the accumulators
             // bit-for-bit unchanged, so the loop body has no branch.  A pair inside the +-1e-6 band around the exact
@@ -298,7 +298,7 @@ __device__ __forceinline__ G6 monomer_force(const KArgs &k, const S &s, const Ne
         } else {
             const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
             int n = a.ljcnt[(size_t)traj * a.Npad + i];
-            if (near.stale_lj) {
+            if (near.stale_lj && ncnt != MD_NEAR_FULL_EXACT) { // (an escalated monomer's row was written out when it was escalated)
                 const int nnc = a.ncandcnt[(size_t)traj * a.Npad + i];
                 const bool all = nnc == MD_NEAR_FULL;
                 lj = all ? a.cand + (size_t)traj * MD_CAND_CAPACITY * a.Npad + i : a.ncand + (size_t)traj * MD_NCAND_CAPACITY * a.Npad + i;
@@ -1197,6 +1197,7 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
 
     int near_state = 0; // 0: not built, 1: valid, 2: overflowed (full list until the next rebuild)
     float gx[MPT], gy[MPT], gz[MPT]; // positions when the near list was formed (displacement guard)
+    unsigned esc = 0;                 // bit t: monomer t tripped the guard and was escalated (no further watching until the next formation)
 #pragma unroll
     for (int t = 0; t < MPT; t++) gx[t] = gy[t] = gz[t] = 0.f;
     const unsigned rops = (p.lj_on ? OP_REBUILD_LJ : 0u) | (p.is_assembly ? OP_REBUILD_BONDS : 0u);
@@ -1255,17 +1256,17 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
             }
             fixed_flags_dirty--;
         }
-        bool moved = false;
+        unsigned moved = 0; // bit t: monomer t of this thread has left its guard sphere (and has not been escalated yet)
         Frame fr[MPT];
 #pragma unroll
         for (int t = 0; t < MPT; t++) {
             if (idx[t] < N) {
                 fr[t] = publish(s, idx[t], mo[t], ls);
                 const float dx = mo[t].x - gx[t], dy = mo[t].y - gy[t], dz = mo[t].z - gz[t];
-                moved |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_NEAR_GUARD2;
+                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > MD_NEAR_GUARD2 && !(esc & (1u << t))) moved |= 1u << t;
             }
         }
-        const bool any_moved = __syncthreads_or(moved && near_state == 1) != 0;
+        const bool any_moved = __syncthreads_or(moved != 0 && near_state == 1) != 0;
         const bool update_now = to_update == 0;
         to_update = update_now ? freq - 1 : to_update - 1;
         const bool do_rebuild = rops != 0 && update_now && !(step == k.first_step && (k.run_flags & MADDY_RUN_SKIP_FIRST_REBUILD));
@@ -1285,7 +1286,36 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
                 for (int t = 0; t < MPT; t++)
                     if (idx[t] < N) near.topo[idx[t]] = load_topo(a, traj, idx[t]);
             }
-        } else if (near.cap > 0 && p.lj_on && (near_state == 0 || any_moved)) {
+        } else if (near.cap > 0 && p.lj_on && near_state == 1 && any_moved) {
+            // Displacement guard tripped: only pairs of the monomers that left their guard sphere can be missing from a
+            // near row.  Each of them - and every partner in its Verlet row - is ESCALATED to walking its exact Verlet row
+            // (written out first where the list is lazy) until the next list-update step; everybody else keeps the near row,
+            // whose pairs are still covered by their own guards.  A monomer that tripped needs no further watching (all its
+            // listed pairs are exact now).  Same forces as a whole-trajectory refresh, at the cost of ~50 monomers instead
+            // of the trajectory - free dimers that the reference's insertion rule drops onto one another trip at every step.
+            if (stale) __syncthreads(); // rpos of the whole trajectory is in place
+#pragma unroll
+            for (int t = 0; t < MPT; t++) {
+                if (!(moved & (1u << t))) continue;
+                const int i = idx[t];
+                esc |= 1u << t;
+                if (stale) materialise_row(k, traj, i);
+                const uint16_t *lj = a.lj + (size_t)traj * MADDY_LJ_CAPACITY * a.Npad + i;
+                const int n = a.ljcnt[(size_t)traj * a.Npad + i];
+                for (int kk = 0; kk < n; kk++) near.cnt[lj[(size_t)kk * a.Npad]] = MD_NEAR_PENDING;
+                near.cnt[i] = MD_NEAR_FULL_EXACT;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int t = 0; t < MPT; t++) {
+                const int i = idx[t];
+                if (i < N && near.cnt[i] == MD_NEAR_PENDING) {
+                    if (stale) materialise_row(k, traj, i);
+                    near.cnt[i] = MD_NEAR_FULL_EXACT;
+                }
+            }
+            if (threadIdx.x == 0) atomicAdd(a.stats + 0, 1ull);
+        } else if (near.cap > 0 && p.lj_on && near_state == 0) {
             if (stale) { // the refresh below reads the Verlet list: write it out now and stay exact for the rest of the launch
                 __syncthreads(); // rpos of the whole trajectory is in place
 #pragma unroll
@@ -1298,10 +1328,10 @@ __global__ void __launch_bounds__(MD_RUN_THREADS, MINB) run_kernel(const __grid_
             if (refresh_near<MPT>(k, s, near, traj, mo, idx)) atomicAdd(a.stats + 3, 1ull);
             __syncthreads();
             near_state = 1;
-            if (threadIdx.x == 0 && any_moved) atomicAdd(a.stats + 0, 1ull);
             formed = true;
         }
         if (formed) {
+            esc = 0;
 #pragma unroll
             for (int t = 0; t < MPT; t++) {
                 gx[t] = mo[t].x;

@@ -101,6 +101,8 @@ struct DevSys {
 #define MD_NCAND_CAPACITY 64
 #define MD_NCAND_R2 72.25f // (MD_NEAR_R + MD_CAND_SKIN)^2 = 8.5^2
 #define MD_NEAR_FULL 255 // near.cnt value of a monomer whose near list overflowed: it walks its full Verlet list instead
+#define MD_NEAR_FULL_EXACT 254 // ... of a monomer escalated by the displacement guard: it walks its EXACT Verlet row (materialised if the list was lazy)
+#define MD_NEAR_PENDING 253    // ... marked for escalation by a partner that tripped the guard in this step
 #define MD_FILTER_BATCH 8 // candidate indices fetched per round trip in filter_candidates
 
 // Per-run constants evaluated ONCE on the device (consts_kernel) with the same fast-math float expressions the
@@ -150,8 +152,9 @@ struct HydArgs {
     uint8_t *own;                            // [2][nd][ntr_l] this shard's transposed inputs: GTP state, then static mask (hyd_prepare_kernel)
     uint8_t *all;                            // [shards][2][nd][ntr_l] the inputs of EVERY shard (== own for one shard); the plan works on this copy
     int ntr_l, shards, shard;                // trajectories per shard, number of shards, this shard: ntr = shards * ntr_l is the GLOBAL count
-    unsigned *rowcount;                      // [nd] draws of the current event per dimer row
-    unsigned long long *rowstart;            // [nd] index of each row's first draw in the plan's stream
+    int seg, nseg, nrows;                    // a dimer row is cut into nseg segments of seg trajectories: nrows = nd * nseg units of work (one warp each)
+    unsigned *rowcount;                      // [nrows] draws of the current event per row segment
+    unsigned long long *rowstart;            // [nrows] index of each segment's first draw in the plan's stream
     unsigned long long *cursor;              // [1] draws consumed so far by the plan
     unsigned long long *event_start;         // [n_events] first draw of every event
     const uint32_t *stream;                  // the plan's draws (rand() values), stream_count of them

@@ -298,3 +298,38 @@ def test_loop_takes_over_on_the_host_when_the_device_cannot_decide(case, rundir,
     for x, y in zip(a[:4], b[:4]):
         assert np.array_equal(x, y)
     assert all(np.array_equal(x, y) and x.shape[0] == 4 for x, y in zip(a[4], b[4])) and a[5] == b[5] and a[6] == b[6]
+
+
+def test_guard_escalation_equals_step_granular_path(rundir, load_system):
+    """Dimers dropped next to one another (the reference's insertion rule does that) fly apart and trip the near-list
+    displacement guard step after step: the fused loop escalates them and their listed partners to their exact Verlet rows
+    instead of refreshing the whole trajectory - bitwise the step-granular path (full list walk), lists included."""
+    s = load_system(rundir("mt120_constconc", runnum=5, steps=400), ["hydrolysis=no"])
+    N = s.Ntot
+    a, b = Engine(s), Engine(s)
+    extra = np.array(s.extra).reshape(s.Ntr, N)
+    idx, rec = [], []
+    for t in (0, 2, 3):
+        free = np.flatnonzero(extra[t])[::2][:3]
+        for q, (x, y, z) in zip(free, ((10.0, 12.0, 100.0), (10.5, 12.3, 100.2), (30.0, -6.0, 60.0))):
+            idx.append(t * N + int(q))
+            rec.append((x, y, z, z + 4.0))
+    for eng in (a, b):
+        eng.run(0, 20)
+        eng.rebuild_lj()
+        eng.rebuild_bonds()
+        eng.insert_dimers(idx, rec)
+        eng.list_stats(reset=True)
+    a.run(20, 180, skip_first_rebuild=True)
+    for step in range(20, 200):
+        if step % 20 == 0 and step != 20:
+            b.rebuild_lj()
+            b.rebuild_bonds()
+        b.force()
+        b.integrate()
+    assert a.list_stats()["near_refresh"] > 0  # the guard did trip
+    assert np.isfinite(a.coords()).all()
+    assert np.array_equal(a.coords(), b.coords()) and np.array_equal(a.rng_state(), b.rng_state())
+    for kind in (capi.LIST_LJ, capi.LIST_LONGITUDINAL, capi.LIST_LATERAL):
+        (ca, ea), (cb, eb) = a.download_list(kind), b.download_list(kind)
+        assert np.array_equal(ca, cb) and np.array_equal(ea, eb)
