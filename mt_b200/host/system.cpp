@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <sys/resource.h>
+#include <thread>
 #include "mt_host.hpp"
 
 namespace mt {
@@ -451,23 +453,48 @@ class AppendFiles {
         open_.clear();
     }
 
+    // Handles kept open: all the process may have (the soft descriptor limit is raised to the hard one once), minus a
+    // reserve for everything else.  2 files per trajectory: an ensemble of 2048 needs 4096.
+    static size_t max_open()
+    {
+        static const size_t k = [] {
+            struct rlimit rl;
+            if (getrlimit(RLIMIT_NOFILE, &rl) != 0) return (size_t)768;
+            if (rl.rlim_cur < rl.rlim_max) {
+                struct rlimit want = rl;
+                want.rlim_cur = rl.rlim_max == RLIM_INFINITY ? 65536 : (rl.rlim_max > 65536 ? 65536 : rl.rlim_max);
+                if (want.rlim_cur > rl.rlim_cur && setrlimit(RLIMIT_NOFILE, &want) == 0) rl = want;
+            }
+            const size_t cur = rl.rlim_cur == RLIM_INFINITY ? 65536 : (size_t)rl.rlim_cur;
+            return cur > 512 ? cur - 256 : cur / 2;
+        }();
+        return k;
+    }
+    size_t kMaxOpen = 768; // per partition (see FramePartitions)
+
   private:
-    static constexpr size_t kMaxOpen = 768;
     std::map<std::string, FILE *> open_;
     FILE *transient_ = nullptr;
+};
+// The per-trajectory files of an ensemble, partitioned over a few writer threads (trajectory t belongs to partition
+// t % parts): one host driving eight GPUs appends 4096 frames per stride, which one thread does not keep up with.
+struct FramePartitions {
+    std::vector<AppendFiles> part;
+    explicit FramePartitions(int n) : part(n)
+    {
+        for (AppendFiles &f : part) f.kMaxOpen = AppendFiles::max_open() / (size_t)n;
+    }
 };
 
 // one frame per trajectory appended to <dcd_xyz> (x,y,z) and <dcd_ang> (fi,psi,theta); each frame is assembled in
 // memory and written with a single fwrite (the reference does open / 9 small fwrites / close per file)
-static void write_dcd_frames(const std::vector<float> &r, int N, int Ntr, const std::vector<std::string> &xyz,
-                             const std::vector<std::string> &ang, AppendFiles *files = nullptr)
+static void write_dcd_frames_part(const std::vector<float> &r, int N, int Ntr, const std::vector<std::string> &xyz,
+                                  const std::vector<std::string> &ang, AppendFiles *files, int first, int step)
 {
-    AppendFiles local;
-    if (!files) files = &local;
     const size_t frame_bytes = 3 * ((size_t)N * 4 + 8);
     std::vector<char> buf(frame_bytes);
     const int len = N * 4;
-    for (int t = 0; t < Ntr; t++) {
+    for (int t = first; t < Ntr; t += step) {
         for (int pass = 0; pass < 2; pass++) {
             static const int col[2][3] = {{0, 1, 2}, {3, 5, 4}};
             char *o = buf.data();
@@ -485,16 +512,73 @@ static void write_dcd_frames(const std::vector<float> &r, int N, int Ntr, const 
         }
     }
 }
+static void write_dcd_frames(const std::vector<float> &r, int N, int Ntr, const std::vector<std::string> &xyz,
+                             const std::vector<std::string> &ang, FramePartitions *files = nullptr)
+{
+    if (!files) {
+        AppendFiles local;
+        write_dcd_frames_part(r, N, Ntr, xyz, ang, &local, 0, 1);
+        return;
+    }
+    const int P = (int)files->part.size();
+    if (P == 1) {
+        write_dcd_frames_part(r, N, Ntr, xyz, ang, &files->part[0], 0, 1);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<std::string> err(P);
+    for (int p = 0; p < P; p++)
+        th.emplace_back([&, p] {
+            try {
+                write_dcd_frames_part(r, N, Ntr, xyz, ang, &files->part[p], p, P);
+            } catch (const std::exception &e) {
+                err[p] = e.what();
+            }
+        });
+    for (std::thread &t : th) t.join();
+    for (const std::string &e : err)
+        if (!e.empty()) die("%s", e.c_str());
+}
 
 void save_coord_dcd(System &s)
 {
     if (s.writer) {
-        auto snap = std::make_shared<std::vector<float>>(s.r);
+        // snapshot for the writer thread: buffers are recycled (a fresh 30 MB vector per stride is mostly page faults at
+        // 2048 trajectories) and filled by a few threads
+        static thread_local std::vector<std::shared_ptr<std::vector<float>>> pool;
+        std::shared_ptr<std::vector<float>> snap;
+        for (auto &b : pool)
+            if (b.use_count() == 1 && b->size() == s.r.size()) {
+                snap = b;
+                break;
+            }
+        if (!snap) {
+            snap = std::make_shared<std::vector<float>>(s.r.size());
+            if (pool.size() >= 4) pool.erase(pool.begin());
+            pool.push_back(snap);
+        }
+        {
+            const size_t bytes = s.r.size() * sizeof(float), chunk = (size_t)1 << 20, nchunk = (bytes + chunk - 1) / chunk;
+            const char *src = reinterpret_cast<const char *>(s.r.data());
+            char *dst = reinterpret_cast<char *>(snap->data());
+            int nt = (int)(std::thread::hardware_concurrency() / 4);
+            nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+#pragma omp parallel for schedule(static) num_threads(nt) if (bytes > ((size_t)8 << 20))
+            for (long long c = 0; c < (long long)nchunk; c++) {
+                const size_t o = (size_t)c * chunk;
+                memcpy(dst + o, src + o, bytes - o < chunk ? bytes - o : chunk);
+            }
+        }
         const int N = s.par.n_tot, Ntr = s.par.n_tr;
         const HostParams *hp = &s.hp;
-        auto files = std::static_pointer_cast<AppendFiles>(s.writer_files);
+        auto files = std::static_pointer_cast<FramePartitions>(s.writer_files);
         if (!files) {
-            files = std::make_shared<AppendFiles>();
+            // writer threads: one per ~512 trajectories, at most 8 (and never more than half the hardware threads)
+            int parts = (Ntr + 511) / 512;
+            const int hw = (int)std::thread::hardware_concurrency() / 2;
+            parts = parts > 8 ? 8 : parts;
+            parts = parts > hw ? (hw < 1 ? 1 : hw) : parts;
+            files = std::make_shared<FramePartitions>(parts);
             s.writer_files = files;
         }
         s.writer->submit([snap, N, Ntr, hp, files] { write_dcd_frames(*snap, N, Ntr, hp->dcd_xyz, hp->dcd_ang, files.get()); });

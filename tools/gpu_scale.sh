@@ -7,7 +7,7 @@ O=gpurun_out
 mkdir -p $O
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 $RUN bench.py --gpus $N --steps 20 --warmup 5 > $O/${TAG}_scale_own_n$N.json 2> $O/${TAG}_scale_own_n$N.err
-$RUN bench.py --impl reference --gpus $N --steps 20 --warmup 5 > $O/${TAG}_scale_ref_n$N.json 2> $O/${TAG}_scale_ref_n$N.err
+[ -z "$SKIP_REF" ] && $RUN bench.py --impl reference --gpus $N --steps 20 --warmup 5 > $O/${TAG}_scale_ref_n$N.json 2> $O/${TAG}_scale_ref_n$N.err
 python tools/one_host_probe.py $N 256 20000 4 > $O/${TAG}_one_host_n$N.log 2>&1
 python - <<PY
 import json
