@@ -367,6 +367,12 @@ def run_own(args):
         est = max(t_warm / warm * K * 1e-3, 1e-6)  # seconds per repetition
         reps = int(min(61, max(1, math.ceil(args.min_timed_s / est))))
         reps += 1 - reps % 2
+        if world > 1:
+            # every rank must issue the SAME number of strides: the sharded hydrolysis plan all-gathers inside a stride, and a
+            # rank that stopped early would leave the others waiting (each rank's estimate comes from its own warm-up time)
+            rt = torch.tensor([reps], dtype=torch.int64, device="cuda")
+            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+            reps = int(rt.item())
         launches0 = eng.launches
         if world > 1:
             dist.barrier()
