@@ -95,3 +95,27 @@ def test_consecutive_hydrolysis_events_continue_the_libc_stream(rundir, load_sys
         snaps.append(exp.copy())
     assert np.array_equal(first, snaps[0]) and np.array_equal(second, snaps[1])
     assert (second == 0).sum() > (first == 0).sum() > 0
+
+
+def test_rand_jump_ahead_matches_libc(rundir, load_system):
+    """maddy_rand_discard / HostRand::discard (polynomial jump-ahead of glibc's TYPE_3 generator, maddy_lfib.h): the window
+    after n draws is the one libc reaches by drawing, for small, block-sized and large n; the documented next-draw formula."""
+    import ctypes as C
+    from mt_b200 import capi
+    s = load_system(rundir(runnum=1))
+    for seed, n in ((1, 1), (1234567, 2), (7, 30), (7, 31), (7, 32), (99, 124), (99, 248 * 32 + 5), (4242, 1_000_003)):
+        s.srand(seed)
+        libc.srand(seed)
+        w = s.rand_window()
+        assert ((int(w[0]) + int(w[28])) & 0xFFFFFFFF) >> 1 == libc.rand()  # the next draw is (w[0] + w[28]) >> 1
+        libc.srand(seed)
+        s.rand_discard(n)
+        for _ in range(n):
+            libc.rand()
+        assert [s.rand_next() for _ in range(64)] == [libc.rand() for _ in range(64)], (seed, n)
+        # the C-ABI entry on a raw window
+        s.srand(seed)
+        w = s.rand_window().copy()
+        capi.lib.maddy_rand_discard(w.ctypes.data_as(C.POINTER(C.c_uint)), n)
+        s.rand_discard(n)
+        assert np.array_equal(w, s.rand_window())
