@@ -60,8 +60,8 @@ UNIT = "monomer-steps/s"
 B_ALG = {"lattice": 352.0, "free": 220.0}
 B_ALG_TERMS = "64 state r/w + 64 RNG r/w + 4*(n_LJ+1) LJ list + 4*(n_bonded+3) bond lists + 8 flags"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (a 100-step fused window at 520 x 256) from the
-# `ncu --set full` capture summarised in profiles/r1_run_kernel_ncu_full.txt (32.8 MB read + 0.13 MB written)
-NCU_TRAFFIC_PER_LAUNCH = {("mt40_ensemble", 256): (32.9e6, 100)}
+# `ncu --set full` capture summarised in profiles/r2_run_kernel_ncu_full.txt (32.8 MB read + 0.2 MB written)
+NCU_TRAFFIC_PER_LAUNCH = {("mt40_ensemble", 256): (33.0e6, 100)}
 REF_NTR_LIMIT = 100  # Parameters::zs[100], parameters.h:12,293
 
 
@@ -483,7 +483,7 @@ def run_own(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / pk["hbm_gbs"] if achieved else None,
                              "traffic": traffic[0] * md_per_launch / traffic[1] if traffic else None,
-                             "traffic_unit": "bytes per average launch, scaled from the ncu dram read+write of a 100-step window (profiles/r1_run_kernel_ncu_full.txt)",
+                             "traffic_unit": "bytes per average launch, scaled from the ncu dram read+write of a 100-step window (profiles/r2_run_kernel_ncu_full.txt)",
                              "algorithmic_bytes_per_launch": alg_per_launch, "avg_md_steps_per_launch": md_per_launch,
                              "avg_launch_ms": avg_launch_ms, "launches_timed": len(win_ms),
                              "window_share_of_timed_region": sum(win_ms) / max(sum(rep_ms), 1e-9),
