@@ -8,6 +8,8 @@
                              /root/reference/src when that tree is present (nvcc)
   oracle/_ref/mt_stub        the reference's own HOST (main/preparator/updater/...) with compute() replaced by
                              oracle/compute_b200_stub.cpp, linked against libmaddy_b200.so
+  oracle/_ref/ref_events_probe  the reference's host callbacks (updater.cpp: mt_length, hydrolyse, change_conc) behind a
+                             dump driver (oracle/ref_events_probe.cu); host code, makes tests/golden/ref_events.npz
   oracle/_ref/{disc,p3d22d,temp_calc}  the reference's analysis tools (scripts/), same rule (g++)
 
 Run:  python -m mt_b200.build [--force] [--no-ref]
@@ -134,6 +136,13 @@ def build_reference(force=False):
         host_only = [f for f in common if not f.endswith(".cu")]
         _run([NVCC, "-O2", "-DCUDA", "-DMORSE", "-w", f"-I{src}", f"-I{ROOT / 'include'}", "-o", REF_STUB, *[src / f for f in host_only],
               src / "main.cpp", stub_src, f"-L{PKG}", "-lmaddy_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../mt_b200"])
+    # the reference's host callbacks of the stride block (updater.cpp) behind a dump driver: runs without a GPU, makes
+    # tests/golden/ref_events.npz (tests/golden/make_events_golden.py)
+    events_src = ORACLE / "ref_events_probe.cu"
+    events_bin = REF_MT.parent / "ref_events_probe"
+    if events_src.exists() and (force or _stale(events_bin, [events_src])):
+        _run([NVCC, "-O2", "-arch=sm_100", "-rdc=true", "-DCUDA", "-DMORSE", "-w", f"-I{src}", "-o", events_bin, src / "updater.cpp",
+              src / "globals.cpp", events_src])
     probe_src = ORACLE / "ref_probe.cu"
     if probe_src.exists() and (force or _stale(REF_PROBE, [probe_src])):
         _run([NVCC, *flags, "-o", REF_PROBE, *[src / f for f in common], probe_src])
