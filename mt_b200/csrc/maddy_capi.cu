@@ -1649,6 +1649,7 @@ static int sched_reserve(maddy_handle *h, size_t bytes)
     if (bytes > h->sched_capacity) {
         CU(h, cudaStreamSynchronize(h->stream)); // a running window may still read the old buffers
         CU(h, cudaStreamSynchronize(h->copy_stream));
+        if (h->aux_stream) CU(h, cudaStreamSynchronize(h->aux_stream)); // ... and a plan may still be writing them
         const size_t cap = bytes < 4 * n ? 4 * n : bytes; // room for a few events without another resize
         for (int b = 0; b < 2; b++) {
             if (h->d_sched_buf[b]) cudaFree(h->d_sched_buf[b]);
