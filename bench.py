@@ -314,7 +314,9 @@ def run_own(args):
     torch.cuda.set_device(local)
     cpu_group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a collective that a rank never joins fails after 5 minutes instead of holding the box for the default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
         cpu_group = dist.new_group(backend="gloo")  # host-side waits that must not put a spinning kernel on a GPU
     pk, pk_src = peaks()
     ntr_local = args.ntr
