@@ -257,6 +257,13 @@ int maddy_snapshot_tubule_lengths(maddy_handle *h, int *mt_len, int *undecided);
 /* 1 when the exact on-tubule rule could be derived from this process's cosf (it then is, for every libm seen so far);
  * 0: MADDY_SNAP_ONTUBULE is refused and the caller classifies on the host. */
 int maddy_has_exact_on_tubule(const maddy_handle *h);
+/* The rule itself (host-only call, no device needed; what the classification kernel is given): with rad =
+ * sqrtf(x*x + y*y) in float and a = |theta|, a monomer is on the tubule iff rad < *rad_hi && (double)rad > 1.0 && a in
+ * [0, e0) U (e1, e2) U (e3, e4) U (e5, e6); a >= *a_max (or NaN) is undecided.  edges[MADDY_ON_TUBULE_EDGES] are the float
+ * values at which this process's `cosf(theta) > cosf(ANG_THRES)` (updater.cpp:166-168, mt.h:23-30) switches, found by
+ * bisection over the float bit patterns.  MADDY_EINVAL when no such rule could be derived. */
+#define MADDY_ON_TUBULE_EDGES 7
+int maddy_on_tubule_rule(float *rad_hi, float *a_max, float *edges);
 /* on_tubule_cur[n_tr_local * n_tot] / mt_len[n_tr_local] of the snapshot collected last by maddy_snapshot_end. */
 int maddy_snapshot_on_tubule(maddy_handle *h, int *on_tubule_cur, int *mt_len);
 int maddy_snapshot_gtp(maddy_handle *h, int *gtp);

@@ -105,7 +105,7 @@ KERNEL_SYMBOLS = [
     "maddy_analysis_protofilaments", "maddy_ensemble_stats_begin", "maddy_ensemble_stats_end", "maddy_download_tea",
     "maddy_snapshot_tubule_lengths", "maddy_snapshot_on_tubule", "maddy_insert_dimers", "maddy_has_exact_on_tubule",
     "maddy_hydrolysis_plan", "maddy_hydrolysis_result", "maddy_apply_scheduled_gtp", "maddy_rand_discard", "maddy_snapshot_gtp", "maddy_clear_guard",
-    "maddy_hydrolysis_inputs", "maddy_hydrolysis_plan_sharded", "maddy_hydrolysis_plan_all",
+    "maddy_hydrolysis_inputs", "maddy_hydrolysis_plan_sharded", "maddy_hydrolysis_plan_all", "maddy_on_tubule_rule",
 ]
 HOST_SYMBOLS = [
     "mt_host_last_error", "mt_system_load", "mt_system_free", "mt_system_params", "mt_system_topology", "mt_system_coords",
@@ -157,6 +157,7 @@ _sig(lib.maddy_snapshot_tubule_lengths, _i, [_vp, _pi, _pi])
 _sig(lib.maddy_snapshot_on_tubule, _i, [_vp, _pi, _pi])
 _sig(lib.maddy_insert_dimers, _i, [_vp, _i, _pi, _pf])
 _sig(lib.maddy_has_exact_on_tubule, _i, [_vp])
+_sig(lib.maddy_on_tubule_rule, _i, [_pf, _pf, _pf])
 _sig(lib.maddy_hydrolysis_plan, _i, [_vp, C.POINTER(C.c_uint), _ll, _ll, _i, _u])
 _sig(lib.maddy_hydrolysis_result, _i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _pi])
 _sig(lib.maddy_apply_scheduled_gtp, _i, [_vp, _ll])

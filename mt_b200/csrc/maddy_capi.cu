@@ -553,7 +553,7 @@ extern "C" int maddy_destroy(maddy_handle *h)
 }
 
 extern "C" int maddy_upload_list(maddy_handle *h, int kind, const int *counts, const int *entries);
-static bool make_ontub_rule(OnTubRule &r);
+static bool process_ontub_rule(OnTubRule &r);
 static int cls_pair_ready(maddy_handle *h);
 
 // The HybridTaus seed table of an ensemble (HybridTaus.cu:21-48): ran2 is sequential (9 ns per draw, 10 ms at 520 x 256), so
@@ -852,12 +852,7 @@ extern "C" int maddy_create(const maddy_params *par, const maddy_topology *top, 
     }
     {
         // exact on-tubule rule of this process's cosf (MADDY_SNAP_ONTUBULE): bisected once
-        static std::once_flag once;
-        static OnTubRule rule;
-        static bool rule_ok = false;
-        std::call_once(once, [] { rule_ok = make_ontub_rule(rule); });
-        h->ontub_rule = rule;
-        h->ontub_rule_ok = rule_ok;
+        h->ontub_rule_ok = process_ontub_rule(h->ontub_rule);
         if (const char *e = getenv("MADDY_ONTUB_AMAX")) { // (the cached rule was made once per process: the hook is per handle)
             const float v = (float)atof(e);
             if (v > 0.f && v < h->ontub_rule.a_max) h->ontub_rule.a_max = v;
@@ -1073,11 +1068,27 @@ static bool make_ontub_rule(OnTubRule &r)
         r.edge[k] = on_at_lo ? flt(hi) : flt(lo);
     }
     r.a_max = (float)(ONTUB_EDGES * pi); // the end of the last branch that was bisected
-    if (const char *e = getenv("MADDY_ONTUB_AMAX")) { // test hook: a small range makes "undecided" (and the host's take-over) easy to reach
-        const float v = (float)atof(e);
-        if (v > 0.f && v < r.a_max) r.a_max = v;
-    }
     return true;
+}
+// the rule of this process, made once (the MADDY_ONTUB_AMAX test hook narrows a handle's copy, never this one)
+static bool process_ontub_rule(OnTubRule &r)
+{
+    static std::once_flag once;
+    static OnTubRule rule;
+    static bool rule_ok = false;
+    std::call_once(once, [] { rule_ok = make_ontub_rule(rule); });
+    r = rule;
+    return rule_ok;
+}
+static_assert(ONTUB_EDGES == MADDY_ON_TUBULE_EDGES, "maddy_b200.h and OnTubRule disagree");
+extern "C" int maddy_on_tubule_rule(float *rad_hi, float *a_max, float *edges)
+{
+    OnTubRule r;
+    if (!process_ontub_rule(r)) return MADDY_EINVAL;
+    if (rad_hi) *rad_hi = r.rad_hi;
+    if (a_max) *a_max = r.a_max;
+    if (edges) memcpy(edges, r.edge, sizeof r.edge);
+    return MADDY_OK;
 }
 
 // the two on-tubule classification buffers; both start as the flags the handle was created with (called by maddy_create)

@@ -119,3 +119,60 @@ def test_rand_jump_ahead_matches_libc(rundir, load_system):
         capi.lib.maddy_rand_discard(w.ctypes.data_as(C.POINTER(C.c_uint)), n)
         s.rand_discard(n)
         assert np.array_equal(w, s.rand_window())
+
+
+def test_device_on_tubule_rule_equals_the_host_cosf_test(rundir, load_system):
+    """The classification kernel never calls cosf: it is given interval edges of |theta| bisected from this process's cosf
+    (maddy_on_tubule_rule, host-only).  The rule, restated in numpy exactly as ontubule_kernel evaluates it, must agree with
+    the host's mt_length() - the reference's own predicate (updater.cpp:164-170, pinned in test_events_golden.py) - on every
+    float within 300 ulps of each edge, on both signs, on random angles up to the rule's range, and at the radius limits."""
+    import ctypes as C
+    from mt_b200 import capi
+    rad_hi, a_max = C.c_float(), C.c_float()
+    edges = np.zeros(7, dtype=np.float32)
+    assert capi.lib.maddy_on_tubule_rule(C.byref(rad_hi), C.byref(a_max), edges.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    rad_hi, a_max = np.float32(rad_hi.value), np.float32(a_max.value)
+    assert rad_hi == np.float32(8.12) + np.float32(16.0) and np.all(np.diff(edges) > 0) and a_max > edges[-1]
+    # cos(theta) > cos(1): the crossings are at 1, 2 pi - 1, 2 pi + 1, 4 pi - 1, ...
+    exact = np.array([1, 2 * np.pi - 1, 2 * np.pi + 1, 4 * np.pi - 1, 4 * np.pi + 1, 6 * np.pi - 1, 6 * np.pi + 1])
+    assert np.allclose(edges, exact, rtol=1e-6)
+
+    rng = np.random.default_rng(11)
+    near = np.concatenate([(e.view(np.int32) + np.arange(-300, 301, dtype=np.int32)).view(np.float32) for e in edges.reshape(-1, 1)])
+    theta = np.concatenate([near, -near, rng.uniform(-float(a_max), float(a_max), 4000).astype(np.float32),
+                            np.array([0.0, -0.0, np.nextafter(a_max, np.float32(0))], dtype=np.float32)])
+    x = np.full(theta.shape, 8.12, dtype=np.float32)
+    y = np.zeros_like(x)
+    # radius limits: rad < rad_hi and rad > 1.0, a few ulps either side (theta = 0 there)
+    for lim in (np.float32(1.0), rad_hi):
+        r = (lim.view(np.int32) + np.arange(-40, 41, dtype=np.int32)).view(np.float32)
+        ang = rng.uniform(0, 2 * np.pi, r.size)
+        x = np.concatenate([x, (r * np.cos(ang)).astype(np.float32)])
+        y = np.concatenate([y, (r * np.sin(ang)).astype(np.float32)])
+        theta = np.concatenate([theta, np.zeros(r.size, dtype=np.float32)])
+
+    def rule(x, y, theta):  # ontubule_kernel (mt_b200/csrc/maddy_analysis.cu), float arithmetic in its order
+        rad = np.sqrt(x * x + y * y, dtype=np.float32)
+        a = np.abs(theta)
+        assert (a < a_max).all()
+        inside = a < edges[0]
+        for k in (1, 3, 5):
+            inside |= (a > edges[k]) & (a < edges[k + 1])
+        return (rad < rad_hi) & (rad.astype(np.float64) > 1.0) & inside
+
+    s = load_system(rundir(runnum=1))
+    N = s.Ntot
+    c = s.coords
+    want = rule(x, y, theta)
+    assert 0.2 < want.mean() < 0.8
+    checked = 0
+    for first in range(0, theta.size, N):
+        n = min(N, theta.size - first)
+        c[0, :, 0], c[0, :, 1], c[0, :, 4] = 8.12, 0.0, 0.0
+        c[0, :n, 0], c[0, :n, 1], c[0, :n, 4] = x[first:first + n], y[first:first + n], theta[first:first + n]
+        s.mt_length(1000)
+        got = s.on_tubule_cur[0, :n] == 1
+        bad = np.flatnonzero(got != want[first:first + n])
+        assert bad.size == 0, (first + bad[:5], theta[first + bad[:5]], x[first + bad[:5]], y[first + bad[:5]])
+        checked += n
+    assert checked == theta.size > 12000
